@@ -1,0 +1,178 @@
+/* radmmm_b200 -- C ABI of the B200-native RAD-MMM flow-decoder kernels (libradmmm_b200.so).
+ *
+ * The reference (NVIDIA/RAD-MMM) is pure Python/PyTorch and has no FFI of its own; the interface each entry point
+ * replaces is therefore a Python call site of the reference, cited per function (paths relative to the reference
+ * repository).  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - caller-allocated outputs and workspaces (query the *_bytes functions); no allocation, no synchronisation
+ *     and no global mutable state inside; work is enqueued on the `stream` argument (a cudaStream_t);
+ *   - return 0 on success, a negative code on failure; radmmm_last_error() gives a thread-local message;
+ *   - re-entrant across host threads and CUDA streams.
+ *
+ * Tensor layouts at the boundary are the reference's: fp32, (batch, channel, time) contiguous, time fastest
+ * ("channels-first", cf).  Internally the WN stack works on "rows": row r = b*pitch + t with pitch = Tp + gap
+ * zero rows between utterances, R = round_up(B*pitch, 128) rows in total (radmmm_rows()).
+ */
+#ifndef RADMMM_B200_H
+#define RADMMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RADMMM_ABI_VERSION 1
+
+/* precision of the WN contractions */
+#define RADMMM_MODE_F32 0     /* fp32 FFMA, exact-parity path                                   */
+#define RADMMM_MODE_BF16 1    /* tcgen05, bf16 operands, fp32 accumulate (throughput path)       */
+#define RADMMM_MODE_BF16X3 2  /* tcgen05, bf16 hi/lo split, 3 MMAs per product (fp32-grade parity) */
+
+/* AffineTransformationLayer.scaling_fn, common.py:1127-1141 */
+#define RADMMM_SCALE_TANH 0
+#define RADMMM_SCALE_EXP 1
+#define RADMMM_SCALE_SIGMOID 2
+#define RADMMM_SCALE_TRANSLATE 3
+
+#define RADMMM_MAX_LAYERS 8
+#define RADMMM_ROW_GAP 16     /* >= 2 * max dilation (k=5, dilation 2^i, i < 4) */
+
+int radmmm_abi_version(void);
+const char* radmmm_last_error(void);
+/* sizeof(radmmm_flow_desc) / sizeof(radmmm_flow_grads) as compiled -- lets a binding verify its struct layout */
+size_t radmmm_sizeof_flow_desc(void);
+size_t radmmm_sizeof_flow_grads(void);
+
+/* rows R for a batch of B utterances padded to Tp grouped frames */
+int radmmm_rows(int B, int Tp);
+int radmmm_pitch(int Tp);
+
+/* One flow step = Invertible 1x1 conv + WN-parameterised affine coupling.
+ * Replaces decoders.FlowStep.forward (decoders.py:72-80) -> common.Invertible1x1ConvLUS.forward (common.py:527-548) /
+ * DataInitializedInvertible1x1Conv.forward (common.py:593-617), common.AffineTransformationLayer.forward
+ * (common.py:1163-1185) and common.WN.forward (common.py:816-835) with ConvNorm/PartialConv1d (common.py:179-191,
+ * partialconv1d.py:57-94) and nn.utils.weight_norm underneath. */
+typedef struct radmmm_flow_desc {
+    int32_t mode;        /* RADMMM_MODE_* */
+    int32_t B;           /* batch */
+    int32_t C;           /* channels of this flow step (even) */
+    int32_t Tp;          /* grouped frames (time length of every cf tensor) */
+    int32_t D;           /* conditioning channels (decoder_cond_dims) */
+    int32_t H;           /* WN width (n_channels, 1024 in the reference); multiple of 128 */
+    int32_t L;           /* WN layers (n_conv_layers_per_step), dilation 2^i */
+    int32_t scaling_fn;  /* RADMMM_SCALE_* */
+    int32_t training;    /* 1: keep activations for radmmm_flow_backward */
+    int32_t reserved;
+    const int32_t* lens; /* (B) grouped lengths */
+    /* raw parameters, fp32, reference layouts (state_dict tensors) */
+    const float* start_g; const float* start_v; const float* start_b;      /* (H,1,1) (H,C/2+D,1) (H) */
+    const float* in_g[RADMMM_MAX_LAYERS]; const float* in_v[RADMMM_MAX_LAYERS]; const float* in_b[RADMMM_MAX_LAYERS];   /* (H,1,1) (H,H,5) (H) */
+    const float* rs_g[RADMMM_MAX_LAYERS]; const float* rs_v[RADMMM_MAX_LAYERS]; const float* rs_b[RADMMM_MAX_LAYERS];   /* (H,1,1) (H,H,1) (H) */
+    const float* end_w; const float* end_b;                                 /* (C,H,1) (C) */
+    /* invertible 1x1 conv: W (C,C) assembled by the caller from P,L,U (common.py:529-531) or U (common.py:598);
+     * W_inv (C,C) for the inverse pass; W_T (C,C) = W transposed for the backward pass; mean = input_mean (C) for the
+     * whitening layer or NULL.  Only the pointers a call needs have to be non-NULL. */
+    const float* W; const float* W_inv; const float* W_T; const float* mean;
+    /* prepared (weight-normed, re-laid-out) weights: radmmm_flow_prepared_bytes(), zero-initialised ONCE by the
+     * caller, filled by radmmm_flow_prepare() whenever the raw parameters changed */
+    void* prepared;
+    /* conditioning in row layout, produced once per step by radmmm_context_rows() */
+    const void* ctx_rows; const void* ctx_rows_T;
+    /* per-call activation workspace (radmmm_flow_workspace_bytes()); must outlive backward when training */
+    void* workspace;
+} radmmm_flow_desc;
+
+size_t radmmm_flow_prepared_bytes(int mode, int C, int D, int H, int L);
+size_t radmmm_flow_workspace_bytes(int mode, int training, int B, int Tp, int C, int D, int H, int L);
+size_t radmmm_flow_backward_scratch_bytes(int mode, int B, int Tp, int C, int D, int H, int L);
+size_t radmmm_context_rows_bytes(int mode, int B, int Tp, int D, int transposed);
+
+/* weight norm + layout.  Replaces the per-forward aten::_weight_norm_interface of nn.utils.weight_norm
+ * (common.py:174,791,813). */
+int radmmm_flow_prepare(const radmmm_flow_desc* d, void* stream);
+
+/* context (B, Tp, D) fp32 [the bi-LSTM output of models/radmmm.py:137-146 before its transpose] -> row layout */
+int radmmm_context_rows(int mode, const float* ctx_btd, const int32_t* lens, int B, int Tp, int D,
+                        void* rows, void* rows_T, void* stream);
+/* gradient rows (fp32 [R][Dp]) -> (B, Tp, D) fp32, accumulate != 0 adds */
+int radmmm_context_rows_backward(const float* drows, const int32_t* lens, int B, int Tp, int D, float* dctx_btd,
+                                 int accumulate, void* stream);
+
+/* forward: z_in (B,C,Tp) -> z_mid (after the 1x1 conv), params (B,C,Tp), z_out (B,C,Tp), log_s (B,C/2,Tp) */
+int radmmm_flow_forward(const radmmm_flow_desc* d, const float* z_in, float* z_mid, float* params, float* z_out,
+                        float* log_s, void* stream);
+/* inverse (decoders.py:73-76): z (B,C,Tp) -> coupling^-1 -> W_inv (+ mean) -> z_out; params is scratch (B,C,Tp) */
+int radmmm_flow_inverse(const radmmm_flow_desc* d, const float* z_in, float* params, float* z_tmp, float* z_out,
+                        void* stream);
+/* backward.  Incoming gradients are taken as zero beyond each length (RADMMMLoss masks them, loss.py:91,102).
+ * Outputs: dz_in (B,C,Tp); dctx_rows fp32 [R][Dp] (overwritten); dW (C,C); parameter gradients in the reference
+ * layouts (same shapes as the raw parameters).  dz_mid/dparams are (B,C,Tp) scratch. */
+typedef struct radmmm_flow_grads {
+    float* start_g; float* start_v; float* start_b;
+    float* in_g[RADMMM_MAX_LAYERS]; float* in_v[RADMMM_MAX_LAYERS]; float* in_b[RADMMM_MAX_LAYERS];
+    float* rs_g[RADMMM_MAX_LAYERS]; float* rs_v[RADMMM_MAX_LAYERS]; float* rs_b[RADMMM_MAX_LAYERS];
+    float* end_w; float* end_b;
+    float* W;
+} radmmm_flow_grads;
+
+int radmmm_flow_backward(const radmmm_flow_desc* d, const float* z_in, const float* z_mid, const float* params,
+                         const float* dz_out, const float* dlog_s, float* dz_mid, float* dparams, float* dz_in,
+                         float* dctx_rows, const radmmm_flow_grads* grads, void* scratch, void* stream);
+
+/* Stand-alone ops (also used by the tests) ------------------------------------------------------------- */
+
+/* Invertible 1x1 conv: out[b,co,t] = sum_ci W[co,ci]*(in[b,ci,t]-pre[ci]) + post[co]   (common.py:540-548,605-617) */
+int radmmm_inv1x1(const float* in, const float* W, const float* pre, const float* post, float* out, int B, int Cin,
+                  int Cout, int Tp, void* stream);
+int radmmm_inv1x1_wgrad(const float* dz, const float* x, const float* pre, const int32_t* lens, float* dW, int B,
+                        int C, int Tp, void* stream);
+/* affine coupling tail (common.py:1173-1185) */
+int radmmm_coupling_forward(const float* z, const float* params, float* z_out, float* log_s, int B, int C, int Tp,
+                            int scaling_fn, int inverse, void* stream);
+int radmmm_coupling_backward(const float* dz_out, const float* dlog_s, const float* z, const float* params,
+                             const int32_t* lens, float* dz, float* dparams, int B, int C, int Tp, int scaling_fn,
+                             void* stream);
+/* masked sums for compute_flow_loss (loss.py:85-110): out[0] += sum over t<len of x (square=0) or x^2 (square=1) */
+int radmmm_masked_sum(const float* x, const int32_t* lens, int B, int C, int Tp, int square, double* out, void* stream);
+int radmmm_masked_sum_backward(const float* x, const int32_t* lens, int B, int C, int Tp, int square,
+                               const float* coef, float coef_mul, float* dx, void* stream);
+
+/* Generic masked dilated conv as a row GEMM (testing / FiLM nets): y rows fp32 [R][N] = sum_taps x[r+(j-c)*d] W_j + bias.
+ * x_rows / w in the act format of `mode`; see rad-mmm_b200/csrc/gemm.cuh. */
+int radmmm_conv_rows(int mode, const void* x_rows, long long x_ld, long long x_plane, const void* w, long long w_ld,
+                     long long w_plane, long long w_tap_stride, const float* bias, float* y, long long y_ld, int R,
+                     int K, int N, int taps, int dilation, void* stream);
+/* Weight-gradient GEMM on rows (testing): out[tap][m][n] = sum_r dy[r][m] * x[r + (tap - taps/2)*dilation][n].
+ * dy / x are act-format row matrices; dyT / xT their transposed copies ([M][R] / [N][R], needed by the tensor-core
+ * modes, NULL for RADMMM_MODE_F32).  `out` (fp32, [taps][M][out_ld]) is zeroed by the call. */
+int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_plane, const void* dyT, const void* x,
+                      long long x_ld, long long x_plane, const void* xT, float* out, long long out_ld,
+                      long long out_tap_stride, int R, int M, int N, int taps, int dilation, void* stream);
+/* fp32 rows -> act-format rows of `mode` (hi/lo split for BF16X3) */
+int radmmm_cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, void* stream);
+
+/* Piecewise-quadratic spline coupling (splines.py:241-339; common.py:1040-1090) */
+int radmmm_spline_forward(const float* z1, const float* q, const int32_t* lens, float* z1_out, float* log_s, int B,
+                          int Ch, int Tp, int n_bins, float lo, float hi, int inverse, void* stream);
+int radmmm_spline_backward(const float* z1, const float* q, const int32_t* lens, const float* dz1_out,
+                           const float* dlog_s, float* dz1, float* dq, int B, int Ch, int Tp, int n_bins, float lo,
+                           float hi, void* stream);
+
+/* STFT + mel filterbank + log (audio_processing.py:137-154, 227-255): audio (B,S) in [-1,1] -> mel (B,n_mel,S/hop+1).
+ * mel_basis (n_mel, n_fft/2+1) fp32 as registered by TacotronSTFT.__init__ (audio_processing.py:124-127). */
+int radmmm_stft_mel(const float* audio, const float* mel_basis, float* mel, float* magnitude_or_null, int B, int S,
+                    int n_fft, int hop, int n_mel, float clip, void* stream);
+
+/* Soft attention (common.py:1259-1276) and the context matmul (tts_lightning_modules.py:670).
+ * q (B,Ca,T1), k (B,Ca,T2) are the projected queries/keys; prior (B,T1,T2) or NULL; in_lens (B).
+ * attn, attn_logprob: (B,1,T1,T2).  If txt_enc (B,Dt,T2) != NULL also writes context (B,Dt,T1). */
+int radmmm_soft_attention(const float* q, const float* k, const float* prior, const int32_t* in_lens, float* attn,
+                          float* attn_logprob, const float* txt_enc, float* context, int B, int Ca, int T1, int T2,
+                          int Dt, float temperature, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADMMM_B200_H */

@@ -1,0 +1,550 @@
+"""Flow-op modules with the reference's names, constructor arguments, parameter names and call signatures
+(reference: common.py of NVIDIA/RAD-MMM), backed by the sm_100a kernels in csrc/ through the C ABI.
+
+Mirrored classes (reference file:line):
+  SequenceLength                      common.py:123-128
+  Invertible1x1ConvLUS                common.py:507-548
+  DataInitializedInvertible1x1Conv    common.py:551-617
+  Invertible1x1Conv                   common.py:621-662
+  WN                                  common.py:776-835
+  AffineTransformationLayer           common.py:1093-1185
+  LengthRegulator                     common.py:208-237
+The fused flow step (1x1 conv + WN + coupling in one autograd node) lives in :class:`FlowStepFunction`; the
+standalone modules route through the same native entry points, so there is exactly one implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native as N
+
+_DEFAULT_PRECISION = os.environ.get("RADMMM_B200_PRECISION", "bf16x3")
+
+
+# --------------------------------------------------------------------------------------------- lengths / masks
+def get_mask_from_lengths(lengths: torch.Tensor, max_len: Optional[int] = None) -> torch.Tensor:
+    """common.py:105-116.  ``max_len`` (from a tensor shape) avoids the reference's ``.item()`` device sync."""
+    if max_len is None:
+        max_len = int(torch.max(lengths).item())
+    ids = torch.arange(0, max_len, device=lengths.device)
+    return ids < lengths.unsqueeze(1)
+
+
+class SequenceLength:
+    """common.py:123-128."""
+
+    def __init__(self, lengths: torch.Tensor, max_len: Optional[int] = None):
+        self.lengths = lengths.long()
+        self.mask = get_mask_from_lengths(lengths, max_len)
+
+
+def _lens_of(seq_lens, batch: int, tp: int, device) -> torch.Tensor:
+    """int32 device lengths from a SequenceLength (ours or the reference's), a tensor, or None (= full length)."""
+    if seq_lens is None:
+        return torch.full((batch,), tp, dtype=torch.int32, device=device)
+    lengths = seq_lens.lengths if hasattr(seq_lens, "lengths") else seq_lens
+    return lengths.to(device=device, dtype=torch.int32).contiguous()
+
+
+class LengthRegulator(nn.Module):
+    """common.py:208-237 without the per-token Python loops: x (B,T2,C), dur (B,T2) -> (B, max sum dur, C)."""
+
+    def forward(self, x: torch.Tensor, dur: torch.Tensor) -> torch.Tensor:
+        dur = dur.long().clamp(min=0)
+        ends = torch.cumsum(dur, dim=1)                               # (B,T2)
+        total = int(ends[:, -1].max().item())
+        frames = torch.arange(total, device=x.device)[None, :]        # (1,T)
+        idx = torch.searchsorted(ends, frames.expand(x.shape[0], -1).contiguous(), right=True)
+        valid = frames < ends[:, -1:]
+        idx = idx.clamp(max=x.shape[1] - 1)
+        out = torch.gather(x, 1, idx[..., None].expand(-1, -1, x.shape[2]))
+        return out * valid[..., None].to(x.dtype)
+
+
+# --------------------------------------------------------------------------------------------- context rows cache
+class _ContextRows:
+    """Conditioning (B, Tp, D) fp32 re-laid-out once per step into the row format the WN kernels read."""
+
+    def __init__(self, ctx_btd: torch.Tensor, lens: torch.Tensor, mode: int):
+        lib = N.lib()
+        b, tp, d = ctx_btd.shape
+        self.key = (ctx_btd.data_ptr(), ctx_btd._version, tuple(ctx_btd.shape), mode, lens.data_ptr(), lens._version)
+        self.rows = torch.empty(lib.radmmm_context_rows_bytes(mode, b, tp, d, 0), dtype=torch.uint8, device=ctx_btd.device)
+        nt = lib.radmmm_context_rows_bytes(mode, b, tp, d, 1)
+        self.rows_T = torch.empty(nt, dtype=torch.uint8, device=ctx_btd.device) if nt else None
+        N.check(lib.radmmm_context_rows(mode, N.fptr(ctx_btd), N.ptr(lens), b, tp, d, N.ptr(self.rows),
+                                        N.ptr(self.rows_T), N.stream()))
+
+
+_ctx_cache: List[_ContextRows] = []
+
+
+def _context_rows(ctx_btd: torch.Tensor, lens: torch.Tensor, mode: int) -> _ContextRows:
+    key = (ctx_btd.data_ptr(), ctx_btd._version, tuple(ctx_btd.shape), mode, lens.data_ptr(), lens._version)
+    for c in _ctx_cache:
+        if c.key == key:
+            return c
+    c = _ContextRows(ctx_btd, lens, mode)
+    _ctx_cache.append(c)
+    del _ctx_cache[:-2]
+    return c
+
+
+def _as_btd(context: torch.Tensor) -> torch.Tensor:
+    """(B, D, Tp) conditioning -> contiguous (B, Tp, D) fp32.  The decoder's context is the transpose of the
+    batch-first LSTM output (models/radmmm.py:146), so this is a zero-copy view in the hot path."""
+    x = context.transpose(1, 2)
+    return x if x.is_contiguous() else x.contiguous()
+
+
+_scratch_cache = {}
+
+
+def _backward_scratch(nbytes: int, device) -> torch.Tensor:
+    key = (device.index,)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _scratch_cache[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------------- weight-normed convs
+class _NormedConv1d(nn.Module):
+    """Parameter holder with the key layout ``nn.utils.weight_norm(nn.Conv1d(...))`` produces:
+    ``bias``, ``weight_g`` (out,1,1), ``weight_v`` (out,in,k).  ``init`` follows the reference call site."""
+
+    def __init__(self, cin: int, cout: int, ksize: int, xavier: bool):
+        super().__init__()
+        conv = nn.Conv1d(cin, cout, ksize)
+        if xavier:                                      # ConvNorm, common.py:172-173
+            nn.init.xavier_uniform_(conv.weight, gain=nn.init.calculate_gain("linear"))
+        v = conv.weight.detach()
+        self.bias = nn.Parameter(conv.bias.detach().clone())
+        self.weight_g = nn.Parameter(v.reshape(cout, -1).norm(dim=1).reshape(cout, 1, 1).clone())
+        self.weight_v = nn.Parameter(v.clone())
+
+    def gv(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.weight_g, self.weight_v
+
+
+class _ConvNormHolder(nn.Module):
+    """``ConvNorm`` keeps its conv under ``.conv`` (common.py:168-174) -> keys ``in_layers.i.conv.*``."""
+
+    def __init__(self, cin, cout, ksize):
+        super().__init__()
+        self.conv = _NormedConv1d(cin, cout, ksize, xavier=True)
+
+
+class WN(nn.Module):
+    """common.py:776-835 (softplus activation, partial padding, dilation 2^i)."""
+
+    def __init__(self, n_in_channels, n_context_dim, n_layers, n_channels, kernel_size=5,
+                 affine_activation="softplus", use_partial_padding=True, use_dilation=True):
+        super().__init__()
+        assert kernel_size % 2 == 1
+        assert n_channels % 2 == 0
+        if kernel_size != 5 or affine_activation != "softplus" or not use_partial_padding or not use_dilation:
+            raise NotImplementedError("radmmm_b200.WN builds the configuration RADMMMFlow uses: kernel_size=5, softplus, "
+                                      "partial padding, dilation 2^i")
+        self.n_layers = n_layers
+        self.n_channels = n_channels
+        self.n_in_channels = n_in_channels
+        self.n_context_dim = n_context_dim
+        self.affine_activation = affine_activation
+        self.use_partial_padding = use_partial_padding
+        self.use_dilation = use_dilation
+        self.in_layers = nn.ModuleList()
+        self.res_skip_layers = nn.ModuleList()
+        self.start = _NormedConv1d(n_in_channels + n_context_dim, n_channels, 1, xavier=False)
+        end = nn.Conv1d(n_channels, 2 * n_in_channels, 1)
+        end.weight.data.zero_()                       # common.py:799-802: couplings start as the identity
+        end.bias.data.zero_()
+        self.end = end
+        for _ in range(n_layers):
+            self.in_layers.append(_ConvNormHolder(n_channels, n_channels, kernel_size))
+            self.res_skip_layers.append(_NormedConv1d(n_channels, n_channels, 1, xavier=False))
+        self._prepared = {}        # mode -> (version key, uint8 tensor)
+
+    # -- raw parameter list in the fixed order FlowStepFunction uses
+    def raw_params(self) -> List[Optional[torch.Tensor]]:
+        out: List[Optional[torch.Tensor]] = []
+        g, v = self.start.gv()
+        out += [g, v, self.start.bias]
+        for i in range(self.n_layers):
+            g, v = self.in_layers[i].conv.gv()
+            out += [g, v, self.in_layers[i].conv.bias]
+        for i in range(self.n_layers):
+            g, v = self.res_skip_layers[i].gv()
+            out += [g, v, self.res_skip_layers[i].bias]
+        out += [self.end.weight, self.end.bias]
+        return out
+
+    def fill_desc(self, d: N.FlowDesc, params: List[Optional[torch.Tensor]]):
+        L = self.n_layers
+        d.start_g, d.start_v, d.start_b = (N.fptr(p) for p in params[0:3])
+        for i in range(L):
+            d.in_g[i], d.in_v[i], d.in_b[i] = (N.fptr(p) for p in params[3 + 3 * i: 6 + 3 * i])
+            o = 3 + 3 * L + 3 * i
+            d.rs_g[i], d.rs_v[i], d.rs_b[i] = (N.fptr(p) for p in params[o: o + 3])
+        d.end_w, d.end_b = N.fptr(params[3 + 6 * L]), N.fptr(params[4 + 6 * L])
+
+    def prepared(self, d: N.FlowDesc, params: List[Optional[torch.Tensor]]) -> torch.Tensor:
+        """Weight-normed, re-laid-out weights for ``d.mode``; recomputed only when a raw parameter changed."""
+        lib = N.lib()
+        key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+        hit = self._prepared.get(d.mode)
+        if hit is None or hit[1].device != params[1].device:
+            nbytes = lib.radmmm_flow_prepared_bytes(d.mode, d.C, d.D, d.H, d.L)
+            hit = (None, torch.zeros(nbytes, dtype=torch.uint8, device=params[1].device))
+        d.prepared = N.ptr(hit[1])
+        if hit[0] != key:
+            N.check(lib.radmmm_flow_prepare(C.byref(d), N.stream()))
+            hit = (key, hit[1])
+            self._prepared[d.mode] = hit
+        return hit[1]
+
+    def forward(self, forward_input, seq_lens=None):
+        """(z0 (B,Cin,T), context (B,D,T)) -> (B, 2*Cin, T).  Inference-only when called on its own; training goes
+        through AffineTransformationLayer / FlowStep (one fused autograd node)."""
+        z0, context = forward_input
+        if torch.is_grad_enabled() and (z0.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("radmmm_b200.WN.forward is not differentiable on its own; call it under torch.no_grad() "
+                               "or use AffineTransformationLayer / FlowStep")
+        zeros = torch.zeros_like(z0)
+        z = torch.cat((z0, zeros), 1)
+        _, _, params = _flow_apply(self, None, None, None, z, context, seq_lens, "translate", _DEFAULT_PRECISION,
+                                   want_params=True)
+        return params
+
+
+# --------------------------------------------------------------------------------------------- fused flow step
+def _make_desc(wn: WN, mode: int, batch: int, chans: int, tp: int, scaling_fn: str, training: bool,
+               lens: torch.Tensor) -> N.FlowDesc:
+    d = N.FlowDesc()
+    d.mode, d.B, d.C, d.Tp = mode, batch, chans, tp
+    d.D, d.H, d.L = wn.n_context_dim, wn.n_channels, wn.n_layers
+    d.scaling_fn = N.SCALING[scaling_fn]
+    d.training = int(training)
+    d.lens = N.ptr(lens)
+    return d
+
+
+class FlowStepFunction(torch.autograd.Function):
+    """One flow step as a single autograd node: z -> W(z - mean) -> affine coupling parameterised by WN.
+
+    forward  -> radmmm_flow_forward   (decoders.py:72-80 forward branch)
+    backward -> radmmm_flow_backward  (hand-written dgrad / wgrad chain; gradients w.r.t. z, the conditioning,
+                the 1x1 matrix and every WN parameter in the reference's (g, v, bias) parametrisation)
+    """
+
+    @staticmethod
+    def forward(ctx, wn: WN, scaling_fn: str, mode: int, z, ctx_btd, lens, W, mean, *params):
+        lib = N.lib()
+        z = z.contiguous()
+        batch, chans, tp = z.shape
+        training = any(ctx.needs_input_grad)
+        d = _make_desc(wn, mode, batch, chans, tp, scaling_fn, training, lens)
+        plist = list(params)
+        wn.fill_desc(d, plist)
+        prepared = wn.prepared(d, plist)
+        rows = _context_rows(ctx_btd, lens, mode)
+        d.ctx_rows, d.ctx_rows_T = N.ptr(rows.rows), N.ptr(rows.rows_T)
+        ws = torch.empty(lib.radmmm_flow_workspace_bytes(mode, int(training), batch, tp, chans, d.D, d.H, d.L),
+                         dtype=torch.uint8, device=z.device)
+        d.workspace = N.ptr(ws)
+        Wc = W.contiguous() if W is not None else None
+        d.W, d.mean = N.fptr(Wc), N.fptr(mean)
+        z_mid = torch.empty_like(z) if W is not None else z
+        p_out = torch.empty_like(z)
+        z_out = torch.empty_like(z)
+        log_s = torch.empty(batch, chans // 2, tp, dtype=z.dtype, device=z.device)
+        N.check(lib.radmmm_flow_forward(C.byref(d), N.fptr(z), N.fptr(z_mid), N.fptr(p_out), N.fptr(z_out),
+                                        N.fptr(log_s), N.stream()))
+        ctx.wn, ctx.scaling_fn, ctx.mode, ctx.rows, ctx.ws, ctx.prepared_buf = wn, scaling_fn, mode, rows, ws, prepared
+        ctx.has_W, ctx.has_mean = W is not None, mean is not None
+        ctx.ctx_shape = tuple(ctx_btd.shape)
+        ctx.save_for_backward(z, z_mid, p_out, lens, Wc if Wc is not None else z.new_empty(0),
+                              mean if mean is not None else z.new_empty(0), *[p for p in plist])
+        ctx.mark_non_differentiable(p_out)
+        return z_out, log_s, p_out
+
+    @staticmethod
+    def backward(ctx, dz_out, dlog_s, _dparams_unused):
+        lib = N.lib()
+        z, z_mid, p_out, lens, W, mean, *plist = ctx.saved_tensors
+        wn, mode = ctx.wn, ctx.mode
+        batch, chans, tp = z.shape
+        d = _make_desc(wn, mode, batch, chans, tp, ctx.scaling_fn, True, lens)
+        wn.fill_desc(d, plist)
+        d.prepared = N.ptr(ctx.prepared_buf)
+        d.ctx_rows, d.ctx_rows_T = N.ptr(ctx.rows.rows), N.ptr(ctx.rows.rows_T)
+        d.workspace = N.ptr(ctx.ws)
+        W_T = W.t().contiguous() if ctx.has_W else None
+        d.W, d.W_T, d.mean = (N.fptr(W) if ctx.has_W else None), N.fptr(W_T), (N.fptr(mean) if ctx.has_mean else None)
+        dz_out = dz_out.contiguous() if dz_out is not None else torch.zeros_like(z)
+        dlog_s = dlog_s.contiguous() if dlog_s is not None else None
+        grads = [torch.empty_like(p) for p in plist]
+        g = N.FlowGrads()
+        L = wn.n_layers
+        g.start_g, g.start_v, g.start_b = (N.fptr(t) for t in grads[0:3])
+        for i in range(L):
+            g.in_g[i], g.in_v[i], g.in_b[i] = (N.fptr(t) for t in grads[3 + 3 * i: 6 + 3 * i])
+            o = 3 + 3 * L + 3 * i
+            g.rs_g[i], g.rs_v[i], g.rs_b[i] = (N.fptr(t) for t in grads[o: o + 3])
+        g.end_w, g.end_b = N.fptr(grads[3 + 6 * L]), N.fptr(grads[4 + 6 * L])
+        dW = torch.empty_like(W) if ctx.has_W else None
+        g.W = N.fptr(dW)
+        dz_mid = torch.empty_like(z)
+        dparams = torch.empty_like(z)
+        dz_in = torch.empty_like(z) if ctx.has_W else dz_mid
+        R, Dp = N.rows(batch, tp), N.round_up(d.D, 128)
+        dctx_rows = torch.empty(R, Dp, dtype=torch.float32, device=z.device)
+        scratch = _backward_scratch(lib.radmmm_flow_backward_scratch_bytes(mode, batch, tp, chans, d.D, d.H, d.L), z.device)
+        N.check(lib.radmmm_flow_backward(C.byref(d), N.fptr(z), N.fptr(z_mid), N.fptr(p_out), N.fptr(dz_out),
+                                         N.fptr(dlog_s), N.fptr(dz_mid), N.fptr(dparams), N.fptr(dz_in),
+                                         N.fptr(dctx_rows), C.byref(g), N.ptr(scratch), N.stream()))
+        dctx = None
+        if ctx.needs_input_grad[4]:
+            dctx = torch.empty(ctx.ctx_shape, dtype=torch.float32, device=z.device)
+            N.check(lib.radmmm_context_rows_backward(N.fptr(dctx_rows), N.ptr(lens), batch, tp, d.D, N.fptr(dctx), 0,
+                                                     N.stream()))
+        return (None, None, None, dz_in, dctx, None, dW, None, *grads)
+
+
+def _flow_apply(wn: WN, W, W_inv, mean, z, context, seq_lens, scaling_fn: str, precision: str, inverse: bool = False,
+                want_params: bool = False):
+    """Shared driver.  ``context`` is (B, D, Tp) like the reference's ``context_w_spkvec``."""
+    if not z.is_cuda:
+        raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    mode = N.MODES[precision]
+    batch, chans, tp = z.shape
+    lens = _lens_of(seq_lens, batch, tp, z.device)
+    ctx_btd = _as_btd(context.float())
+    if ctx_btd.shape[1] != tp:
+        raise RuntimeError(f"context has {ctx_btd.shape[1]} frames, z has {tp}")
+    params = wn.raw_params()
+    if inverse:
+        lib = N.lib()
+        z = z.contiguous().float()
+        d = _make_desc(wn, mode, batch, chans, tp, scaling_fn, False, lens)
+        with torch.no_grad():
+            wn.fill_desc(d, params)
+            wn.prepared(d, params)
+            rows = _context_rows(ctx_btd, lens, mode)
+            d.ctx_rows, d.ctx_rows_T = N.ptr(rows.rows), N.ptr(rows.rows_T)
+            ws = torch.empty(lib.radmmm_flow_workspace_bytes(mode, 0, batch, tp, chans, d.D, d.H, d.L),
+                             dtype=torch.uint8, device=z.device)
+            d.workspace = N.ptr(ws)
+            if W_inv is None:
+                W_inv = torch.eye(chans, device=z.device)
+            W_inv = W_inv.contiguous()
+            d.W_inv, d.mean = N.fptr(W_inv), N.fptr(mean)
+            p_out, z_tmp, z_out = torch.empty_like(z), torch.empty_like(z), torch.empty_like(z)
+            N.check(lib.radmmm_flow_inverse(C.byref(d), N.fptr(z), N.fptr(p_out), N.fptr(z_tmp), N.fptr(z_out),
+                                            N.stream()))
+        return z_out
+    return FlowStepFunction.apply(wn, scaling_fn, mode, z.float(), ctx_btd, lens, W, mean, *params)
+
+
+class AffineTransformationLayer(nn.Module):
+    """common.py:1093-1185 for ``affine_model='wavenet'`` (the only model RADMMMFlow builds, decoders.py:63-66)."""
+
+    def __init__(self, n_mel_channels, n_context_dim, n_layers, affine_model="simple_conv", with_dilation=True,
+                 kernel_size=5, scaling_fn="exp", affine_activation="softplus", n_channels=1024,
+                 use_partial_padding=False):
+        super().__init__()
+        if affine_model not in ("wavenet", "simple_conv", "film_stack"):
+            raise Exception("{} affine model not supported".format(affine_model))
+        if isinstance(scaling_fn, list) or scaling_fn not in ("translate", "exp", "tanh", "sigmoid"):
+            if isinstance(scaling_fn, list):
+                raise NotImplementedError("per-channel scaling_fn lists are not built in radmmm_b200")
+            raise Exception("{} scaling fn not supported".format(scaling_fn))
+        if affine_model != "wavenet":
+            raise NotImplementedError("radmmm_b200 builds affine_model='wavenet' (what RADMMMFlow instantiates)")
+        self.affine_model = affine_model
+        self.scaling_fn = scaling_fn
+        self.affine_param_predictor = WN(int(n_mel_channels / 2), n_context_dim, n_layers=n_layers,
+                                         n_channels=n_channels, affine_activation=affine_activation,
+                                         use_partial_padding=use_partial_padding)
+        self.n_mel_channels = n_mel_channels
+        self.precision = _DEFAULT_PRECISION
+
+    def forward(self, z, context, inverse=False, seq_lens=None):
+        if inverse:
+            return _flow_apply(self.affine_param_predictor, None, None, None, z, context, seq_lens, self.scaling_fn,
+                               self.precision, inverse=True)
+        z_out, log_s, _ = _flow_apply(self.affine_param_predictor, None, None, None, z, context, seq_lens,
+                                      self.scaling_fn, self.precision)
+        return z_out, log_s
+
+
+# --------------------------------------------------------------------------------------------- invertible 1x1 convs
+class _Inv1x1Function(torch.autograd.Function):
+    """out = W (z - pre) + post on (B, C, T);  common.py:540-548 / 605-617."""
+
+    @staticmethod
+    def forward(ctx, z, W, pre, post, lens):
+        lib = N.lib()
+        z = z.contiguous().float()
+        W = W.contiguous().float()
+        b, c, t = z.shape
+        out = torch.empty(b, W.shape[0], t, dtype=torch.float32, device=z.device)
+        N.check(lib.radmmm_inv1x1(N.fptr(z), N.fptr(W), N.fptr(pre), N.fptr(post), N.fptr(out), b, c, W.shape[0], t,
+                                  N.stream()))
+        ctx.save_for_backward(z, W, pre if pre is not None else z.new_empty(0), lens)
+        ctx.has_pre = pre is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = N.lib()
+        z, W, pre, lens = ctx.saved_tensors
+        b, c, t = z.shape
+        dout = dout.contiguous()
+        dz = torch.empty_like(z)
+        Wt = W.t().contiguous()
+        N.check(lib.radmmm_inv1x1(N.fptr(dout), N.fptr(Wt), None, None, N.fptr(dz), b, W.shape[0], c, t, N.stream()))
+        dW = torch.empty_like(W)
+        N.check(lib.radmmm_inv1x1_wgrad(N.fptr(dout), N.fptr(z), N.fptr(pre) if ctx.has_pre else None, N.ptr(lens),
+                                        N.fptr(dW), b, c, t, N.stream()))
+        return dz, dW, None, None, None
+
+
+class _InvertibleBase(nn.Module):
+    cache_inverse: bool
+
+    def _weight(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def _inverse_weight(self) -> torch.Tensor:
+        if self.cache_inverse and getattr(self, "W_inverse", None) is not None:
+            return self.W_inverse
+        w_inv = torch.linalg.inv(self._weight().detach().float())
+        if self.cache_inverse:
+            self.W_inverse = w_inv
+        return w_inv
+
+    def log_det(self) -> torch.Tensor:
+        return torch.sum(torch.log(torch.abs(self.upper_diag)))
+
+
+class Invertible1x1ConvLUS(_InvertibleBase):
+    """common.py:507-548: W = P (L + I) (U + diag(d)), log|det W| = sum log|d|."""
+
+    def __init__(self, c, cache_inverse=False):
+        super().__init__()
+        W = torch.linalg.qr(torch.randn(c, c))[0]
+        if torch.det(W) < 0:
+            W[:, 0] = -1 * W[:, 0]
+        p, lower, upper = torch.linalg.lu(W)
+        self.register_buffer("p", p)
+        self.register_buffer("lower_diag", torch.ones(c))
+        self.lower = nn.Parameter(torch.tril(lower, -1))
+        self.upper_diag = nn.Parameter(torch.diag(upper).clone())
+        self.upper = nn.Parameter(torch.triu(upper, 1))
+        self.cache_inverse = cache_inverse
+
+    def _weight(self):
+        U = torch.triu(self.upper, 1) + torch.diag(self.upper_diag)
+        Lm = torch.tril(self.lower, -1) + torch.diag(self.lower_diag)
+        return torch.mm(self.p, torch.mm(Lm, U))
+
+    def forward(self, z, inverse=False, lens=None):
+        b, c, t = z.shape
+        ln = _lens_of(lens, b, t, z.device)
+        if inverse:
+            return _Inv1x1Function.apply(z, self._inverse_weight(), None, None, ln)
+        return _Inv1x1Function.apply(z, self._weight(), None, None, ln), self.log_det()
+
+
+class DataInitializedInvertible1x1Conv(_InvertibleBase):
+    """common.py:551-617: z <- U (z - mean) with a one-off data-dependent whitening initialisation."""
+
+    def __init__(self, c, cache_inverse=False):
+        super().__init__()
+        self.register_buffer("input_mean", torch.zeros(c, 1))
+        self.register_buffer("initialized", torch.tensor(False))
+        W = torch.linalg.qr(torch.randn(c, c))[0]
+        if torch.det(W) < 0:
+            W[:, 0] = -1 * W[:, 0]
+        p, _, upper = torch.linalg.lu(W)
+        self.register_buffer("p", p)
+        self.upper_diag = nn.Parameter(torch.diag(upper).clone())
+        self.upper = nn.Parameter(torch.triu(upper, 1))
+        self.cache_inverse = cache_inverse
+
+    def initialize(self, data, lens):
+        """common.py:569-591: mean / covariance over valid frames, W = chol(cov^-1) (upper); rank 0 broadcasts."""
+        with torch.no_grad():
+            lengths = lens.lengths if hasattr(lens, "lengths") else lens
+            mask = get_mask_from_lengths(lengths.to(data.device), data.shape[2])[:, None].to(data.dtype)
+            n = mask.sum()
+            mean = (data * mask).sum((0, 2)) / n
+            cen = (data - mean[None, :, None]) * mask
+            covar = torch.einsum("bct,bdt->cd", cen, cen) / n
+            self.covar = covar
+            wm = torch.linalg.cholesky(torch.linalg.inv(covar), upper=True).contiguous()
+            mean = mean[:, None].contiguous()
+            if dist.is_available() and dist.is_initialized():
+                dist.broadcast(wm, 0)
+                dist.broadcast(mean, 0)
+            self.input_mean.copy_(mean)
+            self.upper_diag.copy_(torch.diag(wm))
+            self.upper.copy_(torch.triu(wm, 1))
+            self.initialized.fill_(True)
+
+    def maybe_initialize(self, z, lens):
+        """Runs :meth:`initialize` on the first training forward (common.py:594-597).  The device-side flag is read
+        once; afterwards a host flag short-circuits the check so the hot path has no device sync."""
+        if not self.training or getattr(self, "_init_seen", False):
+            return
+        if not bool(self.initialized):
+            self.initialize(z, lens)
+            print("initialized invertible conv")
+        self._init_seen = True
+
+    def _weight(self):
+        return torch.triu(self.upper, 1) + torch.diag(self.upper_diag)
+
+    def forward(self, z, inverse=False, lens=None):
+        b, c, t = z.shape
+        ln = _lens_of(lens, b, t, z.device)
+        mean = self.input_mean.reshape(-1).contiguous()
+        if inverse:
+            return _Inv1x1Function.apply(z, self._inverse_weight(), None, mean, ln)
+        self.maybe_initialize(z, lens if lens is not None else ln)
+        return _Inv1x1Function.apply(z, self._weight(), mean, None, ln), self.log_det()
+
+
+class Invertible1x1Conv(nn.Module):
+    """common.py:621-662: plain-W variant (never instantiated by the shipped configs), log-det via ``logdet``."""
+
+    def __init__(self, c, cache_inverse=False):
+        super().__init__()
+        self.conv = nn.Conv1d(c, c, kernel_size=1, stride=1, padding=0, bias=False)
+        W = torch.linalg.qr(torch.randn(c, c))[0]
+        if torch.det(W) < 0:
+            W[:, 0] = -1 * W[:, 0]
+        self.conv.weight.data = W.view(c, c, 1).contiguous()
+        self.cache_inverse = cache_inverse
+
+    def forward(self, z, inverse=False):
+        W = self.conv.weight.squeeze(-1)
+        ln = _lens_of(None, z.shape[0], z.shape[2], z.device)
+        if inverse:
+            if not (self.cache_inverse and getattr(self, "W_inverse", None) is not None):
+                self.W_inverse = torch.linalg.inv(W.detach().float())
+            w_inv = self.W_inverse
+            if not self.cache_inverse:
+                self.W_inverse = None
+            return _Inv1x1Function.apply(z, w_inv, None, None, ln)
+        return _Inv1x1Function.apply(z, W, None, None, ln), torch.logdet(W).clone()

@@ -1,0 +1,122 @@
+// Fused soft attention (common.py:1259-1276) + text->frame expansion (tts_lightning_modules.py:670).
+// The reference materialises the (B, 80, T1, T2) squared-difference tensor (0.3-2 GB); here one warp owns one
+// query frame: keys stay resident in shared memory for the CTA's ROWS query frames, distances are accumulated in
+// registers, log-softmax / prior / mask / softmax run on warp shuffles, and the attention row is reused from
+// shared memory for context = txt_enc . attn^T.  HBM traffic is the algorithmic minimum:
+// (Ca*(T1+T2) + [prior] T1*T2 + 2*T1*T2 + Dt*(T2+T1)) * 4 B per utterance.
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace radmmm {
+
+namespace {
+
+constexpr int ROWS = 8;   // query frames (warps) per CTA
+
+__global__ void __launch_bounds__(ROWS * 32) soft_attention_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ prior,
+    const int* __restrict__ in_lens, float* __restrict__ attn, float* __restrict__ attn_logprob,
+    const float* __restrict__ txt_enc, float* __restrict__ context, int Ca, int T1, int T2, int Dt, float temp) {
+    extern __shared__ float sm[];
+    float* ks = sm;                          // [Ca][T2]
+    float* qs = ks + (size_t)Ca * T2;        // [ROWS][Ca]
+    float* as = qs + ROWS * Ca;              // [ROWS][T2]  attention rows
+    const int b = blockIdx.y, t1_0 = blockIdx.x * ROWS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* kb = k + (long long)b * Ca * T2;
+    for (int i = tid; i < Ca * T2; i += ROWS * 32) ks[i] = kb[i];
+    for (int i = tid; i < ROWS * Ca; i += ROWS * 32) {
+        const int r = i / Ca, c = i % Ca, t1 = t1_0 + r;
+        qs[i] = (t1 < T1) ? q[((long long)b * Ca + c) * T1 + t1] : 0.0f;
+    }
+    __syncthreads();
+    const int t1 = t1_0 + wid;
+    const int len = min(in_lens[b], T2);
+    float* arow = as + (size_t)wid * T2;
+    if (t1 < T1) {
+        // logits
+        float mx = -INFINITY;
+        for (int t2 = lane; t2 < T2; t2 += 32) {
+            float d = 0.0f;
+            for (int c = 0; c < Ca; ++c) {
+                const float df = qs[wid * Ca + c] - ks[c * T2 + t2];
+                d = fmaf(df, df, d);
+            }
+            const float lg = -temp * d;
+            arow[t2] = lg;
+            mx = fmaxf(mx, lg);
+        }
+        const long long orow = ((long long)b * T1 + t1) * T2;
+        if (prior != nullptr) {
+            // log_softmax over ALL T2 keys (padded ones included, as the reference does), then + log(prior + 1e-8)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float se = 0.0f;
+            for (int t2 = lane; t2 < T2; t2 += 32) se += expf(arow[t2] - mx);
+            se = warp_sum(se);
+            const float lse = mx + logf(se);
+            for (int t2 = lane; t2 < T2; t2 += 32) arow[t2] = arow[t2] - lse + logf(prior[orow + t2] + 1e-8f);
+        }
+        // attn_logprob = pre-mask copy; softmax over the unmasked keys
+        float m2 = -INFINITY;
+        for (int t2 = lane; t2 < T2; t2 += 32) {
+            const float v = arow[t2];
+            attn_logprob[orow + t2] = v;
+            if (t2 < len) m2 = fmaxf(m2, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        float s2 = 0.0f;
+        for (int t2 = lane; t2 < T2; t2 += 32) {
+            const float e = (t2 < len) ? expf(arow[t2] - m2) : 0.0f;
+            arow[t2] = e;
+            s2 += e;
+        }
+        s2 = warp_sum(s2);
+        const float inv = 1.0f / s2;
+        for (int t2 = lane; t2 < T2; t2 += 32) {
+            const float a = arow[t2] * inv;
+            arow[t2] = a;
+            attn[orow + t2] = a;
+        }
+    }
+    if (txt_enc == nullptr) return;
+    __syncthreads();
+    // context[b, d, t1] = sum_t2 txt_enc[b, d, t2] * attn[t1, t2]; thread = (row r, channel slice): coalesced over t1 is
+    // impossible with 8 rows, so lanes run over channels and the ROWS frames are written as one 32-byte segment.
+    const float* tb = txt_enc + (long long)b * Dt * T2;
+    for (int d = tid; d < Dt; d += ROWS * 32) {
+        float acc[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r] = 0.0f;
+        const float* trow = tb + (long long)d * T2;
+        for (int t2 = 0; t2 < len; ++t2) {
+            const float tv = __ldg(trow + t2);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(tv, as[r * T2 + t2], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            if (t1_0 + r < T1) context[((long long)b * Dt + d) * T1 + t1_0 + r] = acc[r];
+    }
+}
+
+}  // namespace
+
+int soft_attention(const float* q, const float* k, const float* prior, const int* in_lens, float* attn,
+                   float* attn_logprob, const float* txt_enc, float* context, int B, int Ca, int T1, int T2, int Dt,
+                   float temperature, cudaStream_t st) {
+    RADMMM_REQUIRE(B > 0 && Ca > 0 && T1 > 0 && T2 > 0, "soft_attention: bad sizes");
+    RADMMM_REQUIRE(txt_enc == nullptr || context != nullptr, "soft_attention: context output missing");
+    const size_t smem = sizeof(float) * ((size_t)Ca * T2 + (size_t)ROWS * Ca + (size_t)ROWS * T2);
+    RADMMM_REQUIRE(smem <= 220 * 1024, "soft_attention: T2=%d keys do not fit in shared memory", T2);
+    if (smem > 48 * 1024)
+        RADMMM_CUDA(cudaFuncSetAttribute(soft_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(T1, ROWS), B);
+    soft_attention_kernel<<<grid, ROWS * 32, smem, st>>>(q, k, prior, in_lens, attn, attn_logprob, txt_enc, context, Ca,
+                                                         T1, T2, Dt, temperature);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+}  // namespace radmmm

@@ -1,0 +1,509 @@
+// HBM-bound kernels of the flow step: layout packing, affine coupling (fwd / inverse / bwd), invertible 1x1
+// convolution, flow-NLL reduction, weight-norm preparation and its backward, bias-gradient column sums.
+// All are sized so that a warp touches consecutive addresses along the contiguous (time or channel) axis.
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace radmmm {
+
+// =========================================================================================================
+// cf (B, C, Tp) fp32  ->  act rows [R][ld] (+ transposed copy [ld][R]); invalid rows and pad columns are zero.
+// 32x32 tile transpose through shared memory: reads coalesced along t, row writes coalesced along c.
+// =========================================================================================================
+template <int MODE>
+__global__ void rows_from_cf_kernel(const float* __restrict__ src, long long batch_stride, int n_ch, RowGeom g,
+                                    ActMat dst, ActMat dstT, int n_cols, int mask_invalid) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        int b, t, len;
+        row_decode(g, r, b, t, len);
+        float v = 0.0f;
+        const bool ok = mask_invalid ? (t < len) : (b < g.B && t < g.Tp);
+        if (c < n_ch && ok) v = src[(long long)b * batch_stride + (long long)c * g.Tp + t];
+        tile[i][tx] = v;
+        if (dstT.ptr && c < n_cols) act_store<MODE>(dstT, (long long)c * dstT.ld + r, v);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        if (c < n_cols) act_store<MODE>(dst, (long long)r * dst.ld + c, tile[tx][i]);
+    }
+}
+
+int rows_from_cf(int mode, const float* src, long long batch_stride, int n_ch, const RowGeom& g, ActMat dst,
+                 ActMat dstT, int n_cols, int mask_invalid, cudaStream_t st) {
+    dim3 grid(g.R / 32, cdiv(n_cols, 32)), block(32, 8);
+    if (mode == MODE_F32) rows_from_cf_kernel<MODE_F32><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, dstT, n_cols, mask_invalid);
+    else if (mode == MODE_BF16) rows_from_cf_kernel<MODE_BF16><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, dstT, n_cols, mask_invalid);
+    else rows_from_cf_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, dstT, n_cols, mask_invalid);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// =========================================================================================================
+// fp32 (B, Tp, D) (the context bi-LSTM output, channels-last)  ->  act rows [R][ld] (+ transposed copy)
+// =========================================================================================================
+template <int MODE>
+__global__ void rows_from_btd_kernel(const float* __restrict__ src, int D, RowGeom g, ActMat dst, ActMat dstT,
+                                     int n_cols) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        int b, t, len;
+        row_decode(g, r, b, t, len);
+        float v = 0.0f;
+        if (c < D && t < len) v = src[((long long)b * g.Tp + t) * D + c];
+        tile[i][tx] = v;
+        if (c < n_cols) act_store<MODE>(dst, (long long)r * dst.ld + c, v);
+    }
+    if (dstT.ptr == nullptr) return;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < n_cols) act_store<MODE>(dstT, (long long)c * dstT.ld + r, tile[tx][i]);
+    }
+}
+
+int rows_from_btd(int mode, const float* src, int D, const RowGeom& g, ActMat dst, ActMat dstT, int n_cols,
+                  cudaStream_t st) {
+    dim3 grid(g.R / 32, cdiv(n_cols, 32)), block(32, 8);
+    if (mode == MODE_F32) rows_from_btd_kernel<MODE_F32><<<grid, block, 0, st>>>(src, D, g, dst, dstT, n_cols);
+    else if (mode == MODE_BF16) rows_from_btd_kernel<MODE_BF16><<<grid, block, 0, st>>>(src, D, g, dst, dstT, n_cols);
+    else rows_from_btd_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(src, D, g, dst, dstT, n_cols);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// fp32 rows [R][ld] -> fp32 (B, Tp, D) accumulate (gradient of the context back to the LSTM output layout)
+__global__ void btd_from_rows_kernel(const float* __restrict__ rows, long long ld, int D, RowGeom g,
+                                     float* __restrict__ dst, int accumulate) {
+    const int r = blockIdx.x;
+    int b, t, len;
+    row_decode(g, r, b, t, len);
+    if (b >= g.B || t >= g.Tp) return;
+    float* o = dst + ((long long)b * g.Tp + t) * D;
+    const float* s = rows + (long long)r * ld;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float v = (t < len) ? s[c] : 0.0f;
+        o[c] = accumulate ? o[c] + v : v;
+    }
+}
+
+int btd_from_rows(const float* rows, long long ld, int D, const RowGeom& g, float* dst, int accumulate,
+                  cudaStream_t st) {
+    btd_from_rows_kernel<<<g.B * g.pitch, 256, 0, st>>>(rows, ld, D, g, dst, accumulate);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// =========================================================================================================
+// Affine coupling (common.py:1127-1185).  params (B, C, Tp): [:Ch] = scale pre-activation a, [Ch:] = shift b.
+// =========================================================================================================
+__device__ __forceinline__ void scale_fn(int fn, float a, float& s, float& log_s, float& ds_da) {
+    if (fn == SCALE_TANH) {
+        float th = tanhf(a);
+        s = th + 1.0f + 1e-6f;
+        log_s = logf(s);
+        ds_da = 1.0f - th * th;
+    } else if (fn == SCALE_EXP) {
+        s = expf(a);
+        log_s = a;
+        ds_da = s;
+    } else if (fn == SCALE_SIGMOID) {
+        float sg = 1.0f / (1.0f + expf(-(a + 10.0f)));
+        s = sg + 1e-6f;
+        log_s = logf(s);
+        ds_da = sg * (1.0f - sg);
+    } else {  // translate
+        s = 1.0f;
+        log_s = 0.0f;
+        ds_da = 0.0f;
+    }
+}
+
+// grid: (ceil(Tp/256), Ch, B)
+__global__ void coupling_fwd_kernel(const float* __restrict__ z, const float* __restrict__ params,
+                                    float* __restrict__ z_out, float* __restrict__ log_s, int C, int Tp, int fn,
+                                    int inverse) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tp) return;
+    const int c = blockIdx.y, b = blockIdx.z, Ch = C / 2;
+    const long long i0 = ((long long)b * C + c) * Tp + t, i1 = ((long long)b * C + Ch + c) * Tp + t;
+    float s, ls, d;
+    scale_fn(fn, params[i0], s, ls, d);
+    const float shift = params[i1];
+    if (z_out != z) z_out[i0] = z[i0];
+    if (inverse) {
+        z_out[i1] = (z[i1] - shift) / s;
+    } else {
+        z_out[i1] = s * z[i1] + shift;
+        log_s[((long long)b * Ch + c) * Tp + t] = ls;
+    }
+}
+
+int coupling_fwd(const float* z, const float* params, float* z_out, float* log_s, int B, int C, int Tp, int fn,
+                 int inverse, cudaStream_t st) {
+    dim3 grid(cdiv(Tp, 256), C / 2, B);
+    coupling_fwd_kernel<<<grid, 256, 0, st>>>(z, params, z_out, log_s, C, Tp, fn, inverse);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// backward of the forward coupling.  Incoming gradients are treated as zero beyond each length (the flow loss
+// masks them, loss.py:91,102).  Writes dz (B,C,Tp) [first half = pass-through part only] and dparams (B,C,Tp).
+__global__ void coupling_bwd_kernel(const float* __restrict__ dz_out, const float* __restrict__ dlog_s,
+                                    const float* __restrict__ z, const float* __restrict__ params,
+                                    const int* __restrict__ lens, float* __restrict__ dz,
+                                    float* __restrict__ dparams, int C, int Tp, int fn) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tp) return;
+    const int c = blockIdx.y, b = blockIdx.z, Ch = C / 2;
+    const long long i0 = ((long long)b * C + c) * Tp + t, i1 = ((long long)b * C + Ch + c) * Tp + t;
+    const bool valid = t < lens[b];
+    float s, ls, d;
+    scale_fn(fn, params[i0], s, ls, d);
+    const float g1 = valid ? dz_out[i1] : 0.0f;
+    const float gl = (valid && dlog_s) ? dlog_s[((long long)b * Ch + c) * Tp + t] : 0.0f;
+    dz[i0] = valid ? dz_out[i0] : 0.0f;
+    dz[i1] = g1 * s;
+    float da;
+    if (fn == SCALE_EXP) da = g1 * z[i1] * s + gl;
+    else if (fn == SCALE_TRANSLATE) da = 0.0f;
+    else da = (g1 * z[i1] + gl / s) * d;
+    dparams[i0] = da;
+    dparams[i1] = g1;
+}
+
+int coupling_bwd(const float* dz_out, const float* dlog_s, const float* z, const float* params, const int* lens,
+                 float* dz, float* dparams, int B, int C, int Tp, int fn, cudaStream_t st) {
+    dim3 grid(cdiv(Tp, 256), C / 2, B);
+    coupling_bwd_kernel<<<grid, 256, 0, st>>>(dz_out, dlog_s, z, params, lens, dz, dparams, C, Tp, fn);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// =========================================================================================================
+// Invertible 1x1 convolution (common.py:540-548, 605-617):  out[b,co,t] = sum_ci W[co,ci]*(in[b,ci,t]-pre[ci]) + post[co]
+// One CTA per (32-frame tile, batch): W streamed through shared memory in 32-column panels; x tile resident.
+// fp32 FFMA; HBM-bound: 2*C*4 bytes per grouped frame.
+// =========================================================================================================
+constexpr int INV_TT = 32;
+__global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
+                                                     const float* __restrict__ W, const float* __restrict__ pre,
+                                                     const float* __restrict__ post, float* __restrict__ out,
+                                                     long long out_bs, int Cin, int Cout, int Tp) {
+    extern __shared__ float sm[];
+    float* xs = sm;                    // [Cin][INV_TT]
+    float* ws = sm + Cin * INV_TT;     // [Cout][33] panel of 32 input channels
+    const int t0 = blockIdx.x * INV_TT, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < Cin * INV_TT; i += 256) {
+        const int c = i / INV_TT, t = t0 + (i % INV_TT);
+        float v = 0.0f;
+        if (t < Tp) v = in[(long long)b * in_bs + (long long)c * Tp + t] - (pre ? pre[c] : 0.0f);
+        xs[i] = v;
+    }
+    // each warp owns output channels wid, wid+8, ...; lane = frame
+    constexpr int MAXO = 32;           // supports Cout <= 256
+    float acc[MAXO];
+#pragma unroll
+    for (int i = 0; i < MAXO; ++i) acc[i] = 0.0f;
+    for (int k0 = 0; k0 < Cin; k0 += 32) {
+        __syncthreads();
+        for (int i = tid; i < Cout * 32; i += 256) {
+            const int co = i >> 5, k = i & 31;
+            ws[co * 33 + k] = (k0 + k < Cin) ? W[(long long)co * Cin + k0 + k] : 0.0f;
+        }
+        __syncthreads();
+        const int kmax = min(32, Cin - k0);
+        for (int k = 0; k < kmax; ++k) {
+            const float xv = xs[(k0 + k) * INV_TT + lane];
+#pragma unroll
+            for (int i = 0; i < MAXO; ++i) {
+                const int co = wid + 8 * i;
+                if (co < Cout) acc[i] = fmaf(ws[co * 33 + k], xv, acc[i]);
+            }
+        }
+    }
+    const int t = t0 + lane;
+    if (t < Tp) {
+#pragma unroll
+        for (int i = 0; i < MAXO; ++i) {
+            const int co = wid + 8 * i;
+            if (co < Cout) out[(long long)b * out_bs + (long long)co * Tp + t] = acc[i] + (post ? post[co] : 0.0f);
+        }
+    }
+}
+
+int inv1x1(const float* in, long long in_bs, const float* W, const float* pre, const float* post, float* out,
+           long long out_bs, int B, int Cin, int Cout, int Tp, cudaStream_t st) {
+    RADMMM_REQUIRE(Cout <= 256 && Cin <= 1024, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
+    size_t smem = ((size_t)Cin * INV_TT + (size_t)Cout * 33) * sizeof(float);
+    if (smem > 48 * 1024) RADMMM_CUDA(cudaFuncSetAttribute(inv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(Tp, INV_TT), B);
+    inv1x1_kernel<<<grid, 256, smem, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// dW[co][ci] += sum over valid (b,t) of dz[b,co,t] * (x[b,ci,t] - pre[ci]).  32x32 output tile per CTA, split over
+// (batch, time chunks) with atomics into a zeroed fp32 buffer.
+__global__ void __launch_bounds__(256) inv1x1_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ x,
+                                                           const float* __restrict__ pre, const int* __restrict__ lens,
+                                                           float* __restrict__ dW, int C, int Tp, int t_chunk) {
+    __shared__ float a[32][33], bx[32][33];
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+    const int b = blockIdx.z / cdiv(Tp, t_chunk), tc = blockIdx.z % cdiv(Tp, t_chunk);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const int len = min(lens[b], Tp);
+    const int t_begin = tc * t_chunk, t_end = min(len, t_begin + t_chunk);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t0 = t_begin; t0 < t_end; t0 += 32) {
+        for (int i = ty; i < 32; i += 8) {
+            const int t = t0 + tx;
+            const bool ok = t < t_end;
+            a[i][tx] = (ok && co0 + i < C) ? dz[((long long)b * C + co0 + i) * Tp + t] : 0.0f;
+            bx[i][tx] = (ok && ci0 + i < C) ? x[((long long)b * C + ci0 + i) * Tp + t] - (pre ? pre[ci0 + i] : 0.0f) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(a[ty + 8 * j][k], bx[tx][k], acc[j]);
+        __syncthreads();
+    }
+    if (t_begin < t_end)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + ty + 8 * j, ci = ci0 + tx;
+            if (co < C && ci < C) atomicAdd(dW + (long long)co * C + ci, acc[j]);
+        }
+}
+
+int inv1x1_wgrad(const float* dz, const float* x, const float* pre, const int* lens, float* dW, int B, int C, int Tp,
+                 cudaStream_t st) {
+    const int t_chunk = 256;
+    RADMMM_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * C * C, st));
+    dim3 grid(cdiv(C, 32), cdiv(C, 32), B * cdiv(Tp, t_chunk));
+    inv1x1_wgrad_kernel<<<grid, 256, 0, st>>>(dz, x, pre, lens, dW, C, Tp, t_chunk);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// =========================================================================================================
+// Flow NLL reduction (loss.py:85-110): sums[0] = sum (z*m)^2, sums[1+i] = sum log_s_i * m.  fp64 accumulation,
+// warp-shuffle then one atomic per warp.
+// =========================================================================================================
+__global__ void masked_sum_kernel(const float* __restrict__ x, const int* __restrict__ lens, int C, int Tp,
+                                  int square, double* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int len = min(lens[b], Tp);
+    const long long n = (long long)C * Tp;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % Tp);
+        if (t < len) {
+            const float v = x[(long long)b * n + i];
+            acc += square ? (double)v * (double)v : (double)v;
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+
+int masked_sum(const float* x, const int* lens, int B, int C, int Tp, int square, double* out, cudaStream_t st) {
+    dim3 grid(max(1, min(64, cdiv((long long)C * Tp, 1024))), B);
+    masked_sum_kernel<<<grid, 256, 0, st>>>(x, lens, C, Tp, square, out);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// d/dx of  coef * sum (x*m)^2   (square=1: 2*coef*x*m)   or  coef * sum x*m  (square=0: coef*m)
+__global__ void masked_sum_bwd_kernel(const float* __restrict__ x, const int* __restrict__ lens, int C, int Tp,
+                                      int square, const float* __restrict__ coef_ptr, float coef_mul,
+                                      float* __restrict__ dx) {
+    const int b = blockIdx.y;
+    const int len = min(lens[b], Tp);
+    const long long n = (long long)C * Tp;
+    const float coef = coef_ptr[0] * coef_mul;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % Tp);
+        float v = 0.0f;
+        if (t < len) v = square ? 2.0f * coef * x[(long long)b * n + i] : coef;
+        dx[(long long)b * n + i] = v;
+    }
+}
+
+int masked_sum_bwd(const float* x, const int* lens, int B, int C, int Tp, int square, const float* coef_ptr,
+                   float coef_mul, float* dx, cudaStream_t st) {
+    dim3 grid(max(1, min(256, cdiv((long long)C * Tp, 1024))), B);
+    masked_sum_bwd_kernel<<<grid, 256, 0, st>>>(x, lens, C, Tp, square, coef_ptr, coef_mul, dx);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// =========================================================================================================
+// Weight preparation: weight-norm (w = g * v / ||v||, per output channel) and re-layout into the K-major
+// per-tap matrices the contraction kernels read, plus the transposed copies the dgrad GEMMs read.
+// =========================================================================================================
+// one CTA per output channel: norm[co] = ||v[co]||, rowsum[co] = sum v[co]   (fp64 accumulate)
+__global__ void wn_norm_kernel(const float* __restrict__ v, int per_co, float* __restrict__ norm,
+                               float* __restrict__ rowsum) {
+    const int co = blockIdx.x;
+    const float* p = v + (long long)co * per_co;
+    double s2 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < per_co; i += blockDim.x) {
+        const double x = p[i];
+        s2 += x * x;
+        s1 += x;
+    }
+    __shared__ double r2[8], r1[8];
+    s2 = warp_sum(s2);
+    s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { r2[threadIdx.x >> 5] = s2; r1[threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += r2[i]; b += r1[i]; }
+        norm[co] = (float)sqrt(a);
+        if (rowsum) rowsum[co] = (float)b;
+    }
+}
+
+int wn_norm(const float* v, int n_co, int per_co, float* norm, float* rowsum, cudaStream_t st) {
+    wn_norm_kernel<<<n_co, 256, 0, st>>>(v, per_co, norm, rowsum);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// v (co, ci_total, k) fp32; columns [ci_begin, ci_begin+n_ci) go to dst[tap][co][ci - ci_begin] (ld_dst, tap stride)
+// and dstT[tap][ci - ci_begin][co].  scale[co] = g/||v|| (or 1 when g == null).  32x32 tiles, smem transpose.
+template <int MODE>
+__global__ void wn_scatter_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                  const float* __restrict__ norm, int n_co, int ci_total, int ksize, int ci_begin,
+                                  int n_ci, ActMat dst, long long dst_tap, ActMat dstT, long long dstT_tap) {
+    __shared__ float tile[32][33];
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32, tap = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int i = ty; i < 32; i += 8) {
+        const int co = co0 + i, ci = ci0 + tx;
+        float val = 0.0f;
+        if (co < n_co && ci < n_ci) {
+            const float sc = g ? g[co] / norm[co] : 1.0f;
+            val = sc * v[((long long)co * ci_total + ci_begin + ci) * ksize + tap];
+            if (dst.ptr) act_store<MODE>(dst, tap * dst_tap + (long long)co * dst.ld + ci, val);
+        }
+        tile[i][tx] = val;
+    }
+    if (dstT.ptr == nullptr) return;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int ci = ci0 + i, co = co0 + tx;
+        if (co < n_co && ci < n_ci) act_store<MODE>(dstT, tap * dstT_tap + (long long)ci * dstT.ld + co, tile[tx][i]);
+    }
+}
+
+int wn_scatter(int mode, const float* v, const float* g, const float* norm, int n_co, int ci_total, int ksize,
+               int ci_begin, int n_ci, ActMat dst, long long dst_tap, ActMat dstT, long long dstT_tap, cudaStream_t st) {
+    dim3 grid(cdiv(n_co, 32), cdiv(n_ci, 32), ksize), block(32, 8);
+    if (mode == MODE_F32) wn_scatter_kernel<MODE_F32><<<grid, block, 0, st>>>(v, g, norm, n_co, ci_total, ksize, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap);
+    else if (mode == MODE_BF16) wn_scatter_kernel<MODE_BF16><<<grid, block, 0, st>>>(v, g, norm, n_co, ci_total, ksize, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap);
+    else wn_scatter_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(v, g, norm, n_co, ci_total, ksize, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// padq[co] = log(2) * (g/||v||) * rowsum(v[co]) + bias[co]: the res-skip pre-activation on frames beyond the
+// sequence length, where the reference feeds softplus(0) = log 2 on every channel (common.py:830-831).
+__global__ void padq_kernel(const float* g, const float* norm, const float* rowsum, const float* bias, float* padq, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) padq[i] = 0.6931471805599453f * (g[i] / norm[i]) * rowsum[i] + bias[i];
+}
+
+int padq_compute(const float* g, const float* norm, const float* rowsum, const float* bias, float* padq, int n,
+                 cudaStream_t st) {
+    padq_kernel<<<cdiv(n, 256), 256, 0, st>>>(g, norm, rowsum, bias, padq, n);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// backward of weight norm.  dW comes from the weight-grad GEMM as up to two column blocks of [tap][co][ld]:
+//   ci in [0, n_ci0) from src0, ci in [n_ci0, ci_total) from src1.   One CTA per output channel.
+//   dg[co] = <dW, v>/||v|| ;  dv = (g/||v||) * (dW - v * <dW,v>/||v||^2)
+__global__ void wn_bwd_kernel(const float* __restrict__ src0, long long ld0, long long tap0, int n_ci0,
+                              const float* __restrict__ src1, long long ld1, long long tap1,
+                              const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norm,
+                              int ci_total, int ksize, float* __restrict__ dv, float* __restrict__ dg) {
+    const int co = blockIdx.x;
+    const int per_co = ci_total * ksize;
+    const float* vp = v + (long long)co * per_co;
+    auto dw_at = [&](int ci, int k) -> float {
+        return ci < n_ci0 ? src0[k * tap0 + (long long)co * ld0 + ci] : src1[k * tap1 + (long long)co * ld1 + (ci - n_ci0)];
+    };
+    double dot = 0.0;
+    for (int i = threadIdx.x; i < per_co; i += blockDim.x) dot += (double)dw_at(i / ksize, i % ksize) * (double)vp[i];
+    __shared__ double red[8];
+    __shared__ float sdot;
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
+        sdot = (float)a;
+    }
+    __syncthreads();
+    const float nrm = norm[co], gg = g[co];
+    const float d = sdot;
+    if (threadIdx.x == 0) dg[co] = d / nrm;
+    const float sc = gg / nrm, coef = d / (nrm * nrm);
+    float* o = dv + (long long)co * per_co;
+    for (int i = threadIdx.x; i < per_co; i += blockDim.x) o[i] = sc * (dw_at(i / ksize, i % ksize) - vp[i] * coef);
+}
+
+int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const float* src1, long long ld1,
+           long long tap1, const float* v, const float* g, const float* norm, int n_co, int ci_total, int ksize,
+           float* dv, float* dg, cudaStream_t st) {
+    wn_bwd_kernel<<<n_co, 256, 0, st>>>(src0, ld0, tap0, n_ci0, src1, ld1, tap1, v, g, norm, ci_total, ksize, dv, dg);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+// =========================================================================================================
+// Bias gradients: out[n] = sum over valid rows of X[r][n] * (unratio ? 1/ratio(r) : 1).  X is an act matrix.
+// =========================================================================================================
+template <int MODE>
+__global__ void colsum_kernel(ActMat x, RowGeom g, int n_cols, int dilation, int unratio, int rows_per_block,
+                              float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_cols) return;
+    const int r_begin = blockIdx.y * rows_per_block, r_end = min(g.R, r_begin + rows_per_block);
+    float acc = 0.0f;
+    for (int r = r_begin; r < r_end; ++r) {
+        int b, t, len;
+        row_decode(g, r, b, t, len);
+        if (t < len) {
+            float w = unratio ? 1.0f / pconv_ratio(t, len, dilation) : 1.0f;
+            acc += act_load<MODE>(x, (long long)r * x.ld + n) * w;
+        }
+    }
+    atomicAdd(out + n, acc);
+}
+
+int colsum(int mode, ActMat x, const RowGeom& g, int n_cols, int dilation, int unratio, float* out, cudaStream_t st) {
+    RADMMM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, st));
+    const int rpb = 64;
+    dim3 grid(cdiv(n_cols, 128), cdiv(g.R, rpb));
+    if (mode == MODE_F32) colsum_kernel<MODE_F32><<<grid, 128, 0, st>>>(x, g, n_cols, dilation, unratio, rpb, out);
+    else if (mode == MODE_BF16) colsum_kernel<MODE_BF16><<<grid, 128, 0, st>>>(x, g, n_cols, dilation, unratio, rpb, out);
+    else colsum_kernel<MODE_BF16X3><<<grid, 128, 0, st>>>(x, g, n_cols, dilation, unratio, rpb, out);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+}  // namespace radmmm

@@ -1,0 +1,238 @@
+// Contraction interface shared by the FFMA (fp32) and tcgen05 (bf16 / bf16x3) kernels, and the fused epilogues.
+//
+// "Row GEMM":   D[r][n] = sum_seg sum_k A_seg[r + row_shift_seg][k] * W_seg[n][k]        r in [0,R), n in [0,N)
+//     A_seg are act matrices over rows (activations / gradients, [R][K_seg]); rows outside [0,R) read as zero.
+//     W_seg are prepared weights [N_pad][K_seg], K-major.  A k=5 dilated conv is 5 segments with row shifts
+//     (j-2)*d; the WN start conv is 2 segments (z0 | context); the fused dgrad of a layer is 6 segments.
+// "Weight-grad GEMM":  D_tap[m][n] = sum_r dY[r][m] * X[r + shift_tap][n]                 (K = rows)
+//
+// The epilogue (one of EPI_*) consumes the fp32 accumulators while they are still on chip.
+#pragma once
+#include "common.cuh"
+
+namespace radmmm {
+
+enum {
+    EPI_START = 0,  // h0 = (acc + bias) masked                               (common.py:820)
+    EPI_IN = 1,     // h = softplus(acc * ratio + bias) masked                 (partialconv1d.py:84-94, common.py:190,830)
+    EPI_RS = 2,     // s = softplus(acc + bias); out += s; sig = 1-exp(-s)     (common.py:831-832)
+    EPI_END = 3,    // params = acc + bias -> channels-first fp32              (common.py:834)
+    EPI_DOUT = 4,   // d_out = acc; dq_i = d_out * sig_i  for every layer i
+    EPI_DH = 5,     // dacc = acc * softplus'(p) * ratio, masked
+    EPI_DH0 = 6,    // dh0 = acc masked
+    EPI_DZ0 = 7,    // dz0 -> channels-first fp32 (accumulate)
+    EPI_DCTX = 8,   // dctx rows fp32
+    EPI_WGRAD = 9,  // weight gradient tile -> fp32 (store or atomic add)
+    EPI_F32 = 10,   // generic: rows fp32 = acc (+ bias)
+};
+
+constexpr int kMaxSeg = 6;
+constexpr int kMaxLayers = 8;
+
+struct GemmSeg {
+    ActMat a;        // rows operand [R][K]   (weight-grad: dY [R][M])
+    ActMat aT;       // transposed copy [K][R] (weight-grad on tensor cores: dY^T [M][R]); may be null in MODE_F32
+    ActMat w;        // weights [N_pad][K]    (weight-grad: X [R][N])
+    ActMat wT;       // (weight-grad on tensor cores: X^T [N][R])
+    int K;           // contraction length of this segment (multiple of 64)
+    int shift;       // row shift applied to A (row GEMM) / to X (weight-grad GEMM)
+};
+
+struct EpiParams {
+    int kind;
+    RowGeom geom;
+    int N;                       // logical number of output columns
+    int M;                       // weight-grad: logical number of output rows
+    const float* bias;           // [N] or null
+    int dilation;
+    int first, last, accumulate, n_layers;
+    ActMat out0, out0T, out1, out1T;
+    float* f32_out;
+    long long f32_ld;
+    long long f32_tap_stride;    // weight-grad: elements between taps
+    const float* padq;
+    ActMat sig[kMaxLayers];
+    ActMat dq[kMaxLayers], dqT[kMaxLayers];
+    ActMat h;
+    float* cf_out;               // channels-first (B, cf_C, Tp) fp32
+    int cf_C, cf_c0;
+    int atomic;                  // weight-grad split-K: atomicAdd instead of store
+};
+
+struct GemmArgs {
+    int n_seg;
+    GemmSeg seg[kMaxSeg];
+    int R;          // rows (multiple of 128)
+    int n_tiles_n;  // informational
+    int wgrad;      // 0 row GEMM, 1 weight-grad GEMM (n_seg = number of taps, one output tile set per tap)
+    int split_k;    // weight-grad only
+    EpiParams epi;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue for one row r and NV consecutive columns n0..n0+NV-1 (n0 % NV == 0, NV in {4, 8, 16, 32}).
+// `lane_rows` tells whether consecutive lanes hold consecutive rows (tcgen05 path) -- only a perf hint.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE, int NV>
+__device__ __forceinline__ void store_row_vec(const ActMat& m, int r, int n0, const float* v) {
+    if (m.ptr == nullptr) return;
+    long long idx = (long long)r * m.ld + n0;
+    if constexpr (MODE == MODE_F32) {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(m.ptr) + idx);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(m.ptr);
+        if constexpr (NV >= 8) {
+#pragma unroll
+            for (int i = 0; i < NV / 8; ++i) {
+                __nv_bfloat162 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = v[8 * i + 2 * j], b = v[8 * i + 2 * j + 1];
+                    h[j] = __floats2bfloat162_rn(a, b);
+                    if constexpr (MODE == MODE_BF16X3)
+                        l[j] = __floats2bfloat162_rn(a - __bfloat162float(h[j].x), b - __bfloat162float(h[j].y));
+                }
+                *reinterpret_cast<uint4*>(base + idx + 8 * i) = *reinterpret_cast<uint4*>(h);
+                if constexpr (MODE == MODE_BF16X3)
+                    *reinterpret_cast<uint4*>(base + idx + m.plane_stride + 8 * i) = *reinterpret_cast<uint4*>(l);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) act_store<MODE>(m, idx + i, v[i]);
+        }
+    }
+}
+
+template <int MODE, int NV>
+__device__ __forceinline__ void store_col_vec(const ActMat& mT, int r, int n0, const float* v) {
+    if (mT.ptr == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) act_store<MODE>(mT, (long long)(n0 + i) * mT.ld + r, v[i]);
+}
+
+template <int MODE, int NV>
+__device__ __forceinline__ void load_row_vec(const ActMat& m, int r, int n0, float* v) {
+    long long idx = (long long)r * m.ld + n0;
+    if constexpr (MODE == MODE_F32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(m.ptr) + idx);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            float4 t = p[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = act_load<MODE>(m, idx + i);
+    }
+}
+
+template <int MODE, int KIND, int NV>
+__device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, float* acc) {
+    int b, t, len;
+    row_decode(p.geom, r, b, t, len);
+    const bool valid = t < len;
+    float out[NV];
+    if constexpr (KIND == EPI_START) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] + __ldg(p.bias + n0 + i) : 0.0f;
+        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
+    } else if constexpr (KIND == EPI_IN) {
+        const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) out[i] = valid ? softplus_f(acc[i] * ratio + __ldg(p.bias + n0 + i)) : 0.0f;
+        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
+    } else if constexpr (KIND == EPI_RS) {
+        float s[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float q = valid ? acc[i] + __ldg(p.bias + n0 + i) : __ldg(p.padq + n0 + i);
+            s[i] = softplus_f(q);
+            out[i] = valid ? sigmoid_from_softplus(s[i]) : 0.0f;
+        }
+        store_row_vec<MODE, NV>(p.out0, r, n0, out);           // sig_i (training only)
+        float* o = p.f32_out + (long long)r * p.f32_ld + n0;
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            float4 prev = p.first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(o)[i];
+            prev.x += s[4 * i]; prev.y += s[4 * i + 1]; prev.z += s[4 * i + 2]; prev.w += s[4 * i + 3];
+            reinterpret_cast<float4*>(o)[i] = prev;
+            s[4 * i] = prev.x; s[4 * i + 1] = prev.y; s[4 * i + 2] = prev.z; s[4 * i + 3] = prev.w;
+        }
+        if (p.last) {
+            store_row_vec<MODE, NV>(p.out1, r, n0, s);
+            store_col_vec<MODE, NV>(p.out1T, r, n0, s);
+        }
+    } else if constexpr (KIND == EPI_END || KIND == EPI_DZ0) {
+        if (b < p.geom.B && t < p.geom.Tp) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                int n = n0 + i;
+                if (n < p.N) {
+                    float v = acc[i] + (KIND == EPI_END ? __ldg(p.bias + n) : 0.0f);
+                    float* dst = p.cf_out + ((long long)(b * p.cf_C + p.cf_c0 + n)) * p.geom.Tp + t;
+                    if (p.accumulate) v += *dst;
+                    *dst = v;
+                }
+            }
+        }
+    } else if constexpr (KIND == EPI_DOUT) {
+        for (int l = 0; l < p.n_layers; ++l) {
+            float sg[NV];
+            load_row_vec<MODE, NV>(p.sig[l], r, n0, sg);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) out[i] = acc[i] * sg[i];
+            store_row_vec<MODE, NV>(p.dq[l], r, n0, out);
+            store_col_vec<MODE, NV>(p.dqT[l], r, n0, out);
+        }
+    } else if constexpr (KIND == EPI_DH) {
+        if (valid) {
+            float hv[NV];
+            load_row_vec<MODE, NV>(p.h, r, n0, hv);
+            const float ratio = pconv_ratio(t, len, p.dilation);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) out[i] = acc[i] * sigmoid_from_softplus(hv[i]) * ratio;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) out[i] = 0.0f;
+        }
+        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
+    } else if constexpr (KIND == EPI_DH0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] : 0.0f;
+        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
+    } else if constexpr (KIND == EPI_DCTX || KIND == EPI_F32) {
+        float* o = p.f32_out + (long long)r * p.f32_ld + n0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (n0 + i < p.N) {
+                float v = acc[i] + ((KIND == EPI_F32 && p.bias) ? __ldg(p.bias + n0 + i) : 0.0f);
+                o[i] = p.accumulate ? o[i] + v : v;
+            }
+    }
+}
+
+// weight-grad tile element (m, n0..n0+NV) of tap `tap`
+template <int NV>
+__device__ __forceinline__ void epi_wgrad(const EpiParams& p, int tap, int m, int n0, const float* acc) {
+    if (m >= p.M) return;
+    float* o = p.f32_out + (long long)tap * p.f32_tap_stride + (long long)m * p.f32_ld + n0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (n0 + i < p.N) {
+            if (p.atomic) atomicAdd(o + i, acc[i]);
+            else o[i] = acc[i];
+        }
+}
+
+// launchers (gemm_ffma.cu / gemm_tc.cu)
+int launch_gemm_ffma(const GemmArgs& args, cudaStream_t stream);
+int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream);
+int launch_gemm(const GemmArgs& args, int mode, cudaStream_t stream);
+
+}  // namespace radmmm

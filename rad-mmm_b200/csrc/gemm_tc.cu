@@ -1,0 +1,514 @@
+// tcgen05 / TMA / TMEM contraction kernel for sm_100a (MODE_BF16 and MODE_BF16X3).
+//
+// Persistent, warp-specialised: one CTA per SM loops over 128 x BN output tiles.
+//   warp 0      TMA producer   cp.async.bulk.tensor (128B-swizzled K-major boxes) into a multi-stage smem ring
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16),
+//                              fp32 accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
+//                              overlaps the main loop of tile i+1; tcgen05.commit releases smem slots / publishes TMEM
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue (gemm.cuh) -> HBM
+// A k=5 dilated conv is five K-segments whose A boxes are the same activation matrix shifted by (j-2)*d rows
+// (TMA zero-fills rows outside [0,R); utterances are separated by >= 16 zero rows, so no tap crosses a sequence).
+// MODE_BF16X3 loads hi and lo planes of both operands and issues hi*hi + lo*hi + hi*lo into the same accumulator.
+// The weight-grad GEMM contracts over rows: both operands are the transposed ([channels][R]) copies, the tap shift
+// moves the K coordinate of the X box, and split-K partial tiles are reduced with fp32 atomics.
+// Roofline: tensor pipe (dense bf16, MEASURED_PEAKS.json); BF16X3 has one third of it.
+#include <cuda.h>
+#include "gemm.cuh"
+
+namespace radmmm {
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kMaxMaps = 4;   // unique A maps and unique B maps per launch
+
+struct TcSeg {
+    int a_map, b_map;      // indices into the map tables
+    int a_row_shift;       // row GEMM: shift on the A outer coordinate; weight-grad: unused
+    int b_row_off;         // row GEMM: first weight row of this segment inside the B map; weight-grad: K shift of X
+    int k_blocks;          // K / 64
+};
+
+struct TcParams {
+    CUtensorMap a_hi[kMaxMaps], a_lo[kMaxMaps], b_hi[kMaxMaps], b_lo[kMaxMaps];
+    TcSeg seg[kMaxSeg];
+    int n_seg, n_a_maps, n_b_maps;
+    int m_tiles, n_tiles, taps, split_k, k_blocks_total;   // weight-grad: k_blocks_total = R/64
+    EpiParams epi;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1ll << 22)) {     // a pipeline bug must trap, never hang the device
+            printf("radmmm gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int MODE, int BN>
+struct Cfg {
+    static constexpr int planes = (MODE == MODE_BF16X3) ? 2 : 1;
+    static constexpr int a_bytes = BM * BK * 2;
+    static constexpr int b_bytes = BN * BK * 2;
+    static constexpr int stage_bytes = planes * (a_bytes + b_bytes);
+    static constexpr int stages = (200 * 1024) / stage_bytes > 8 ? 8 : (200 * 1024) / stage_bytes;
+    static constexpr int tmem_cols = 2 * BN;      // 256 or 512: powers of two
+    static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int MODE, int KIND, int BN, bool WGRAD>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
+    using C = Cfg<MODE, BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
+    uint64_t* full = bars;                       // [stages]
+    uint64_t* empty = bars + C::stages;          // [stages]
+    uint64_t* tfull = bars + 2 * C::stages;      // [2]
+    uint64_t* tempty = bars + 2 * C::stages + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < P.n_a_maps; ++i) { prefetch_tmap(&P.a_hi[i]); if (C::planes == 2) prefetch_tmap(&P.a_lo[i]); }
+        for (int i = 0; i < P.n_b_maps; ++i) { prefetch_tmap(&P.b_hi[i]); if (C::planes == 2) prefetch_tmap(&P.b_lo[i]); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_mn = P.m_tiles * P.n_tiles;
+    const int n_tiles_total = WGRAD ? tiles_mn * P.taps * P.split_k : tiles_mn;
+
+    // weight-grad split-K range (in 64-row K blocks)
+    auto k_range = [&](int split, int& kb0, int& kb1) {
+        const int per = (P.k_blocks_total + P.split_k - 1) / P.split_k;
+        kb0 = min(P.k_blocks_total, split * per);
+        kb1 = min(P.k_blocks_total, kb0 + per);
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+                int mn = tile, tap = 0, split = 0;
+                if (WGRAD) { mn = tile % tiles_mn; const int ts = tile / tiles_mn; tap = ts / P.split_k; split = ts % P.split_k; }
+                const int m_blk = mn / P.n_tiles, n_blk = mn % P.n_tiles;
+                const int seg_begin = WGRAD ? tap : 0, seg_end = WGRAD ? tap + 1 : P.n_seg;
+                for (int s = seg_begin; s < seg_end; ++s) {
+                    const TcSeg sg = P.seg[s];
+                    int kb0 = 0, kb1 = sg.k_blocks;
+                    if (WGRAD) k_range(split, kb0, kb1);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * C::stage_bytes;
+                        mbar_expect_tx(&full[stage], C::stage_bytes);
+                        int a_c0, a_c1, b_c0, b_c1;
+                        if (!WGRAD) {
+                            a_c0 = kb * BK; a_c1 = m_blk * BM + sg.a_row_shift;
+                            b_c0 = kb * BK; b_c1 = n_blk * BN + sg.b_row_off;
+                        } else {
+                            a_c0 = kb * BK; a_c1 = m_blk * BM;
+                            b_c0 = kb * BK + sg.b_row_off; b_c1 = n_blk * BN;
+                        }
+                        tma_load_2d(st, &P.a_hi[sg.a_map], &full[stage], a_c0, a_c1);
+                        tma_load_2d(st + C::planes * C::a_bytes, &P.b_hi[sg.b_map], &full[stage], b_c0, b_c1);
+                        if (C::planes == 2) {
+                            tma_load_2d(st + C::a_bytes, &P.a_lo[sg.a_map], &full[stage], a_c0, a_c1);
+                            tma_load_2d(st + 2 * C::a_bytes + C::b_bytes, &P.b_lo[sg.b_map], &full[stage], b_c0, b_c1);
+                        }
+                        if (++stage == C::stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc(BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+            int total_kb = 0;
+            if (!WGRAD) {
+                for (int s = 0; s < P.n_seg; ++s) total_kb += P.seg[s].k_blocks;
+            } else {
+                const int split = (tile / tiles_mn) % P.split_k;
+                int kb0, kb1;
+                k_range(split, kb0, kb1);
+                total_kb = kb1 - kb0;
+            }
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tempty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(smem + stage * C::stage_bytes);
+                    const uint64_t da_hi = make_smem_desc(st);
+                    const uint64_t db_hi = make_smem_desc(st + C::planes * C::a_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    if (C::planes == 2) {
+                        const uint64_t da_lo = make_smem_desc(st + C::a_bytes);
+                        const uint64_t db_lo = make_smem_desc(st + 2 * C::a_bytes + C::b_bytes);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                            umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&empty[stage]);                       // smem slot reusable once these MMAs retire
+                    if (kb == total_kb - 1) tc_commit(&tfull[as]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == C::stages) { stage = 0; phase ^= 1; }
+            }
+            if (total_kb == 0 && elect_one()) tc_commit(&tfull[as]);
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------------------------------ epilogue
+        const int q = warp - 4;                      // TMEM lane quarter of this warp (warp % 4)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+            int mn = tile, tap = 0, split = 0;
+            if (WGRAD) { mn = tile % tiles_mn; const int ts = tile / tiles_mn; tap = ts / P.split_k; split = ts % P.split_k; }
+            const int m_blk = mn / P.n_tiles, n_blk = mn % P.n_tiles;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const int row = m_blk * BM + q * 32 + lane;
+            bool has_acc = true;
+            if (WGRAD) { int kb0, kb1; k_range(split, kb0, kb1); has_acc = kb1 > kb0; }
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), v);
+                const int n0 = n_blk * BN + c;
+                if (WGRAD) {
+                    if (has_acc) epi_wgrad<32>(P.epi, tap, row, n0, v);
+                } else {
+                    if (n0 < P.epi.N || KIND == EPI_RS || KIND == EPI_START || KIND == EPI_IN)
+                        epi_apply<MODE, KIND, 32>(P.epi, row, n0, v);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    }
+    return fn;
+}
+
+// bf16 matrix [outer][inner] with row pitch ld elements; box = 64 x box_rows, 128B swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
+    EncodeFn enc = get_encode();
+    RADMMM_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    RADMMM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, "gemm_tc: operand not 16-byte aligned");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RADMMM_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with code %d (inner=%lld outer=%lld ld=%lld box=%d)",
+                   (int)r, inner, outer, ld, box_rows);
+    return RADMMM_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int MODE, int KIND, int BN, bool WGRAD>
+static int launch_inst(const TcParams& P, int n_tiles_total, cudaStream_t st) {
+    using C = Cfg<MODE, BN>;
+    auto kern = gemm_tc_kernel<MODE, KIND, BN, WGRAD>;
+    static bool configured = false;
+    if (!configured) {
+        RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+        configured = true;
+    }
+    int grid = n_tiles_total < sm_count() ? n_tiles_total : sm_count();
+    if (grid < 1) grid = 1;
+    kern<<<grid, kThreads, C::smem_bytes, st>>>(P);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+template <int MODE, int BN>
+static int launch_kind(const TcParams& P, int n_tiles_total, bool wgrad, cudaStream_t st) {
+    if (wgrad) return launch_inst<MODE, EPI_WGRAD, BN, true>(P, n_tiles_total, st);
+    switch (P.epi.kind) {
+        case EPI_START: return launch_inst<MODE, EPI_START, BN, false>(P, n_tiles_total, st);
+        case EPI_IN: return launch_inst<MODE, EPI_IN, BN, false>(P, n_tiles_total, st);
+        case EPI_RS: return launch_inst<MODE, EPI_RS, BN, false>(P, n_tiles_total, st);
+        case EPI_END: return launch_inst<MODE, EPI_END, BN, false>(P, n_tiles_total, st);
+        case EPI_DOUT: return launch_inst<MODE, EPI_DOUT, BN, false>(P, n_tiles_total, st);
+        case EPI_DH: return launch_inst<MODE, EPI_DH, BN, false>(P, n_tiles_total, st);
+        case EPI_DH0: return launch_inst<MODE, EPI_DH0, BN, false>(P, n_tiles_total, st);
+        case EPI_DZ0: return launch_inst<MODE, EPI_DZ0, BN, false>(P, n_tiles_total, st);
+        case EPI_DCTX: return launch_inst<MODE, EPI_DCTX, BN, false>(P, n_tiles_total, st);
+        case EPI_F32: return launch_inst<MODE, EPI_F32, BN, false>(P, n_tiles_total, st);
+    }
+    set_error("gemm_tc: unknown epilogue kind %d", P.epi.kind);
+    return RADMMM_ERR_ARG;
+}
+
+struct MapKey { const void* ptr; long long ld, plane; };
+
+}  // namespace
+
+int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
+    RADMMM_REQUIRE(mode == MODE_BF16 || mode == MODE_BF16X3, "gemm_tc: bad mode %d", mode);
+    RADMMM_REQUIRE(args.R % BM == 0, "gemm_tc: R=%d must be a multiple of %d", args.R, BM);
+    RADMMM_REQUIRE(args.n_seg >= 1 && args.n_seg <= kMaxSeg, "gemm_tc: bad segment count %d", args.n_seg);
+    const bool x3 = mode == MODE_BF16X3;
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.epi = args.epi;
+    P.n_seg = args.n_seg;
+
+    // output tiling
+    const int N = args.epi.N;
+    const int n_pad = (int)round_up(N, 128);
+    const int BN = (!x3 && n_pad % 256 == 0) ? 256 : 128;
+    P.n_tiles = n_pad / BN;
+    int n_tiles_total;
+
+    MapKey a_keys[kMaxMaps], b_keys[kMaxMaps];
+    int n_a = 0, n_b = 0;
+    auto find_or_add = [&](MapKey* keys, int& n, const void* ptr, long long ld, long long plane) -> int {
+        for (int i = 0; i < n; ++i)
+            if (keys[i].ptr == ptr && keys[i].ld == ld && keys[i].plane == plane) return i;
+        if (n == kMaxMaps) return -1;
+        keys[n] = MapKey{ptr, ld, plane};
+        return n++;
+    };
+
+    if (!args.wgrad) {
+        P.m_tiles = args.R / BM;
+        n_tiles_total = P.m_tiles * P.n_tiles;
+        // B maps: segments whose weight matrices sit in one allocation (same ld / plane stride, row-aligned offsets)
+        // share a map anchored at the lowest pointer; the segment carries its row offset.
+        for (int s = 0; s < args.n_seg; ++s) {
+            const GemmSeg& g = args.seg[s];
+            RADMMM_REQUIRE(g.K % BK == 0 && g.K > 0, "gemm_tc: segment K=%d must be a positive multiple of %d", g.K, BK);
+            RADMMM_REQUIRE(g.a.ptr && g.w.ptr, "gemm_tc: null operand");
+            int ai = find_or_add(a_keys, n_a, g.a.ptr, g.a.ld, g.a.plane_stride);
+            RADMMM_REQUIRE(ai >= 0, "gemm_tc: too many distinct A operands");
+            int bi = -1, row_off = 0;
+            for (int i = 0; i < n_b; ++i) {
+                if (b_keys[i].ld != g.w.ld || b_keys[i].plane != g.w.plane_stride) continue;
+                const long long diff = (const char*)g.w.ptr - (const char*)b_keys[i].ptr;
+                const long long row_bytes = g.w.ld * 2;
+                if (diff % row_bytes == 0 && diff >= 0 && diff / row_bytes < (1 << 24)) {
+                    bi = i; row_off = (int)(diff / row_bytes);
+                    break;
+                }
+            }
+            if (bi < 0) {
+                bi = find_or_add(b_keys, n_b, g.w.ptr, g.w.ld, g.w.plane_stride);
+                RADMMM_REQUIRE(bi >= 0, "gemm_tc: too many distinct B operands");
+            }
+            P.seg[s] = TcSeg{ai, bi, g.shift, row_off, g.K / BK};
+        }
+        // NB the B-map sharing above requires the anchor to be the LOWEST address; callers list segments in
+        // ascending weight order (the WN builders do).  Outer extents: A = R rows exactly (zero fill beyond), B large.
+        for (int i = 0; i < n_a; ++i) {
+            long long kmax = 0;
+            for (int s = 0; s < args.n_seg; ++s) if (P.seg[s].a_map == i) kmax = kmax > args.seg[s].K ? kmax : args.seg[s].K;
+            RADMMM_TRY(make_map(&P.a_hi[i], a_keys[i].ptr, kmax, args.R, a_keys[i].ld, BM));
+            if (x3) RADMMM_TRY(make_map(&P.a_lo[i], (const __nv_bfloat16*)a_keys[i].ptr + a_keys[i].plane, kmax, args.R, a_keys[i].ld, BM));
+        }
+        for (int i = 0; i < n_b; ++i) {
+            long long kmax = 0, rows = 0;
+            for (int s = 0; s < args.n_seg; ++s)
+                if (P.seg[s].b_map == i) {
+                    kmax = kmax > args.seg[s].K ? kmax : args.seg[s].K;
+                    const long long need = (long long)P.seg[s].b_row_off + n_pad;
+                    rows = rows > need ? rows : need;
+                }
+            RADMMM_TRY(make_map(&P.b_hi[i], b_keys[i].ptr, kmax, rows, b_keys[i].ld, BN));
+            if (x3) RADMMM_TRY(make_map(&P.b_lo[i], (const __nv_bfloat16*)b_keys[i].ptr + b_keys[i].plane, kmax, rows, b_keys[i].ld, BN));
+        }
+    } else {
+        // weight-grad: A = dY^T [M][R], B = X^T [N][R]; one output tile set per tap, K = rows split in split_k ranges
+        const GemmSeg& g0 = args.seg[0];
+        RADMMM_REQUIRE(g0.aT.ptr && g0.wT.ptr, "gemm_tc: weight-grad needs the transposed operand copies");
+        const int M = args.epi.M;
+        P.m_tiles = cdiv(M, BM);
+        P.taps = args.n_seg;
+        P.k_blocks_total = args.R / BK;
+        // split K (= rows) so that the persistent grid sees >= ~4 tiles per SM while every tile keeps >= 8 K blocks
+        const int tiles0 = P.m_tiles * P.n_tiles * P.taps;
+        int split = args.split_k;
+        if (split < 1) {
+            split = cdiv(4 * sm_count(), tiles0);
+            const int max_split = P.k_blocks_total / 8 > 1 ? P.k_blocks_total / 8 : 1;
+            if (split > max_split) split = max_split;
+        }
+        if (split > P.k_blocks_total) split = P.k_blocks_total;
+        if (split < 1) split = 1;
+        {   // no empty ranges
+            const int per = cdiv(P.k_blocks_total, split);
+            split = cdiv(P.k_blocks_total, per);
+        }
+        P.split_k = split;
+        n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
+        RADMMM_REQUIRE(split == 1 || args.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
+        const long long a_rows = g0.aT.plane_stride / g0.aT.ld, b_rows = g0.wT.plane_stride / g0.wT.ld;
+        RADMMM_TRY(make_map(&P.a_hi[0], g0.aT.ptr, args.R, a_rows, g0.aT.ld, BM));
+        RADMMM_TRY(make_map(&P.b_hi[0], g0.wT.ptr, args.R, b_rows, g0.wT.ld, BN));
+        if (x3) {
+            RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.aT.ptr + g0.aT.plane_stride, args.R, a_rows, g0.aT.ld, BM));
+            RADMMM_TRY(make_map(&P.b_lo[0], (const __nv_bfloat16*)g0.wT.ptr + g0.wT.plane_stride, args.R, b_rows, g0.wT.ld, BN));
+        }
+        for (int s = 0; s < args.n_seg; ++s) {
+            RADMMM_REQUIRE(args.seg[s].aT.ptr == g0.aT.ptr && args.seg[s].wT.ptr == g0.wT.ptr, "gemm_tc: weight-grad taps must share operands");
+            P.seg[s] = TcSeg{0, 0, 0, args.seg[s].shift, P.k_blocks_total};
+        }
+        n_a = n_b = 1;
+    }
+    P.n_a_maps = n_a;
+    P.n_b_maps = n_b;
+
+    if (x3) return launch_kind<MODE_BF16X3, 128>(P, n_tiles_total, args.wgrad != 0, stream);
+    if (BN == 256) return launch_kind<MODE_BF16, 256>(P, n_tiles_total, args.wgrad != 0, stream);
+    return launch_kind<MODE_BF16, 128>(P, n_tiles_total, args.wgrad != 0, stream);
+}
+
+}  // namespace radmmm

@@ -1,0 +1,67 @@
+"""Flow negative log-likelihood (reference: loss.py:85-110 ``compute_flow_loss`` and the flow part of
+``RADMMMLoss.forward``, loss.py:518-538) on masked-sum reduction kernels (fp64 accumulation, warp shuffles)."""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+
+class _MaskedSum(torch.autograd.Function):
+    """sum over t < len_b of x (square=False) or x^2 (square=True), x: (B, C, T)."""
+
+    @staticmethod
+    def forward(ctx, x, lens, square: bool):
+        lib = N.lib()
+        x = x.contiguous().float()
+        b, c, t = x.shape
+        out = torch.zeros(1, dtype=torch.float64, device=x.device)
+        N.check(lib.radmmm_masked_sum(N.fptr(x), N.ptr(lens), b, c, t, int(square), N.ptr(out), N.stream()))
+        ctx.save_for_backward(x, lens)
+        ctx.square = square
+        return out.float().reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = N.lib()
+        x, lens = ctx.saved_tensors
+        b, c, t = x.shape
+        dx = torch.empty_like(x)
+        coef = g.reshape(1).float().contiguous()
+        N.check(lib.radmmm_masked_sum_backward(N.fptr(x), N.ptr(lens), b, c, t, int(ctx.square), N.fptr(coef), 1.0,
+                                               N.fptr(dx), N.stream()))
+        return dx, None, None
+
+
+def flow_nll(z, log_det_W_list, log_s_list, lens_g, sigma: float = 1.0):
+    """(loss, loss_prior) of loss.py:85-110 from grouped lengths instead of a dense mask."""
+    lens = lens_g.to(device=z.device, dtype=torch.int32).contiguous()
+    n = lens.sum().to(torch.float32)
+    log_s_total = sum(_MaskedSum.apply(ls, lens, False) for ls in log_s_list)
+    log_det_total = sum(log_det_W_list) * n if len(log_det_W_list) else 0.0
+    prior = _MaskedSum.apply(z, lens, True) / (2 * sigma * sigma)
+    denom = n * z.size(1)
+    return (prior - log_s_total - log_det_total) / denom, prior / denom
+
+
+def compute_flow_loss(z, log_det_W_list, log_s_list, n_elements, n_dims, mask, sigma=1.0):
+    """Same signature as the reference (loss.py:85).  ``mask`` is the (B,1,T') prefix mask; lengths are recovered
+    from it.  Unlike the reference, ``log_det_W_list[0]`` is NOT modified in place."""
+    lens = mask.reshape(mask.shape[0], -1).sum(1).to(torch.int32)
+    return flow_nll(z, list(log_det_W_list), log_s_list, lens, sigma)
+
+
+class RADMMMFlowLoss(torch.nn.Module):
+    """Flow part of RADMMMLoss (loss.py:500-538): {'loss_mel': (loss, 1.0), 'loss_prior_mel': (prior, 0.0)}."""
+
+    def __init__(self, sigma=1.0, n_group_size=1):
+        super().__init__()
+        self.sigma = sigma
+        self.n_group_size = n_group_size
+
+    def forward(self, model_output, out_lens):
+        lengths = out_lens.lengths if hasattr(out_lens, "lengths") else out_lens
+        lens_g = torch.div(lengths, self.n_group_size, rounding_mode="floor")
+        loss, prior = flow_nll(model_output["z_mel"], model_output["log_det_W_list"], model_output["log_s_list"],
+                               lens_g, self.sigma)
+        return {"loss_mel": (loss, 1.0), "loss_prior_mel": (prior, 0.0)}
