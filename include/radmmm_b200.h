@@ -79,7 +79,7 @@ typedef struct radmmm_flow_desc {
      * caller, filled by radmmm_flow_prepare() whenever the raw parameters changed */
     void* prepared;
     /* conditioning in row layout, produced once per step by radmmm_context_rows() */
-    const void* ctx_rows; const void* ctx_rows_T;
+    const void* ctx_rows;
     /* per-call activation workspace (radmmm_flow_workspace_bytes()); must outlive backward when training */
     void* workspace;
 } radmmm_flow_desc;
@@ -87,7 +87,7 @@ typedef struct radmmm_flow_desc {
 size_t radmmm_flow_prepared_bytes(int mode, int C, int D, int H, int L);
 size_t radmmm_flow_workspace_bytes(int mode, int training, int B, int Tp, int C, int D, int H, int L);
 size_t radmmm_flow_backward_scratch_bytes(int mode, int B, int Tp, int C, int D, int H, int L);
-size_t radmmm_context_rows_bytes(int mode, int B, int Tp, int D, int transposed);
+size_t radmmm_context_rows_bytes(int mode, int B, int Tp, int D);
 
 /* weight norm + layout.  Replaces the per-forward aten::_weight_norm_interface of nn.utils.weight_norm
  * (common.py:174,791,813). */
@@ -95,7 +95,7 @@ int radmmm_flow_prepare(const radmmm_flow_desc* d, void* stream);
 
 /* context (B, Tp, D) fp32 [the bi-LSTM output of models/radmmm.py:137-146 before its transpose] -> row layout */
 int radmmm_context_rows(int mode, const float* ctx_btd, const int32_t* lens, int B, int Tp, int D,
-                        void* rows, void* rows_T, void* stream);
+                        void* rows, void* stream);
 /* gradient rows (fp32 [R][Dp]) -> (B, Tp, D) fp32, accumulate != 0 adds */
 int radmmm_context_rows_backward(const float* drows, const int32_t* lens, int B, int Tp, int D, float* dctx_btd,
                                  int accumulate, void* stream);
@@ -145,10 +145,10 @@ int radmmm_conv_rows(int mode, const void* x_rows, long long x_ld, long long x_p
                      long long w_plane, long long w_tap_stride, const float* bias, float* y, long long y_ld, int R,
                      int K, int N, int taps, int dilation, void* stream);
 /* Weight-gradient GEMM on rows (testing): out[tap][m][n] = sum_r dy[r][m] * x[r + (tap - taps/2)*dilation][n].
- * dy / x are act-format row matrices; dyT / xT their transposed copies ([M][R] / [N][R], needed by the tensor-core
- * modes, NULL for RADMMM_MODE_F32).  `out` (fp32, [taps][M][out_ld]) is zeroed by the call. */
-int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_plane, const void* dyT, const void* x,
-                      long long x_ld, long long x_plane, const void* xT, float* out, long long out_ld,
+ * dy [R][M] / x [R][N] are act-format row matrices (M, N multiples of 128 in the tensor-core modes).
+ * `out` (fp32, [taps][M][out_ld]) is zeroed by the call. */
+int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_plane, const void* x,
+                      long long x_ld, long long x_plane, float* out, long long out_ld,
                       long long out_tap_stride, int R, int M, int N, int taps, int dilation, void* stream);
 /* fp32 rows -> act-format rows of `mode` (hi/lo split for BF16X3) */
 int radmmm_cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, void* stream);

@@ -34,7 +34,7 @@ class FlowDesc(C.Structure):
         ("end_w", _fp), ("end_b", _fp),
         ("W", _fp), ("W_inv", _fp), ("W_T", _fp), ("mean", _fp),
         ("prepared", _fp),
-        ("ctx_rows", _fp), ("ctx_rows_T", _fp),
+        ("ctx_rows", _fp),
         ("workspace", _fp),
     ]
 
@@ -62,9 +62,9 @@ SIGNATURES = {
     "radmmm_flow_prepared_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "radmmm_flow_workspace_bytes": (_sz, [_i] * 8),
     "radmmm_flow_backward_scratch_bytes": (_sz, [_i] * 7),
-    "radmmm_context_rows_bytes": (_sz, [_i] * 5),
+    "radmmm_context_rows_bytes": (_sz, [_i] * 4),
     "radmmm_flow_prepare": (_i, [_P(FlowDesc), _fp]),
-    "radmmm_context_rows": (_i, [_i, _fp, _fp, _i, _i, _i, _fp, _fp, _fp]),
+    "radmmm_context_rows": (_i, [_i, _fp, _fp, _i, _i, _i, _fp, _fp]),
     "radmmm_context_rows_backward": (_i, [_fp, _fp, _i, _i, _i, _fp, _i, _fp]),
     "radmmm_flow_forward": (_i, [_P(FlowDesc), _fp, _fp, _fp, _fp, _fp, _fp]),
     "radmmm_flow_inverse": (_i, [_P(FlowDesc), _fp, _fp, _fp, _fp, _fp]),
@@ -76,7 +76,7 @@ SIGNATURES = {
     "radmmm_masked_sum": (_i, [_fp, _fp, _i, _i, _i, _i, _fp, _fp]),
     "radmmm_masked_sum_backward": (_i, [_fp, _fp, _i, _i, _i, _i, _fp, _f, _fp, _fp]),
     "radmmm_conv_rows": (_i, [_i, _fp, _ll, _ll, _fp, _ll, _ll, _ll, _fp, _fp, _ll, _i, _i, _i, _i, _i, _fp]),
-    "radmmm_wgrad_rows": (_i, [_i, _fp, _ll, _ll, _fp, _fp, _ll, _ll, _fp, _fp, _ll, _ll, _i, _i, _i, _i, _i, _fp]),
+    "radmmm_wgrad_rows": (_i, [_i, _fp, _ll, _ll, _fp, _ll, _ll, _fp, _ll, _ll, _i, _i, _i, _i, _i, _fp]),
     "radmmm_cast_rows": (_i, [_i, _fp, _ll, _fp, _ll, _fp]),
     "radmmm_spline_forward": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _i, _fp]),
     "radmmm_spline_backward": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _fp]),

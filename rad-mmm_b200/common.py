@@ -77,11 +77,8 @@ class _ContextRows:
         lib = N.lib()
         b, tp, d = ctx_btd.shape
         self.key = (ctx_btd.data_ptr(), ctx_btd._version, tuple(ctx_btd.shape), mode, lens.data_ptr(), lens._version)
-        self.rows = torch.empty(lib.radmmm_context_rows_bytes(mode, b, tp, d, 0), dtype=torch.uint8, device=ctx_btd.device)
-        nt = lib.radmmm_context_rows_bytes(mode, b, tp, d, 1)
-        self.rows_T = torch.empty(nt, dtype=torch.uint8, device=ctx_btd.device) if nt else None
-        N.check(lib.radmmm_context_rows(mode, N.fptr(ctx_btd), N.ptr(lens), b, tp, d, N.ptr(self.rows),
-                                        N.ptr(self.rows_T), N.stream()))
+        self.rows = torch.empty(lib.radmmm_context_rows_bytes(mode, b, tp, d), dtype=torch.uint8, device=ctx_btd.device)
+        N.check(lib.radmmm_context_rows(mode, N.fptr(ctx_btd), N.ptr(lens), b, tp, d, N.ptr(self.rows), N.stream()))
 
 
 _ctx_cache: List[_ContextRows] = []
@@ -257,7 +254,7 @@ class FlowStepFunction(torch.autograd.Function):
         wn.fill_desc(d, plist)
         prepared = wn.prepared(d, plist)
         rows = _context_rows(ctx_btd, lens, mode)
-        d.ctx_rows, d.ctx_rows_T = N.ptr(rows.rows), N.ptr(rows.rows_T)
+        d.ctx_rows = N.ptr(rows.rows)
         ws = torch.empty(lib.radmmm_flow_workspace_bytes(mode, int(training), batch, tp, chans, d.D, d.H, d.L),
                          dtype=torch.uint8, device=z.device)
         d.workspace = N.ptr(ws)
@@ -286,7 +283,7 @@ class FlowStepFunction(torch.autograd.Function):
         d = _make_desc(wn, mode, batch, chans, tp, ctx.scaling_fn, True, lens)
         wn.fill_desc(d, plist)
         d.prepared = N.ptr(ctx.prepared_buf)
-        d.ctx_rows, d.ctx_rows_T = N.ptr(ctx.rows.rows), N.ptr(ctx.rows.rows_T)
+        d.ctx_rows = N.ptr(ctx.rows.rows)
         d.workspace = N.ptr(ctx.ws)
         W_T = W.t().contiguous() if ctx.has_W else None
         d.W, d.W_T, d.mean = (N.fptr(W) if ctx.has_W else None), N.fptr(W_T), (N.fptr(mean) if ctx.has_mean else None)
@@ -340,7 +337,7 @@ def _flow_apply(wn: WN, W, W_inv, mean, z, context, seq_lens, scaling_fn: str, p
             wn.fill_desc(d, params)
             wn.prepared(d, params)
             rows = _context_rows(ctx_btd, lens, mode)
-            d.ctx_rows, d.ctx_rows_T = N.ptr(rows.rows), N.ptr(rows.rows_T)
+            d.ctx_rows = N.ptr(rows.rows)
             ws = torch.empty(lib.radmmm_flow_workspace_bytes(mode, 0, batch, tp, chans, d.D, d.H, d.L),
                              dtype=torch.uint8, device=z.device)
             d.workspace = N.ptr(ws)

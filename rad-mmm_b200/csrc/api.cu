@@ -32,8 +32,8 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
 size_t flow_prepared_bytes(int mode, int C, int D, int H, int L);
 size_t flow_workspace_bytes(int mode, int training, int B, int Tp, int C, int D, int H, int L);
 size_t flow_scratch_bytes(int mode, int B, int Tp, int C, int D, int H, int L);
-size_t context_rows_bytes(int mode, int B, int Tp, int D, int transposed);
-int context_rows(int mode, const float* ctx_btd, const int* lens, int B, int Tp, int D, void* rows, void* rows_T, cudaStream_t st);
+size_t context_rows_bytes(int mode, int B, int Tp, int D);
+int context_rows(int mode, const float* ctx_btd, const int* lens, int B, int Tp, int D, void* rows, cudaStream_t st);
 int context_rows_backward(const float* drows, const int* lens, int B, int Tp, int D, float* dctx, int accumulate, cudaStream_t st);
 
 template <int MODE>
@@ -74,13 +74,11 @@ size_t radmmm_flow_workspace_bytes(int mode, int training, int B, int Tp, int C,
 size_t radmmm_flow_backward_scratch_bytes(int mode, int B, int Tp, int C, int D, int H, int L) {
     return flow_scratch_bytes(mode, B, Tp, C, D, H, L);
 }
-size_t radmmm_context_rows_bytes(int mode, int B, int Tp, int D, int transposed) {
-    return context_rows_bytes(mode, B, Tp, D, transposed);
-}
+size_t radmmm_context_rows_bytes(int mode, int B, int Tp, int D) { return context_rows_bytes(mode, B, Tp, D); }
 int radmmm_flow_prepare(const radmmm_flow_desc* d, void* stream) { return flow_prepare(d, ST(stream)); }
 int radmmm_context_rows(int mode, const float* ctx_btd, const int32_t* lens, int B, int Tp, int D, void* rows,
-                        void* rows_T, void* stream) {
-    return context_rows(mode, ctx_btd, lens, B, Tp, D, rows, rows_T, ST(stream));
+                        void* stream) {
+    return context_rows(mode, ctx_btd, lens, B, Tp, D, rows, ST(stream));
 }
 int radmmm_context_rows_backward(const float* drows, const int32_t* lens, int B, int Tp, int D, float* dctx_btd,
                                  int accumulate, void* stream) {
@@ -148,14 +146,13 @@ int radmmm_conv_rows(int mode, const void* x_rows, long long x_ld, long long x_p
         GemmSeg& s = a.seg[a.n_seg++];
         s.a.ptr = const_cast<void*>(x_rows); s.a.ld = x_ld; s.a.plane_stride = x_plane;
         s.w.ptr = (char*)const_cast<void*>(w) + (size_t)j * w_tap_stride * es; s.w.ld = w_ld; s.w.plane_stride = w_plane;
-        s.aT.ptr = nullptr; s.wT.ptr = nullptr;
         s.K = K;
         s.shift = (j - taps / 2) * dilation;
     }
     return launch_gemm(a, mode, ST(stream));
 }
-int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_plane, const void* dyT, const void* x,
-                      long long x_ld, long long x_plane, const void* xT, float* out, long long out_ld,
+int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_plane, const void* x,
+                      long long x_ld, long long x_plane, float* out, long long out_ld,
                       long long out_tap_stride, int R, int M, int N, int taps, int dilation, void* stream) {
     RADMMM_REQUIRE(mode >= 0 && mode <= 2, "wgrad_rows: bad mode %d", mode);
     RADMMM_REQUIRE(taps >= 1 && taps <= kMaxSeg && taps % 2 == 1, "wgrad_rows: taps=%d must be odd and <= %d", taps, kMaxSeg);
@@ -175,9 +172,7 @@ int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_pl
     for (int j = 0; j < taps; ++j) {
         GemmSeg& s = a.seg[a.n_seg++];
         s.a.ptr = const_cast<void*>(dy); s.a.ld = dy_ld; s.a.plane_stride = dy_plane;
-        s.aT.ptr = const_cast<void*>(dyT); s.aT.ld = R; s.aT.plane_stride = dy_plane;
         s.w.ptr = const_cast<void*>(x); s.w.ld = x_ld; s.w.plane_stride = x_plane;
-        s.wT.ptr = const_cast<void*>(xT); s.wT.ld = R; s.wT.plane_stride = x_plane;
         s.K = R;
         s.shift = (j - taps / 2) * dilation;
         RADMMM_CUDA(cudaMemset2DAsync(out + j * out_tap_stride, sizeof(float) * out_ld, 0, sizeof(float) * N, M, ST(stream)));

@@ -7,12 +7,12 @@
 namespace radmmm {
 
 // =========================================================================================================
-// cf (B, C, Tp) fp32  ->  act rows [R][ld] (+ transposed copy [ld][R]); invalid rows and pad columns are zero.
+// cf (B, C, Tp) fp32  ->  act rows [R][ld]; invalid rows and pad columns are zero.
 // 32x32 tile transpose through shared memory: reads coalesced along t, row writes coalesced along c.
 // =========================================================================================================
 template <int MODE>
 __global__ void rows_from_cf_kernel(const float* __restrict__ src, long long batch_stride, int n_ch, RowGeom g,
-                                    ActMat dst, ActMat dstT, int n_cols, int mask_invalid) {
+                                    ActMat dst, int n_cols, int mask_invalid) {
     __shared__ float tile[32][33];
     const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
@@ -24,7 +24,6 @@ __global__ void rows_from_cf_kernel(const float* __restrict__ src, long long bat
         const bool ok = mask_invalid ? (t < len) : (b < g.B && t < g.Tp);
         if (c < n_ch && ok) v = src[(long long)b * batch_stride + (long long)c * g.Tp + t];
         tile[i][tx] = v;
-        if (dstT.ptr && c < n_cols) act_store<MODE>(dstT, (long long)c * dstT.ld + r, v);
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -34,22 +33,20 @@ __global__ void rows_from_cf_kernel(const float* __restrict__ src, long long bat
 }
 
 int rows_from_cf(int mode, const float* src, long long batch_stride, int n_ch, const RowGeom& g, ActMat dst,
-                 ActMat dstT, int n_cols, int mask_invalid, cudaStream_t st) {
+                 int n_cols, int mask_invalid, cudaStream_t st) {
     dim3 grid(g.R / 32, cdiv(n_cols, 32)), block(32, 8);
-    if (mode == MODE_F32) rows_from_cf_kernel<MODE_F32><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, dstT, n_cols, mask_invalid);
-    else if (mode == MODE_BF16) rows_from_cf_kernel<MODE_BF16><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, dstT, n_cols, mask_invalid);
-    else rows_from_cf_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, dstT, n_cols, mask_invalid);
+    if (mode == MODE_F32) rows_from_cf_kernel<MODE_F32><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, n_cols, mask_invalid);
+    else if (mode == MODE_BF16) rows_from_cf_kernel<MODE_BF16><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, n_cols, mask_invalid);
+    else rows_from_cf_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(src, batch_stride, n_ch, g, dst, n_cols, mask_invalid);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }
 
 // =========================================================================================================
-// fp32 (B, Tp, D) (the context bi-LSTM output, channels-last)  ->  act rows [R][ld] (+ transposed copy)
+// fp32 (B, Tp, D) (the context bi-LSTM output, channels-last)  ->  act rows [R][ld]
 // =========================================================================================================
 template <int MODE>
-__global__ void rows_from_btd_kernel(const float* __restrict__ src, int D, RowGeom g, ActMat dst, ActMat dstT,
-                                     int n_cols) {
-    __shared__ float tile[32][33];
+__global__ void rows_from_btd_kernel(const float* __restrict__ src, int D, RowGeom g, ActMat dst, int n_cols) {
     const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
     for (int i = ty; i < 32; i += 8) {
@@ -58,23 +55,15 @@ __global__ void rows_from_btd_kernel(const float* __restrict__ src, int D, RowGe
         row_decode(g, r, b, t, len);
         float v = 0.0f;
         if (c < D && t < len) v = src[((long long)b * g.Tp + t) * D + c];
-        tile[i][tx] = v;
         if (c < n_cols) act_store<MODE>(dst, (long long)r * dst.ld + c, v);
-    }
-    if (dstT.ptr == nullptr) return;
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + tx;
-        if (c < n_cols) act_store<MODE>(dstT, (long long)c * dstT.ld + r, tile[tx][i]);
     }
 }
 
-int rows_from_btd(int mode, const float* src, int D, const RowGeom& g, ActMat dst, ActMat dstT, int n_cols,
-                  cudaStream_t st) {
+int rows_from_btd(int mode, const float* src, int D, const RowGeom& g, ActMat dst, int n_cols, cudaStream_t st) {
     dim3 grid(g.R / 32, cdiv(n_cols, 32)), block(32, 8);
-    if (mode == MODE_F32) rows_from_btd_kernel<MODE_F32><<<grid, block, 0, st>>>(src, D, g, dst, dstT, n_cols);
-    else if (mode == MODE_BF16) rows_from_btd_kernel<MODE_BF16><<<grid, block, 0, st>>>(src, D, g, dst, dstT, n_cols);
-    else rows_from_btd_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(src, D, g, dst, dstT, n_cols);
+    if (mode == MODE_F32) rows_from_btd_kernel<MODE_F32><<<grid, block, 0, st>>>(src, D, g, dst, n_cols);
+    else if (mode == MODE_BF16) rows_from_btd_kernel<MODE_BF16><<<grid, block, 0, st>>>(src, D, g, dst, n_cols);
+    else rows_from_btd_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(src, D, g, dst, n_cols);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }

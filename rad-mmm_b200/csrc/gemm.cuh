@@ -4,7 +4,8 @@
 //     A_seg are act matrices over rows (activations / gradients, [R][K_seg]); rows outside [0,R) read as zero.
 //     W_seg are prepared weights [N_pad][K_seg], K-major.  A k=5 dilated conv is 5 segments with row shifts
 //     (j-2)*d; the WN start conv is 2 segments (z0 | context); the fused dgrad of a layer is 6 segments.
-// "Weight-grad GEMM":  D_tap[m][n] = sum_r dY[r][m] * X[r + shift_tap][n]                 (K = rows)
+// "Weight-grad GEMM":  D_tap[m][n] = sum_r dY[r][m] * X[r + shift_tap][n]                 (K = rows; both operands
+//     are read from the same row matrices -- MN-major UMMA operands on the tensor-core path, no transposed copies)
 //
 // The epilogue (one of EPI_*) consumes the fp32 accumulators while they are still on chip.
 #pragma once
@@ -31,9 +32,7 @@ constexpr int kMaxLayers = 8;
 
 struct GemmSeg {
     ActMat a;        // rows operand [R][K]   (weight-grad: dY [R][M])
-    ActMat aT;       // transposed copy [K][R] (weight-grad on tensor cores: dY^T [M][R]); may be null in MODE_F32
     ActMat w;        // weights [N_pad][K]    (weight-grad: X [R][N])
-    ActMat wT;       // (weight-grad on tensor cores: X^T [N][R])
     int K;           // contraction length of this segment (multiple of 64)
     int shift;       // row shift applied to A (row GEMM) / to X (weight-grad GEMM)
 };
@@ -46,13 +45,13 @@ struct EpiParams {
     const float* bias;           // [N] or null
     int dilation;
     int first, last, accumulate, n_layers;
-    ActMat out0, out0T, out1, out1T;
+    ActMat out0, out1;
     float* f32_out;
     long long f32_ld;
     long long f32_tap_stride;    // weight-grad: elements between taps
     const float* padq;
     ActMat sig[kMaxLayers];
-    ActMat dq[kMaxLayers], dqT[kMaxLayers];
+    ActMat dq[kMaxLayers];
     ActMat h;
     float* cf_out;               // channels-first (B, cf_C, Tp) fp32
     int cf_C, cf_c0;
@@ -106,13 +105,6 @@ __device__ __forceinline__ void store_row_vec(const ActMat& m, int r, int n0, co
 }
 
 template <int MODE, int NV>
-__device__ __forceinline__ void store_col_vec(const ActMat& mT, int r, int n0, const float* v) {
-    if (mT.ptr == nullptr) return;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) act_store<MODE>(mT, (long long)(n0 + i) * mT.ld + r, v[i]);
-}
-
-template <int MODE, int NV>
 __device__ __forceinline__ void load_row_vec(const ActMat& m, int r, int n0, float* v) {
     long long idx = (long long)r * m.ld + n0;
     if constexpr (MODE == MODE_F32) {
@@ -138,13 +130,11 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, flo
 #pragma unroll
         for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] + __ldg(p.bias + n0 + i) : 0.0f;
         store_row_vec<MODE, NV>(p.out0, r, n0, out);
-        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
     } else if constexpr (KIND == EPI_IN) {
         const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) out[i] = valid ? softplus_f(acc[i] * ratio + __ldg(p.bias + n0 + i)) : 0.0f;
         store_row_vec<MODE, NV>(p.out0, r, n0, out);
-        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
     } else if constexpr (KIND == EPI_RS) {
         float s[NV];
 #pragma unroll
@@ -164,7 +154,6 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, flo
         }
         if (p.last) {
             store_row_vec<MODE, NV>(p.out1, r, n0, s);
-            store_col_vec<MODE, NV>(p.out1T, r, n0, s);
         }
     } else if constexpr (KIND == EPI_END || KIND == EPI_DZ0) {
         if (b < p.geom.B && t < p.geom.Tp) {
@@ -186,7 +175,6 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, flo
 #pragma unroll
             for (int i = 0; i < NV; ++i) out[i] = acc[i] * sg[i];
             store_row_vec<MODE, NV>(p.dq[l], r, n0, out);
-            store_col_vec<MODE, NV>(p.dqT[l], r, n0, out);
         }
     } else if constexpr (KIND == EPI_DH) {
         if (valid) {
@@ -200,12 +188,10 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, flo
             for (int i = 0; i < NV; ++i) out[i] = 0.0f;
         }
         store_row_vec<MODE, NV>(p.out0, r, n0, out);
-        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
     } else if constexpr (KIND == EPI_DH0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] : 0.0f;
         store_row_vec<MODE, NV>(p.out0, r, n0, out);
-        store_col_vec<MODE, NV>(p.out0T, r, n0, out);
     } else if constexpr (KIND == EPI_DCTX || KIND == EPI_F32) {
         float* o = p.f32_out + (long long)r * p.f32_ld + n0;
 #pragma unroll

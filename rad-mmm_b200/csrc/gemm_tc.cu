@@ -10,8 +10,9 @@
 // A k=5 dilated conv is five K-segments whose A boxes are the same activation matrix shifted by (j-2)*d rows
 // (TMA zero-fills rows outside [0,R); utterances are separated by >= 16 zero rows, so no tap crosses a sequence).
 // MODE_BF16X3 loads hi and lo planes of both operands and issues hi*hi + lo*hi + hi*lo into the same accumulator.
-// The weight-grad GEMM contracts over rows: both operands are the transposed ([channels][R]) copies, the tap shift
-// moves the K coordinate of the X box, and split-K partial tiles are reduced with fp32 atomics.
+// The weight-grad GEMM contracts over rows: dY [R][M] and X [R][N] are read as MN-major UMMA operands straight from the
+// row matrices (64-channel x 64-row boxes, 128B swizzle), so the tap shift is an outer (row) TMA coordinate and no
+// transposed copies exist; split-K partial tiles are reduced with fp32 atomics.
 // Roofline: tensor pipe (dense bf16, MEASURED_PEAKS.json); BF16X3 has one third of it.
 #include <cuda.h>
 #include "gemm.cuh"
@@ -111,6 +112,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// MN-major, 128B-swizzled operand tile (weight-grad): atoms of 64 channels (128 B) x 8 K-rows; atoms along K are
+// 1024 B apart (SBO), 64-channel atom columns are BK*128 B = 8192 B apart (LBO); one UMMA_K step = 16 K-rows = 2048 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((BK * 128) >> 4) << 16;            // leading byte offset: next 64-channel atom column
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next 8-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 B apart (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -122,8 +134,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int bn, bool mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 template <int MODE, int BN>
@@ -197,19 +210,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* st = smem + stage * C::stage_bytes;
                         mbar_expect_tx(&full[stage], C::stage_bytes);
-                        int a_c0, a_c1, b_c0, b_c1;
+                        uint8_t* sa_hi = st;
+                        uint8_t* sb_hi = st + C::planes * C::a_bytes;
+                        uint8_t* sa_lo = st + C::a_bytes;
+                        uint8_t* sb_lo = st + 2 * C::a_bytes + C::b_bytes;
                         if (!WGRAD) {
-                            a_c0 = kb * BK; a_c1 = m_blk * BM + sg.a_row_shift;
-                            b_c0 = kb * BK; b_c1 = n_blk * BN + sg.b_row_off;
+                            const int a_c0 = kb * BK, a_c1 = m_blk * BM + sg.a_row_shift;
+                            const int b_c0 = kb * BK, b_c1 = n_blk * BN + sg.b_row_off;
+                            tma_load_2d(sa_hi, &P.a_hi[sg.a_map], &full[stage], a_c0, a_c1);
+                            tma_load_2d(sb_hi, &P.b_hi[sg.b_map], &full[stage], b_c0, b_c1);
+                            if (C::planes == 2) {
+                                tma_load_2d(sa_lo, &P.a_lo[sg.a_map], &full[stage], a_c0, a_c1);
+                                tma_load_2d(sb_lo, &P.b_lo[sg.b_map], &full[stage], b_c0, b_c1);
+                            }
                         } else {
-                            a_c0 = kb * BK; a_c1 = m_blk * BM;
-                            b_c0 = kb * BK + sg.b_row_off; b_c1 = n_blk * BN;
-                        }
-                        tma_load_2d(st, &P.a_hi[sg.a_map], &full[stage], a_c0, a_c1);
-                        tma_load_2d(st + C::planes * C::a_bytes, &P.b_hi[sg.b_map], &full[stage], b_c0, b_c1);
-                        if (C::planes == 2) {
-                            tma_load_2d(st + C::a_bytes, &P.a_lo[sg.a_map], &full[stage], a_c0, a_c1);
-                            tma_load_2d(st + 2 * C::a_bytes + C::b_bytes, &P.b_lo[sg.b_map], &full[stage], b_c0, b_c1);
+                            // 64-channel x 64-row boxes; inner coordinate = channel, outer = row (tap shift on X)
+                            const int ra = kb * BK, rb = kb * BK + sg.b_row_off;
+#pragma unroll
+                            for (int i = 0; i < BM / 64; ++i) {
+                                tma_load_2d(sa_hi + i * (BK * 128), &P.a_hi[0], &full[stage], m_blk * BM + i * 64, ra);
+                                if (C::planes == 2) tma_load_2d(sa_lo + i * (BK * 128), &P.a_lo[0], &full[stage], m_blk * BM + i * 64, ra);
+                            }
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i) {
+                                tma_load_2d(sb_hi + i * (BK * 128), &P.b_hi[0], &full[stage], n_blk * BN + i * 64, rb);
+                                if (C::planes == 2) tma_load_2d(sb_lo + i * (BK * 128), &P.b_lo[0], &full[stage], n_blk * BN + i * 64, rb);
+                            }
                         }
                         if (++stage == C::stages) { stage = 0; phase ^= 1; }
                     }
@@ -218,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc(BN);
+        constexpr uint32_t idesc = make_idesc(BN, WGRAD);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -242,19 +268,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t st = smem_u32(smem + stage * C::stage_bytes);
-                    const uint64_t da_hi = make_smem_desc(st);
-                    const uint64_t db_hi = make_smem_desc(st + C::planes * C::a_bytes);
+                    // K-major: one UMMA_K step = 32 B inside the 128 B swizzle row; MN-major: 16 K-rows = 2048 B
+                    constexpr uint32_t kstep = WGRAD ? (UMMA_K * 128) : (UMMA_K * 2);
+                    const uint64_t da_hi = WGRAD ? make_smem_desc_mn(st) : make_smem_desc(st);
+                    const uint64_t db_hi = WGRAD ? make_smem_desc_mn(st + C::planes * C::a_bytes)
+                                                 : make_smem_desc(st + C::planes * C::a_bytes);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        const uint64_t koff = (uint64_t)((k * kstep) >> 4);
                         umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     if (C::planes == 2) {
-                        const uint64_t da_lo = make_smem_desc(st + C::a_bytes);
-                        const uint64_t db_lo = make_smem_desc(st + 2 * C::a_bytes + C::b_bytes);
+                        const uint64_t da_lo = WGRAD ? make_smem_desc_mn(st + C::a_bytes) : make_smem_desc(st + C::a_bytes);
+                        const uint64_t db_lo = WGRAD ? make_smem_desc_mn(st + 2 * C::a_bytes + C::b_bytes)
+                                                     : make_smem_desc(st + 2 * C::a_bytes + C::b_bytes);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            const uint64_t koff = (uint64_t)((k * kstep) >> 4);
                             umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
                             umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
                         }
@@ -466,9 +496,11 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
             if (x3) RADMMM_TRY(make_map(&P.b_lo[i], (const __nv_bfloat16*)b_keys[i].ptr + b_keys[i].plane, kmax, rows, b_keys[i].ld, BN));
         }
     } else {
-        // weight-grad: A = dY^T [M][R], B = X^T [N][R]; one output tile set per tap, K = rows split in split_k ranges
+        // weight-grad: A = dY [R][M], B = X [R][N] as MN-major operands; one output tile set per tap, K = rows split
+        // into split_k ranges
         const GemmSeg& g0 = args.seg[0];
-        RADMMM_REQUIRE(g0.aT.ptr && g0.wT.ptr, "gemm_tc: weight-grad needs the transposed operand copies");
+        RADMMM_REQUIRE(g0.a.ptr && g0.w.ptr, "gemm_tc: null weight-grad operand");
+        RADMMM_REQUIRE(g0.a.ld % 64 == 0 && g0.w.ld % 64 == 0, "gemm_tc: weight-grad operands need ld %% 64 == 0");
         const int M = args.epi.M;
         P.m_tiles = cdiv(M, BM);
         P.taps = args.n_seg;
@@ -490,15 +522,14 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         P.split_k = split;
         n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
         RADMMM_REQUIRE(split == 1 || args.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
-        const long long a_rows = g0.aT.plane_stride / g0.aT.ld, b_rows = g0.wT.plane_stride / g0.wT.ld;
-        RADMMM_TRY(make_map(&P.a_hi[0], g0.aT.ptr, args.R, a_rows, g0.aT.ld, BM));
-        RADMMM_TRY(make_map(&P.b_hi[0], g0.wT.ptr, args.R, b_rows, g0.wT.ld, BN));
+        RADMMM_TRY(make_map(&P.a_hi[0], g0.a.ptr, g0.a.ld, args.R, g0.a.ld, 64));
+        RADMMM_TRY(make_map(&P.b_hi[0], g0.w.ptr, g0.w.ld, args.R, g0.w.ld, 64));
         if (x3) {
-            RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.aT.ptr + g0.aT.plane_stride, args.R, a_rows, g0.aT.ld, BM));
-            RADMMM_TRY(make_map(&P.b_lo[0], (const __nv_bfloat16*)g0.wT.ptr + g0.wT.plane_stride, args.R, b_rows, g0.wT.ld, BN));
+            RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.a.ptr + g0.a.plane_stride, g0.a.ld, args.R, g0.a.ld, 64));
+            RADMMM_TRY(make_map(&P.b_lo[0], (const __nv_bfloat16*)g0.w.ptr + g0.w.plane_stride, g0.w.ld, args.R, g0.w.ld, 64));
         }
         for (int s = 0; s < args.n_seg; ++s) {
-            RADMMM_REQUIRE(args.seg[s].aT.ptr == g0.aT.ptr && args.seg[s].wT.ptr == g0.wT.ptr, "gemm_tc: weight-grad taps must share operands");
+            RADMMM_REQUIRE(args.seg[s].a.ptr == g0.a.ptr && args.seg[s].w.ptr == g0.w.ptr, "gemm_tc: weight-grad taps must share operands");
             P.seg[s] = TcSeg{0, 0, 0, args.seg[s].shift, P.k_blocks_total};
         }
         n_a = n_b = 1;

@@ -7,9 +7,8 @@ namespace radmmm {
 enum { SCALE_TANH = 0, SCALE_EXP = 1, SCALE_SIGMOID = 2, SCALE_TRANSLATE = 3 };
 
 int rows_from_cf(int mode, const float* src, long long batch_stride, int n_ch, const RowGeom& g, ActMat dst,
-                 ActMat dstT, int n_cols, int mask_invalid, cudaStream_t st);
-int rows_from_btd(int mode, const float* src, int D, const RowGeom& g, ActMat dst, ActMat dstT, int n_cols,
-                  cudaStream_t st);
+                 int n_cols, int mask_invalid, cudaStream_t st);
+int rows_from_btd(int mode, const float* src, int D, const RowGeom& g, ActMat dst, int n_cols, cudaStream_t st);
 int btd_from_rows(const float* rows, long long ld, int D, const RowGeom& g, float* dst, int accumulate, cudaStream_t st);
 int coupling_fwd(const float* z, const float* params, float* z_out, float* log_s, int B, int C, int Tp, int fn,
                  int inverse, cudaStream_t st);

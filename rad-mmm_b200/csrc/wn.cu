@@ -10,7 +10,6 @@ struct Dims {
     int mode, B, C, Ch, Tp, D, H, L, pitch, R, Kz, KzR, Dp, Cp, Nend;
     size_t es;
     int planes;
-    bool tposed;   // transposed copies kept (tensor-core modes only: the weight-grad GEMM reads K-major operands)
 };
 
 static Dims make_dims(int mode, int B, int C, int Tp, int D, int H, int L) {
@@ -26,7 +25,6 @@ static Dims make_dims(int mode, int B, int C, int Tp, int D, int H, int L) {
     d.Nend = (int)round_up(C, 128);
     d.es = mode_elem_bytes(mode);
     d.planes = mode_planes(mode);
-    d.tposed = mode != MODE_F32;
     return d;
 }
 
@@ -90,40 +88,36 @@ static ActMat sub_mode(const ActMat& m, long long elem_off, size_t es) {
 
 // ------------------------------------------------------------------------------------------------ activations
 struct Workspace {
-    ActMat Z0, Z0T;
-    ActMat Hs[RADMMM_MAX_LAYERS + 1], HsT[RADMMM_MAX_LAYERS + 1];
+    ActMat Z0;
+    ActMat Hs[RADMMM_MAX_LAYERS + 1];
     ActMat SIG[RADMMM_MAX_LAYERS];
     float* OUT;
-    ActMat OUTa, OUTaT;
+    ActMat OUTa;
 };
 
 static size_t layout_workspace(const Dims& d, int training, void* base, Workspace* w) {
     Bump b{(char*)base, 0};
     Workspace q;
     q.Z0 = take_act(b, d, d.R, d.Kz);
-    q.Z0T = (training && d.tposed) ? take_act(b, d, d.Kz, d.R) : null_act();
     const int nH = training ? d.L + 1 : 2;
     for (int i = 0; i <= d.L; ++i) {
         if (i < nH) {
             q.Hs[i] = take_act(b, d, d.R, d.H);
-            q.HsT[i] = (training && d.tposed) ? take_act(b, d, d.H, d.R) : null_act();
         } else {
             q.Hs[i] = q.Hs[i & 1];
-            q.HsT[i] = null_act();
         }
     }
     for (int i = 0; i < d.L; ++i) q.SIG[i] = training ? take_act(b, d, d.R, d.H) : null_act();
     q.OUT = (float*)b.take(sizeof(float) * (size_t)d.R * d.H);
     q.OUTa = take_act(b, d, d.R, d.H);
-    q.OUTaT = (training && d.tposed) ? take_act(b, d, d.H, d.R) : null_act();
     if (w) *w = q;
     return (size_t)round_up((long long)b.off, 1024);
 }
 
 struct Scratch {
-    ActMat DP, DPT;
-    ActMat DQ[RADMMM_MAX_LAYERS], DQT[RADMMM_MAX_LAYERS];
-    ActMat DACC[2], DACCT[2];
+    ActMat DP;
+    ActMat DQ[RADMMM_MAX_LAYERS];
+    ActMat DACC[2];
     float* dW;     // [5][H][H] fp32 (also holds dWz [H][Kz] + dWc [H][Dp])
 };
 
@@ -131,14 +125,11 @@ static size_t layout_scratch(const Dims& d, void* base, Scratch* s) {
     Bump b{(char*)base, 0};
     Scratch q;
     q.DP = take_act(b, d, d.R, d.Cp);
-    q.DPT = d.tposed ? take_act(b, d, d.Cp, d.R) : null_act();
     for (int i = 0; i < d.L; ++i) {
         q.DQ[i] = take_act(b, d, d.R, d.H);
-        q.DQT[i] = d.tposed ? take_act(b, d, d.H, d.R) : null_act();
     }
     for (int i = 0; i < 2; ++i) {
         q.DACC[i] = take_act(b, d, d.R, d.H);
-        q.DACCT[i] = d.tposed ? take_act(b, d, d.H, d.R) : null_act();
     }
     size_t n1 = (size_t)5 * d.H * d.H, n2 = (size_t)d.H * (d.Kz + d.Dp);
     q.dW = (float*)b.take(sizeof(float) * (n1 > n2 ? n1 : n2));
@@ -203,7 +194,7 @@ static void init_args(GemmArgs& a, const Dims& d, const int* lens, int kind, int
 }
 static void add_seg(GemmArgs& a, const ActMat& act, const ActMat& w, int K, int shift) {
     GemmSeg& s = a.seg[a.n_seg++];
-    s.a = act; s.aT = null_act(); s.w = w; s.wT = null_act(); s.K = K; s.shift = shift;
+    s.a = act; s.w = w; s.K = K; s.shift = shift;
 }
 
 // WN forward on rows: fills ws (H*, SIG*, OUT*) and writes params (B, C, Tp)
@@ -213,14 +204,14 @@ static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepa
     const bool tr = f->training != 0;
     ActMat ctx; ctx.ptr = const_cast<void*>(f->ctx_rows); ctx.ld = d.Dp; ctx.plane_stride = (long long)d.R * d.Dp;
     // z0 = z_mid[:, :Ch] -> rows
-    RADMMM_TRY(rows_from_cf(d.mode, z_mid, (long long)d.C * d.Tp, d.Ch, g, w.Z0, w.Z0T, d.Kz, 1, st));
+    RADMMM_TRY(rows_from_cf(d.mode, z_mid, (long long)d.C * d.Tp, d.Ch, g, w.Z0, d.Kz, 1, st));
     GemmArgs a;
     // start
     init_args(a, d, f->lens, EPI_START, d.H);
     add_seg(a, w.Z0, p.Wz, d.Kz, 0);
     add_seg(a, ctx, p.Wc, d.Dp, 0);
     a.epi.bias = f->start_b;
-    a.epi.out0 = w.Hs[0]; a.epi.out0T = w.HsT[0];
+    a.epi.out0 = w.Hs[0];
     RADMMM_TRY(launch_gemm(a, d.mode, st));
     for (int i = 0; i < d.L; ++i) {
         const int dil = 1 << i;
@@ -229,7 +220,7 @@ static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepa
             add_seg(a, w.Hs[i], sub_mode(p.Win, ((long long)i * 5 + j) * p.HH, d.es), d.H, (j - 2) * dil);
         a.epi.bias = f->in_b[i];
         a.epi.dilation = dil;
-        a.epi.out0 = w.Hs[i + 1]; a.epi.out0T = w.HsT[i + 1];
+        a.epi.out0 = w.Hs[i + 1];
         RADMMM_TRY(launch_gemm(a, d.mode, st));
         init_args(a, d, f->lens, EPI_RS, d.H);
         add_seg(a, w.Hs[i + 1], sub_mode(p.Wrs, (long long)i * p.HH, d.es), d.H, 0);
@@ -239,7 +230,7 @@ static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepa
         a.epi.last = (i == d.L - 1);
         a.epi.out0 = tr ? w.SIG[i] : null_act();
         a.epi.f32_out = w.OUT; a.epi.f32_ld = d.H;
-        a.epi.out1 = w.OUTa; a.epi.out1T = w.OUTaT;
+        a.epi.out1 = w.OUTa;
         RADMMM_TRY(launch_gemm(a, d.mode, st));
     }
     init_args(a, d, f->lens, EPI_END, d.C);
@@ -284,14 +275,13 @@ int flow_inverse(const radmmm_flow_desc* f, const float* z_in, float* params, fl
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat& dYT, const ActMat& X, const ActMat& XT,
-                 int M, int N, int taps, int dil, float* out, long long ld, long long tap_stride, cudaStream_t st) {
+static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat& X, int M, int N, int taps, int dil, float* out, long long ld, long long tap_stride, cudaStream_t st) {
     GemmArgs a;
     init_args(a, d, lens, EPI_WGRAD, N);
     a.wgrad = 1;
     for (int j = 0; j < taps; ++j) {
         GemmSeg& s = a.seg[a.n_seg++];
-        s.a = dY; s.aT = dYT; s.w = X; s.wT = XT; s.K = d.R;
+        s.a = dY; s.w = X; s.K = d.R;
         s.shift = taps == 1 ? 0 : (j - 2) * dil;
     }
     a.epi.M = M;
@@ -317,19 +307,17 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
     const RowGeom g = geom_of(d, f->lens);
     const int H = d.H, L = d.L;
     ActMat ctx; ctx.ptr = const_cast<void*>(f->ctx_rows); ctx.ld = d.Dp; ctx.plane_stride = (long long)d.R * d.Dp;
-    ActMat ctxT; ctxT.ptr = const_cast<void*>(f->ctx_rows_T); ctxT.ld = d.R; ctxT.plane_stride = (long long)d.R * d.Dp;
-    if (!d.tposed) ctxT = null_act();
     GemmArgs a;
 
     // 1. coupling tail
     RADMMM_TRY(coupling_bwd(dz_out, dlog_s, z_mid, params, f->lens, dz_mid, dparams, d.B, d.C, d.Tp, f->scaling_fn, st));
-    RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, s.DPT, d.Cp, 1, st));
+    RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, d.Cp, 1, st));
     // 2. end conv: bias, weight, input gradients
     RADMMM_TRY(colsum(d.mode, s.DP, g, d.C, 1, 0, gr->end_b, st));
-    RADMMM_TRY(wgrad(d, f->lens, s.DP, s.DPT, w.OUTa, w.OUTaT, d.C, H, 1, 1, gr->end_w, H, 0, st));
+    RADMMM_TRY(wgrad(d, f->lens, s.DP, w.OUTa, d.C, H, 1, 1, gr->end_w, H, 0, st));
     init_args(a, d, f->lens, EPI_DOUT, H);
     add_seg(a, s.DP, p.WendT, d.Cp, 0);
-    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.SIG[i]; a.epi.dq[i] = s.DQ[i]; a.epi.dqT[i] = s.DQT[i]; }
+    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.SIG[i]; a.epi.dq[i] = s.DQ[i]; }
     RADMMM_TRY(launch_gemm(a, d.mode, st));
     // 3. layers, last to first
     for (int i = L - 1; i >= 0; --i) {
@@ -337,7 +325,7 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         const int cur = i & 1, nxt = (i + 1) & 1;
         // res-skip conv i
         RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], st));
-        RADMMM_TRY(wgrad(d, f->lens, s.DQ[i], s.DQT[i], w.Hs[i + 1], w.HsT[i + 1], H, H, 1, 1, s.dW, H, 0, st));
+        RADMMM_TRY(wgrad(d, f->lens, s.DQ[i], w.Hs[i + 1], H, H, 1, 1, s.dW, H, 0, st));
         RADMMM_TRY(wn_bwd(s.dW, H, 0, H, nullptr, 0, 0, f->rs_v[i], f->rs_g[i], p.norm_rs + (size_t)i * H, H, H, 1,
                           gr->rs_v[i], gr->rs_g[i], st));
         // dh_{i+1} = Wrs_i^T dq_i + sum_taps Win_{i+1,j}^T dacc_{i+1}[r - (j-2) d_{i+1}]  -> dacc_i
@@ -348,27 +336,26 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
                 add_seg(a, s.DACC[nxt], sub_mode(p.WinT, ((long long)(i + 1) * 5 + j) * p.HH, d.es), H, -(j - 2) * (dil * 2));
         a.epi.h = w.Hs[i + 1];
         a.epi.dilation = dil;
-        a.epi.out0 = s.DACC[cur]; a.epi.out0T = s.DACCT[cur];
+        a.epi.out0 = s.DACC[cur];
         RADMMM_TRY(launch_gemm(a, d.mode, st));
         // dilated conv i: bias (un-ratio'd), weights
         RADMMM_TRY(colsum(d.mode, s.DACC[cur], g, H, dil, 1, gr->in_b[i], st));
-        RADMMM_TRY(wgrad(d, f->lens, s.DACC[cur], s.DACCT[cur], w.Hs[i], w.HsT[i], H, H, 5, dil, s.dW, H, p.HH, st));
+        RADMMM_TRY(wgrad(d, f->lens, s.DACC[cur], w.Hs[i], H, H, 5, dil, s.dW, H, p.HH, st));
         RADMMM_TRY(wn_bwd(s.dW, H, p.HH, H, nullptr, 0, 0, f->in_v[i], f->in_g[i], p.norm_in + (size_t)i * H, H, H, 5,
                           gr->in_v[i], gr->in_g[i], st));
     }
     // 4. dh0 (masked) from layer 0's dilated conv; reuse DACC[1] for it
     init_args(a, d, f->lens, EPI_DH0, H);
     for (int j = 0; j < 5; ++j) add_seg(a, s.DACC[0], sub_mode(p.WinT, (long long)j * p.HH, d.es), H, -(j - 2));
-    a.epi.out0 = s.DACC[1]; a.epi.out0T = s.DACCT[1];
+    a.epi.out0 = s.DACC[1];
     RADMMM_TRY(launch_gemm(a, d.mode, st));
     const ActMat& DH0 = s.DACC[1];
-    const ActMat& DH0T = s.DACCT[1];
     // 5. start conv
     RADMMM_TRY(colsum(d.mode, DH0, g, H, 1, 0, gr->start_b, st));
     float* dWz = s.dW;
     float* dWc = s.dW + (size_t)H * d.Kz;
-    RADMMM_TRY(wgrad(d, f->lens, DH0, DH0T, w.Z0, w.Z0T, H, d.Kz, 1, 1, dWz, d.Kz, 0, st));
-    RADMMM_TRY(wgrad(d, f->lens, DH0, DH0T, ctx, ctxT, H, d.Dp, 1, 1, dWc, d.Dp, 0, st));
+    RADMMM_TRY(wgrad(d, f->lens, DH0, w.Z0, H, d.Kz, 1, 1, dWz, d.Kz, 0, st));
+    RADMMM_TRY(wgrad(d, f->lens, DH0, ctx, H, d.Dp, 1, 1, dWc, d.Dp, 0, st));
     RADMMM_TRY(wn_bwd(dWz, d.Kz, 0, d.Ch, dWc, d.Dp, 0, f->start_v, f->start_g, p.norm_start, H, d.Ch + d.D, 1,
                       gr->start_v, gr->start_g, st));
     init_args(a, d, f->lens, EPI_DZ0, d.Ch);
@@ -400,17 +387,14 @@ size_t flow_workspace_bytes(int mode, int training, int B, int Tp, int C, int D,
 size_t flow_scratch_bytes(int mode, int B, int Tp, int C, int D, int H, int L) {
     return layout_scratch(make_dims(mode, B, C, Tp, D, H, L), nullptr, nullptr);
 }
-size_t context_rows_bytes(int mode, int B, int Tp, int D, int transposed) {
+size_t context_rows_bytes(int mode, int B, int Tp, int D) {
     Dims d = make_dims(mode, B, 2, Tp, D, 128, 1);
-    if (transposed && !d.tposed) return 0;
     return (size_t)d.planes * d.R * d.Dp * d.es;
 }
-int context_rows(int mode, const float* ctx_btd, const int* lens, int B, int Tp, int D, void* rows, void* rows_T,
-                 cudaStream_t st) {
+int context_rows(int mode, const float* ctx_btd, const int* lens, int B, int Tp, int D, void* rows, cudaStream_t st) {
     Dims d = make_dims(mode, B, 2, Tp, D, 128, 1);
     ActMat r; r.ptr = rows; r.ld = d.Dp; r.plane_stride = (long long)d.R * d.Dp;
-    ActMat rT; rT.ptr = d.tposed ? rows_T : nullptr; rT.ld = d.R; rT.plane_stride = (long long)d.R * d.Dp;
-    return rows_from_btd(mode, ctx_btd, D, geom_of(d, lens), r, rT, d.Dp, st);
+    return rows_from_btd(mode, ctx_btd, D, geom_of(d, lens), r, d.Dp, st);
 }
 int context_rows_backward(const float* drows, const int* lens, int B, int Tp, int D, float* dctx, int accumulate,
                           cudaStream_t st) {

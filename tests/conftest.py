@@ -27,6 +27,15 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _exact_library_math():
+    """Parity tests compare against an fp32 reference: keep cuDNN (context LSTM) and cuBLAS out of TF32."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

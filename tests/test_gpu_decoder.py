@@ -25,6 +25,8 @@ def _small_layer(fn="tanh", H=128, C=12, D=10, L=3):
         lo, hi = (-0.3, 0.3)
         if k.endswith("weight_g"):
             lo, hi = 0.5, 1.5
+        if k.startswith("affine_param_predictor.end."):      # keep tanh(a) away from saturation (fp32 cancellation)
+            lo, hi = -0.02, 0.02
         sd[k] = syn.hash_uniform("small." + k, tuple(v.shape), lo, hi)
     layer.load_state_dict(sd)
     return layer, sd

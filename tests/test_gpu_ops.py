@@ -13,16 +13,17 @@ from tests.gpu_util import DEV, act_to_float, cast_rows, close, err, gold
 
 pytestmark = pytest.mark.gpu
 LENS = torch.tensor([37, 20, 5])
-MODE_TOL = {N.MODE_F32: 2e-5, N.MODE_BF16X3: 2e-4, N.MODE_BF16: 3e-2}
+MODE_TOL = {"fp32": 2e-5, "bf16x3": 2e-4, "bf16": 3e-2}
 
 
 # ------------------------------------------------------------------------------------------------ contractions
-@pytest.mark.parametrize("mode", [N.MODE_F32, N.MODE_BF16, N.MODE_BF16X3])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("taps,dil,K,Nout", [(1, 1, 128, 256), (5, 1, 128, 256), (5, 8, 256, 128), (1, 1, 192, 160),
                                               (5, 4, 64, 1024)])
-def test_conv_rows(mode, taps, dil, K, Nout):
+def test_conv_rows(precision, taps, dil, K, Nout):
     """Row GEMM (the WN conv): y[r] = sum_j W_j x[r + (j-c)d] + bias, zero outside [0,R)."""
     lib = N.lib()
+    mode = N.MODES[precision]
     R = 384
     npad = N.round_up(Nout, 128)
     x = syn.hash_uniform(f"cr.x{K}", (R, K)).to(DEV)
@@ -46,25 +47,23 @@ def test_conv_rows(mode, taps, dil, K, Nout):
         ref += xs @ wd[j].t()
     ref += bias.double().cpu()[None]
     scale = ref.abs().max().item()
-    close(y[:, :Nout], ref[:, :Nout], MODE_TOL[mode] * scale, what=f"conv_rows mode {mode}")
+    close(y[:, :Nout], ref[:, :Nout], MODE_TOL[precision] * scale, what=f"conv_rows {precision}")
 
 
-@pytest.mark.parametrize("mode", [N.MODE_F32, N.MODE_BF16, N.MODE_BF16X3])
-@pytest.mark.parametrize("taps,dil,M,Nx", [(1, 1, 128, 256), (5, 2, 256, 128), (1, 1, 192, 1152), (5, 8, 128, 128)])
-def test_wgrad_rows(mode, taps, dil, M, Nx):
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
+@pytest.mark.parametrize("taps,dil,M,Nx", [(1, 1, 128, 256), (5, 2, 256, 128), (1, 1, 256, 1152), (5, 8, 128, 128),
+                                            (5, 1, 1024, 1024)])
+def test_wgrad_rows(precision, taps, dil, M, Nx):
     """Weight-grad GEMM: out[j][m][n] = sum_r dy[r][m] x[r + (j-c)d][n]."""
     lib = N.lib()
+    mode = N.MODES[precision]
     R = 640
     dy = syn.hash_uniform(f"wg.dy{M}", (R, M)).to(DEV)
     x = syn.hash_uniform(f"wg.x{Nx}", (R, Nx)).to(DEV)
     dyb, dld, dpl = cast_rows(dy, mode)
     xb, xld, xpl = cast_rows(x, mode)
-    dyT = xT = None
-    if mode != N.MODE_F32:
-        dyT, _, _ = cast_rows(dy.t().contiguous(), mode)
-        xT, _, _ = cast_rows(x.t().contiguous(), mode)
     out = torch.full((taps, M, Nx), float("nan"), device=DEV)
-    N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dyb), dld, dpl, N.ptr(dyT), N.ptr(xb), xld, xpl, N.ptr(xT), N.fptr(out), Nx,
+    N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dyb), dld, dpl, N.ptr(xb), xld, xpl, N.fptr(out), Nx,
                                   M * Nx, R, M, Nx, taps, dil, N.stream()))
     torch.cuda.synchronize()
     dyd, xd = dy.double().cpu(), x.double().cpu()
@@ -75,7 +74,7 @@ def test_wgrad_rows(mode, taps, dil, M, Nx):
         lo, hi = max(0, -s), min(R, R - s)
         xs[lo:hi] = xd[lo + s:hi + s]
         ref[j] = dyd.t() @ xs
-    close(out, ref, MODE_TOL[mode] * ref.abs().max().item(), what=f"wgrad_rows mode {mode}")
+    close(out, ref, MODE_TOL[precision] * ref.abs().max().item(), what=f"wgrad_rows {precision}")
 
 
 # ------------------------------------------------------------------------------------------------ invertible convs
@@ -147,8 +146,10 @@ def test_coupling_kernels(fn):
     g1, g2 = syn.hash_uniform("cp.g1", (B, C, T)).double(), syn.hash_uniform("cp.g2", (B, 6, T)).double()
     ((zo_ref * g1 + 0).mul(mask).sum() + (log_s * g2 * mask).sum()).backward()
     dz, dp = torch.empty_like(zd), torch.empty_like(zd)
-    N.check(lib.radmmm_coupling_backward(N.fptr(g1.float().to(DEV)), N.fptr(g2.float().to(DEV)), N.fptr(zd), N.fptr(pd),
-                                         N.ptr(lens.to(DEV)), N.fptr(dz), N.fptr(dp), B, C, T, N.SCALING[fn], N.stream()))
+    g1d, g2d, lensd = g1.float().to(DEV), g2.float().to(DEV), lens.to(DEV)     # keep alive until the kernel has run
+    N.check(lib.radmmm_coupling_backward(N.fptr(g1d), N.fptr(g2d), N.fptr(zd), N.fptr(pd), N.ptr(lensd), N.fptr(dz),
+                                         N.fptr(dp), B, C, T, N.SCALING[fn], N.stream()))
+    torch.cuda.synchronize()
     ref_dz = zc.grad.clone()
     close(dz, ref_dz, 2e-5, what="dz")
     close(dp, pc.grad, 2e-5 * max(1.0, pc.grad.abs().max().item()), what="dparams")
@@ -187,7 +188,8 @@ def test_spline_kernels():
     lens = torch.tensor([53, 31], dtype=torch.int32)
     zd, qd = z1.to(DEV), q.to(DEV)
     out, ls = torch.empty_like(zd), torch.empty(B, 1, T, device=DEV)
-    N.check(lib.radmmm_spline_forward(N.fptr(zd), N.fptr(qd), N.ptr(lens.to(DEV)), N.fptr(out), N.fptr(ls), B, Ch, T, 32,
+    lensd = lens.to(DEV)
+    N.check(lib.radmmm_spline_forward(N.fptr(zd), N.fptr(qd), N.ptr(lensd), N.fptr(out), N.fptr(ls), B, Ch, T, 32,
                                       -3.0, 3.0, 0, N.stream()))
     zc, qc = z1.double().requires_grad_(True), q.double().requires_grad_(True)
     qq = qc.permute(0, 2, 1).reshape(B, T, Ch, 65)
@@ -198,7 +200,7 @@ def test_spline_kernels():
     close(ls, ls_ref.detach(), 2e-4, what="spline log_s")
     # inverse round trip through the kernel
     back = torch.empty_like(zd)
-    N.check(lib.radmmm_spline_forward(N.fptr(out), N.fptr(qd), N.ptr(lens.to(DEV)), N.fptr(back), None, B, Ch, T, 32,
+    N.check(lib.radmmm_spline_forward(N.fptr(out), N.fptr(qd), N.ptr(lensd), N.fptr(back), None, B, Ch, T, 32,
                                       -3.0, 3.0, 1, N.stream()))
     close(back, z1, 5e-3, what="spline round trip")
     yi, _ = osp.quadratic_spline((y_ref.detach().float().permute(0, 2, 1) + 3) / 6, qq[..., :32].detach().float(),
@@ -209,8 +211,10 @@ def test_spline_kernels():
     g1, g2 = syn.hash_uniform("sk.g1", (B, Ch, T)).double(), syn.hash_uniform("sk.g2", (B, 1, T)).double()
     ((y_ref * g1 * mask).sum() + (ls_ref * g2 * mask).sum()).backward()
     dz, dq = torch.empty_like(zd), torch.empty_like(qd)
-    N.check(lib.radmmm_spline_backward(N.fptr(zd), N.fptr(qd), N.ptr(lens.to(DEV)), N.fptr(g1.float().to(DEV)),
-                                       N.fptr(g2.float().to(DEV)), N.fptr(dz), N.fptr(dq), B, Ch, T, 32, -3.0, 3.0, N.stream()))
+    g1d, g2d = g1.float().to(DEV), g2.float().to(DEV)
+    N.check(lib.radmmm_spline_backward(N.fptr(zd), N.fptr(qd), N.ptr(lensd), N.fptr(g1d), N.fptr(g2d), N.fptr(dz),
+                                       N.fptr(dq), B, Ch, T, 32, -3.0, 3.0, N.stream()))
+    torch.cuda.synchronize()
     close(dz, zc.grad, 1e-3 * max(1.0, zc.grad.abs().max().item()), what="spline dz")
     close(dq, qc.grad, 1e-3 * max(1.0, qc.grad.abs().max().item()), what="spline dq")
 
@@ -256,13 +260,13 @@ def test_soft_attention():
     prior = syn.hash_uniform("att.prior", (3, 37, 11), 0.0, 1.0)
     txt = syn.hash_uniform("att.txt", (3, 24, 11), -1, 1)
     q, k = ofe.attention_projections(sd, "", q_in, k_in)
+    qd, kd, priord, lensd, txtd = q.to(DEV).contiguous(), k.to(DEV).contiguous(), prior.to(DEV), in_lens.to(DEV), txt.to(DEV)
     for use_prior, ga, gl in ((True, "att", "att_logprob"), (False, "att_noprior", "att_logprob_noprior")):
         attn = torch.empty(3, 1, 37, 11, device=DEV)
         logp = torch.empty_like(attn)
         ctx = torch.empty(3, 24, 37, device=DEV)
-        N.check(lib.radmmm_soft_attention(N.fptr(q.to(DEV).contiguous()), N.fptr(k.to(DEV).contiguous()),
-                                          N.fptr(prior.to(DEV)) if use_prior else None, N.ptr(in_lens.to(DEV)),
-                                          N.fptr(attn), N.fptr(logp), N.fptr(txt.to(DEV)), N.fptr(ctx), 3, 80, 37, 11, 24,
+        N.check(lib.radmmm_soft_attention(N.fptr(qd), N.fptr(kd), N.fptr(priord) if use_prior else None, N.ptr(lensd),
+                                          N.fptr(attn), N.fptr(logp), N.fptr(txtd), N.fptr(ctx), 3, 80, 37, 11, 24,
                                           0.0005, N.stream()))
         close(attn, gd[ga], 2e-6, what=ga)
         close(logp, gd[gl], 2e-5, what=gl)
@@ -275,7 +279,8 @@ def test_soft_attention():
     il = torch.tensor([61, 40], dtype=torch.int32)
     a_ref, l_ref = ofe.soft_attention(q2, k2, il.long(), pr)
     attn, logp = torch.empty(B, 1, T1, T2, device=DEV), torch.empty(B, 1, T1, T2, device=DEV)
-    N.check(lib.radmmm_soft_attention(N.fptr(q2.to(DEV)), N.fptr(k2.to(DEV)), N.fptr(pr.to(DEV)), N.ptr(il.to(DEV)),
-                                      N.fptr(attn), N.fptr(logp), None, None, B, 80, T1, T2, 0, 0.0005, N.stream()))
+    q2d, k2d, prd, ild = q2.to(DEV), k2.to(DEV), pr.to(DEV), il.to(DEV)
+    N.check(lib.radmmm_soft_attention(N.fptr(q2d), N.fptr(k2d), N.fptr(prd), N.ptr(ild), N.fptr(attn), N.fptr(logp), None,
+                                      None, B, 80, T1, T2, 0, 0.0005, N.stream()))
     close(attn, a_ref, 2e-6)
     close(logp, l_ref, 2e-5)

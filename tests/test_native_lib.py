@@ -51,8 +51,9 @@ def test_size_queries(lib):
         w_inf = lib.radmmm_flow_workspace_bytes(mode, 0, 8, 400, 160, 1056, 1024, 4)
         assert p > 2 * 26.5e6 * (4 if mode == 0 else 2)      # weights + transposes
         assert w_train > w_inf > 0
-    assert lib.radmmm_context_rows_bytes(0, 8, 400, 1056, 1) == 0       # fp32 path keeps no transposed copies
-    assert lib.radmmm_context_rows_bytes(1, 8, 400, 1056, 1) == 3328 * 1152 * 2
+    assert lib.radmmm_context_rows_bytes(0, 8, 400, 1056) == 3328 * 1152 * 4
+    assert lib.radmmm_context_rows_bytes(1, 8, 400, 1056) == 3328 * 1152 * 2
+    assert lib.radmmm_context_rows_bytes(2, 8, 400, 1056) == 3328 * 1152 * 2 * 2      # hi + lo planes
 
 
 def test_argument_errors_are_reported(lib):
