@@ -41,6 +41,11 @@ extern "C" {
 
 int radmmm_abi_version(void);
 const char* radmmm_last_error(void);
+/* Measurement aid (bench.py): when enabled, every contraction launch is bracketed by CUDA events on its own stream.
+ * radmmm_profile_collect synchronises the device and returns, per tag (epilogue kind 0..10; 16+taps for the
+ * weight-grad GEMM), the launch count, summed device milliseconds and summed executed FLOPs.  Not thread-safe. */
+void radmmm_profile_enable(int on);
+int radmmm_profile_collect(int max_tags, int* counts, double* ms, double* flops);
 /* sizeof(radmmm_flow_desc) / sizeof(radmmm_flow_grads) as compiled -- lets a binding verify its struct layout */
 size_t radmmm_sizeof_flow_desc(void);
 size_t radmmm_sizeof_flow_grads(void);

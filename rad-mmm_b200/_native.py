@@ -55,6 +55,8 @@ _P = C.POINTER
 SIGNATURES = {
     "radmmm_abi_version": (_i, []),
     "radmmm_last_error": (C.c_char_p, []),
+    "radmmm_profile_enable": (None, [_i]),
+    "radmmm_profile_collect": (_i, [_i, _P(C.c_int), _P(C.c_double), _P(C.c_double)]),
     "radmmm_sizeof_flow_desc": (_sz, []),
     "radmmm_sizeof_flow_grads": (_sz, []),
     "radmmm_rows": (_i, [_i, _i]),

@@ -104,6 +104,16 @@ def _as_btd(context: torch.Tensor) -> torch.Tensor:
 
 _scratch_cache = {}
 
+# Optional gradient sink (radmmm_b200.ddp.BucketedGradReducer): maps a parameter's storage pointer to a fresh view of
+# its all-reduce bucket so FlowStepFunction.backward writes parameter gradients straight into bucket storage.
+_grad_sink = None
+
+
+def set_grad_sink(fn):
+    """``fn(param_tensor) -> Tensor | None`` or None to clear."""
+    global _grad_sink
+    _grad_sink = fn
+
 
 def _backward_scratch(nbytes: int, device) -> torch.Tensor:
     key = (device.index,)
@@ -289,7 +299,10 @@ class FlowStepFunction(torch.autograd.Function):
         d.W, d.W_T, d.mean = (N.fptr(W) if ctx.has_W else None), N.fptr(W_T), (N.fptr(mean) if ctx.has_mean else None)
         dz_out = dz_out.contiguous() if dz_out is not None else torch.zeros_like(z)
         dlog_s = dlog_s.contiguous() if dlog_s is not None else None
-        grads = [torch.empty_like(p) for p in plist]
+        grads = []
+        for p in plist:
+            buf = _grad_sink(p) if _grad_sink is not None else None
+            grads.append(buf if buf is not None else torch.empty_like(p))
         g = N.FlowGrads()
         L = wn.n_layers
         g.start_g, g.start_v, g.start_b = (N.fptr(t) for t in grads[0:3])

@@ -16,9 +16,29 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+// ---- optional per-launch profiler (bench.py): CUDA events around every contraction launch, on the launching stream.
+// Off by default; when off the launch path does not touch it.
+struct ProfSlot { cudaEvent_t e0, e1; int tag; double flops; };
+static const int kProfMax = 4096;
+static ProfSlot g_prof[kProfMax];
+static int g_prof_n = 0;
+static bool g_prof_on = false;
+
 int launch_gemm(const GemmArgs& args, int mode, cudaStream_t stream) {
-    if (mode == MODE_F32) return launch_gemm_ffma(args, stream);
-    return launch_gemm_tc(args, mode, stream);
+    ProfSlot* slot = nullptr;
+    if (g_prof_on && g_prof_n < kProfMax) {
+        slot = &g_prof[g_prof_n++];
+        if (!slot->e0) { cudaEventCreate(&slot->e0); cudaEventCreate(&slot->e1); }
+        slot->tag = args.wgrad ? 16 + args.n_seg : args.epi.kind;
+        double k = 0;
+        for (int s = 0; s < args.n_seg; ++s) k += args.seg[s].K;
+        slot->flops = args.wgrad ? 2.0 * args.epi.M * args.epi.N * (double)args.R * args.n_seg
+                                 : 2.0 * args.R * (double)args.epi.N * k;
+        cudaEventRecord(slot->e0, stream);
+    }
+    int rc = (mode == MODE_F32) ? launch_gemm_ffma(args, stream) : launch_gemm_tc(args, mode, stream);
+    if (slot) cudaEventRecord(slot->e1, stream);
+    return rc;
 }
 
 // wn.cu
@@ -61,6 +81,22 @@ using namespace radmmm;
 extern "C" {
 
 int radmmm_abi_version(void) { return RADMMM_ABI_VERSION; }
+
+void radmmm_profile_enable(int on) { g_prof_on = on != 0; if (on) g_prof_n = 0; }
+int radmmm_profile_collect(int max_tags, int* counts, double* ms, double* flops) {
+    cudaDeviceSynchronize();
+    for (int i = 0; i < max_tags; ++i) { counts[i] = 0; ms[i] = 0; flops[i] = 0; }
+    for (int i = 0; i < g_prof_n; ++i) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, g_prof[i].e0, g_prof[i].e1) != cudaSuccess) continue;
+        const int tag = g_prof[i].tag;
+        if (tag < 0 || tag >= max_tags) continue;
+        counts[tag] += 1; ms[tag] += t; flops[tag] += g_prof[i].flops;
+    }
+    const int n = g_prof_n;
+    g_prof_n = 0;
+    return n;
+}
 const char* radmmm_last_error(void) { return last_error(); }
 size_t radmmm_sizeof_flow_desc(void) { return sizeof(radmmm_flow_desc); }
 size_t radmmm_sizeof_flow_grads(void) { return sizeof(radmmm_flow_grads); }

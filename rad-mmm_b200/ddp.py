@@ -1,0 +1,129 @@
+"""Data-parallel gradient exchange for the flow decoder: one flat bucket per flow step, all-reduced over NCCL
+(NVLink 5 / NVSwitch) as soon as that step's backward has produced its gradients.
+
+Replaces Lightning's ``strategy: ddp`` for this path (configs/RADMMM_train_config.yaml:28).
+The flow has no cross-sample operation, so the gradient sum is the ONLY exchange step: flows run backward 7 -> 0, so
+bucket i's all-reduce overlaps the backward of flows i-1 .. 0.  FlowStepFunction.backward returns gradients that are
+views into the bucket, and autograd's AccumulateGrad adopts them without a copy (``.grad`` is ``None`` before
+backward), i.e. gradients are written straight into bucket storage.
+
+Works with any ``torch.distributed`` backend (NCCL on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def default_bucket_key(name: str) -> str:
+    """Bucket assignment by parameter name: 'flows.<i>.' -> one bucket per flow step; everything else -> 'rest'."""
+    parts = name.split(".")
+    if len(parts) > 2 and parts[0] == "flows" and parts[1].isdigit():
+        return "flow%s" % parts[1]
+    return "rest"
+
+
+class BucketedGradReducer:
+    """All-reduce (mean) of parameter gradients in flat buckets, overlapped with backward.
+
+    usage:
+        reducer = BucketedGradReducer(model)        # after the model is on its device
+        loss.backward(); reducer.finish()           # .grad of every parameter now holds the cross-rank mean
+    """
+
+    def __init__(self, module: torch.nn.Module, bucket_key: Callable[[str], str] = default_bucket_key,
+                 process_group=None, average: bool = True):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.average = average
+        self.buckets: Dict[str, dict] = {}
+        self._handles: List = []
+        for name, p in module.named_parameters():
+            if not p.requires_grad:
+                continue
+            b = self.buckets.setdefault(bucket_key(name), {"params": [], "names": []})
+            b["params"].append(p)
+            b["names"].append(name)
+        for key, b in self.buckets.items():
+            n = sum(p.numel() for p in b["params"])
+            p0 = b["params"][0]
+            b["flat"] = torch.zeros(n, dtype=p0.dtype, device=p0.device)
+            b["views"] = []
+            off = 0
+            for p in b["params"]:
+                b["views"].append(b["flat"][off:off + p.numel()].view_as(p))
+                off += p.numel()
+            b["pending"] = len(b["params"])
+            for p, v in zip(b["params"], b["views"]):
+                p.register_post_accumulate_grad_hook(self._make_hook(key, v))
+        self.reset()
+
+    # gradient buffers a custom backward can write into directly (FlowStepFunction does)
+    def grad_view(self, param: torch.nn.Parameter) -> Optional[torch.Tensor]:
+        return self._view_of.get(id(param))
+
+    def fresh_view(self, param: torch.Tensor) -> Optional[torch.Tensor]:
+        """A NEW tensor object viewing ``param``'s slot of its bucket (autograd adopts it as ``.grad`` without a copy
+        because nothing else references the object)."""
+        slot = self._slot_of.get(param.data_ptr())
+        if slot is None:
+            return None
+        flat, off, shape = slot
+        n = 1
+        for d in shape:
+            n *= d
+        return flat[off:off + n].view(shape)
+
+    def install(self):
+        """Route FlowStepFunction's parameter gradients into the buckets."""
+        from . import common
+        common.set_grad_sink(self.fresh_view)
+        return self
+
+    def reset(self):
+        self._view_of = {}
+        self._slot_of = {}
+        for b in self.buckets.values():
+            b["pending"] = len(b["params"])
+            off = 0
+            for p, v in zip(b["params"], b["views"]):
+                self._view_of[id(p)] = v
+                self._slot_of[p.data_ptr()] = (b["flat"], off, tuple(p.shape))
+                off += p.numel()
+        self._handles = []
+
+    def _make_hook(self, key: str, view: torch.Tensor):
+        def hook(param: torch.Tensor):
+            b = self.buckets[key]
+            g = param.grad
+            if g.data_ptr() != view.data_ptr():      # gradient did not land in the bucket: copy it in and alias
+                view.copy_(g)
+                param.grad = view
+            b["pending"] -= 1
+            if b["pending"] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: dict):
+        if self.world > 1:
+            if self.average:
+                b["flat"].div_(self.world)
+            self._handles.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Wait for every outstanding all-reduce (call after ``backward``), then re-arm for the next step."""
+        for b in self.buckets.values():         # buckets with parameters that received no gradient this step
+            if 0 < b["pending"] < len(b["params"]):
+                for p, v in zip(b["params"], b["views"]):
+                    if p.grad is None:
+                        v.zero_()
+                        p.grad = v
+                self._launch(b)
+        for h in self._handles:
+            h.wait()
+        self.reset()
+
+    def bytes_per_step(self) -> int:
+        return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets.values())
