@@ -126,6 +126,19 @@ int radmmm_flow_backward(const radmmm_flow_desc* d, const float* z_in, const flo
                          const float* dz_out, const float* dlog_s, float* dz_mid, float* dparams, float* dz_in,
                          float* dctx_rows, const radmmm_flow_grads* grads, void* scratch, void* stream);
 
+/* Context bi-LSTM recurrence (models/radmmm.py:137-146: pack_padded_sequence -> nn.LSTM(bidirectional, batch_first)
+ * -> pad_packed_sequence).  xproj [R][8H] fp32 holds W_ih x + b_ih + b_hh for every row (columns: direction, gate
+ * i|f|g|o, unit) and is produced by radmmm_conv_rows; the recurrence runs as ONE cooperative kernel per pass.
+ * out (B,Tp,2H) must be zero-initialised (frames beyond each length stay zero); gates [R][8H] and cstate [R][2H] are
+ * saved for the backward pass; dgates [R][8H] (zero-initialised) receives the pre-activation gate gradients, from which
+ * the weight / input gradients follow as contractions (radmmm_wgrad_rows / radmmm_conv_rows).  B <= 64 per call. */
+size_t radmmm_lstm_workspace_bytes(int B, int H);
+int radmmm_lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int32_t* lens, int B, int Tp,
+                        int H, float* out, float* gates, float* cstate, void* workspace, void* stream);
+int radmmm_lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f,
+                         const float* whh_r, const int32_t* lens, int B, int Tp, int H, float* dgates, void* workspace,
+                         void* stream);
+
 /* Stand-alone ops (also used by the tests) ------------------------------------------------------------- */
 
 /* Invertible 1x1 conv: out[b,co,t] = sum_ci W[co,ci]*(in[b,ci,t]-pre[ci]) + post[co]   (common.py:540-548,605-617) */
@@ -149,12 +162,13 @@ int radmmm_masked_sum_backward(const float* x, const int32_t* lens, int B, int C
 int radmmm_conv_rows(int mode, const void* x_rows, long long x_ld, long long x_plane, const void* w, long long w_ld,
                      long long w_plane, long long w_tap_stride, const float* bias, float* y, long long y_ld, int R,
                      int K, int N, int taps, int dilation, void* stream);
-/* Weight-gradient GEMM on rows (testing): out[tap][m][n] = sum_r dy[r][m] * x[r + (tap - taps/2)*dilation][n].
+/* Weight-gradient GEMM on rows: out[tap][m][n] = sum_r dy[r][m] * x[r + (tap - taps/2)*dilation + shift_offset][n].
  * dy [R][M] / x [R][N] are act-format row matrices (M, N multiples of 128 in the tensor-core modes).
  * `out` (fp32, [taps][M][out_ld]) is zeroed by the call. */
 int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_plane, const void* x,
                       long long x_ld, long long x_plane, float* out, long long out_ld,
-                      long long out_tap_stride, int R, int M, int N, int taps, int dilation, void* stream);
+                      long long out_tap_stride, int R, int M, int N, int taps, int dilation, int shift_offset,
+                      void* stream);
 /* fp32 rows -> act-format rows of `mode` (hi/lo split for BF16X3) */
 int radmmm_cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, void* stream);
 

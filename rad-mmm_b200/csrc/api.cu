@@ -135,6 +135,17 @@ int radmmm_flow_backward(const radmmm_flow_desc* d, const float* z_in, const flo
                          ST(stream));
 }
 
+size_t radmmm_lstm_workspace_bytes(int B, int H) { return lstm_workspace_bytes(B, H); }
+int radmmm_lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int32_t* lens, int B, int Tp,
+                        int H, float* out, float* gates, float* cstate, void* workspace, void* stream) {
+    return lstm_forward(xproj, whh_f, whh_r, lens, B, Tp, H, out, gates, cstate, workspace, ST(stream));
+}
+int radmmm_lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f,
+                         const float* whh_r, const int32_t* lens, int B, int Tp, int H, float* dgates, void* workspace,
+                         void* stream) {
+    return lstm_backward(dout, gates, cstate, whh_f, whh_r, lens, B, Tp, H, dgates, workspace, ST(stream));
+}
+
 int radmmm_inv1x1(const float* in, const float* W, const float* pre, const float* post, float* out, int B, int Cin,
                   int Cout, int Tp, void* stream) {
     return inv1x1(in, (long long)Cin * Tp, W, pre, post, out, (long long)Cout * Tp, B, Cin, Cout, Tp, ST(stream));
@@ -189,7 +200,8 @@ int radmmm_conv_rows(int mode, const void* x_rows, long long x_ld, long long x_p
 }
 int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_plane, const void* x,
                       long long x_ld, long long x_plane, float* out, long long out_ld,
-                      long long out_tap_stride, int R, int M, int N, int taps, int dilation, void* stream) {
+                      long long out_tap_stride, int R, int M, int N, int taps, int dilation, int shift_offset,
+                      void* stream) {
     RADMMM_REQUIRE(mode >= 0 && mode <= 2, "wgrad_rows: bad mode %d", mode);
     RADMMM_REQUIRE(taps >= 1 && taps <= kMaxSeg && taps % 2 == 1, "wgrad_rows: taps=%d must be odd and <= %d", taps, kMaxSeg);
     RADMMM_REQUIRE(R % 128 == 0, "wgrad_rows: R=%d must be a multiple of 128", R);
@@ -210,7 +222,7 @@ int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_pl
         s.a.ptr = const_cast<void*>(dy); s.a.ld = dy_ld; s.a.plane_stride = dy_plane;
         s.w.ptr = const_cast<void*>(x); s.w.ld = x_ld; s.w.plane_stride = x_plane;
         s.K = R;
-        s.shift = (j - taps / 2) * dilation;
+        s.shift = (j - taps / 2) * dilation + shift_offset;
         RADMMM_CUDA(cudaMemset2DAsync(out + j * out_tap_stride, sizeof(float) * out_ld, 0, sizeof(float) * N, M, ST(stream)));
     }
     return launch_gemm(a, mode, ST(stream));

@@ -122,10 +122,19 @@ __device__ __forceinline__ float pconv_ratio(int t, int len, int d) {
     return 5.0f / ((float)tap_count(t, len, d) + 1e-6f);
 }
 
-// torch.nn.Softplus(beta=1, threshold=20)
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+// torch.nn.Softplus(beta=1, threshold=20).  FAST (tensor-core modes) uses the MUFU ex2/lg2 intrinsics: absolute error
+// < 2e-7, far below the bf16 / bf16x3 operand rounding; the fp32 checker path keeps the precise libm forms.
+template <bool FAST>
+__device__ __forceinline__ float softplus_f(float x) {
+    if constexpr (FAST) return x > 20.0f ? x : __logf(1.0f + __expf(x));
+    else return x > 20.0f ? x : log1pf(expf(x));
+}
 // d softplus / dx written in terms of the OUTPUT h = softplus(x):  sigmoid(x) = 1 - exp(-h)
-__device__ __forceinline__ float sigmoid_from_softplus(float h) { return h > 20.0f ? 1.0f : -expm1f(-h); }
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_from_softplus(float h) {
+    if constexpr (FAST) return h > 20.0f ? 1.0f : 1.0f - __expf(-h);
+    else return h > 20.0f ? 1.0f : -expm1f(-h);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -466,31 +466,62 @@ int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const fl
 // =========================================================================================================
 // Bias gradients: out[n] = sum over valid rows of X[r][n] * (unratio ? 1/ratio(r) : 1).  X is an act matrix.
 // =========================================================================================================
+// block (32, 8): x = 8 consecutive columns per thread (one 16-byte load in the bf16 modes), y = row lane; each block
+// reduces 64 rows x 256 columns through shared memory and issues one atomic per column.
 template <int MODE>
-__global__ void colsum_kernel(ActMat x, RowGeom g, int n_cols, int dilation, int unratio, int rows_per_block,
-                              float* __restrict__ out) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_cols) return;
-    const int r_begin = blockIdx.y * rows_per_block, r_end = min(g.R, r_begin + rows_per_block);
-    float acc = 0.0f;
-    for (int r = r_begin; r < r_end; ++r) {
-        int b, t, len;
-        row_decode(g, r, b, t, len);
-        if (t < len) {
-            float w = unratio ? 1.0f / pconv_ratio(t, len, dilation) : 1.0f;
-            acc += act_load<MODE>(x, (long long)r * x.ld + n) * w;
+__global__ void __launch_bounds__(256) colsum_kernel(ActMat x, RowGeom g, int n_cols, int dilation, int unratio,
+                                                     float* __restrict__ out) {
+    __shared__ float red[8][256 + 8];
+    const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
+    const int r_begin = blockIdx.y * 64;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 < n_cols) {
+        for (int r = r_begin + threadIdx.y; r < min(g.R, r_begin + 64); r += 8) {
+            int b, t, len;
+            row_decode(g, r, b, t, len);
+            if (t >= len) continue;
+            const float w = unratio ? 1.0f / pconv_ratio(t, len, dilation) : 1.0f;
+            const long long idx = (long long)r * x.ld + c0;
+            float v[8];
+            if constexpr (MODE == MODE_F32) {
+                const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x.ptr) + idx);
+                const float4 c = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x.ptr) + idx + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+            } else {
+                const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(x.ptr);
+                const uint4 hv = *reinterpret_cast<const uint4*>(base + idx);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+                if constexpr (MODE == MODE_BF16X3) {
+                    const uint4 lv = *reinterpret_cast<const uint4*>(base + idx + x.plane_stride);
+                    const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(l2[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], w, acc[j]);
         }
     }
-    atomicAdd(out + n, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
+    __syncthreads();
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][tid];
+    const int c = blockIdx.x * 256 + tid;
+    if (c < n_cols && tot != 0.0f) atomicAdd(out + c, tot);
 }
 
 int colsum(int mode, ActMat x, const RowGeom& g, int n_cols, int dilation, int unratio, float* out, cudaStream_t st) {
+    RADMMM_REQUIRE(x.ld % 8 == 0, "colsum: row pitch must be a multiple of 8");
     RADMMM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, st));
-    const int rpb = 64;
-    dim3 grid(cdiv(n_cols, 128), cdiv(g.R, rpb));
-    if (mode == MODE_F32) colsum_kernel<MODE_F32><<<grid, 128, 0, st>>>(x, g, n_cols, dilation, unratio, rpb, out);
-    else if (mode == MODE_BF16) colsum_kernel<MODE_BF16><<<grid, 128, 0, st>>>(x, g, n_cols, dilation, unratio, rpb, out);
-    else colsum_kernel<MODE_BF16X3><<<grid, 128, 0, st>>>(x, g, n_cols, dilation, unratio, rpb, out);
+    dim3 grid(cdiv(n_cols, 256), cdiv(g.R, 64)), block(32, 8);
+    if (mode == MODE_F32) colsum_kernel<MODE_F32><<<grid, block, 0, st>>>(x, g, n_cols, dilation, unratio, out);
+    else if (mode == MODE_BF16) colsum_kernel<MODE_BF16><<<grid, block, 0, st>>>(x, g, n_cols, dilation, unratio, out);
+    else colsum_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(x, g, n_cols, dilation, unratio, out);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }

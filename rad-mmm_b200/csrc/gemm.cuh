@@ -115,33 +115,66 @@ __device__ __forceinline__ void load_row_vec(const ActMat& m, int r, int n0, flo
             v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
     } else {
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.ptr);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = act_load<MODE>(m, idx + i);
+        for (int i = 0; i < NV / 8; ++i) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(base + idx + 8 * i);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                v[8 * i + 2 * j] = f.x; v[8 * i + 2 * j + 1] = f.y;
+            }
+            if constexpr (MODE == MODE_BF16X3) {
+                const uint4 lv = *reinterpret_cast<const uint4*>(base + idx + m.plane_stride + 8 * i);
+                const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(l2[j]);
+                    v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+                }
+            }
+        }
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void load_vec_f32(const float* __restrict__ src, float* v) {   // 16-byte aligned source
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
     }
 }
 
 template <int MODE, int KIND, int NV>
 __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, float* acc) {
+    constexpr bool FAST = MODE != MODE_F32;
     int b, t, len;
     row_decode(p.geom, r, b, t, len);
     const bool valid = t < len;
     float out[NV];
     if constexpr (KIND == EPI_START) {
+        float bias[NV];
+        load_vec_f32<NV>(p.bias + n0, bias);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] + __ldg(p.bias + n0 + i) : 0.0f;
+        for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] + bias[i] : 0.0f;
         store_row_vec<MODE, NV>(p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_IN) {
         const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
+        float bias[NV];
+        load_vec_f32<NV>(p.bias + n0, bias);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) out[i] = valid ? softplus_f(acc[i] * ratio + __ldg(p.bias + n0 + i)) : 0.0f;
+        for (int i = 0; i < NV; ++i) out[i] = valid ? softplus_f<FAST>(acc[i] * ratio + bias[i]) : 0.0f;
         store_row_vec<MODE, NV>(p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_RS) {
         float s[NV];
+        load_vec_f32<NV>((valid ? p.bias : p.padq) + n0, s);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            float q = valid ? acc[i] + __ldg(p.bias + n0 + i) : __ldg(p.padq + n0 + i);
-            s[i] = softplus_f(q);
-            out[i] = valid ? sigmoid_from_softplus(s[i]) : 0.0f;
+            const float q = valid ? acc[i] + s[i] : s[i];
+            s[i] = softplus_f<FAST>(q);
+            out[i] = valid ? sigmoid_from_softplus<FAST>(s[i]) : 0.0f;
         }
         store_row_vec<MODE, NV>(p.out0, r, n0, out);           // sig_i (training only)
         float* o = p.f32_out + (long long)r * p.f32_ld + n0;
@@ -182,7 +215,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, flo
             load_row_vec<MODE, NV>(p.h, r, n0, hv);
             const float ratio = pconv_ratio(t, len, p.dilation);
 #pragma unroll
-            for (int i = 0; i < NV; ++i) out[i] = acc[i] * sigmoid_from_softplus(hv[i]) * ratio;
+            for (int i = 0; i < NV; ++i) out[i] = acc[i] * sigmoid_from_softplus<FAST>(hv[i]) * ratio;
         } else {
 #pragma unroll
             for (int i = 0; i < NV; ++i) out[i] = 0.0f;
@@ -208,6 +241,17 @@ template <int NV>
 __device__ __forceinline__ void epi_wgrad(const EpiParams& p, int tap, int m, int n0, const float* acc) {
     if (m >= p.M) return;
     float* o = p.f32_out + (long long)tap * p.f32_tap_stride + (long long)m * p.f32_ld + n0;
+    if (n0 + NV <= p.N && (p.f32_ld & 3) == 0) {       // whole vector in range: 16-byte vector reductions / stores
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            if (p.atomic)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(acc[4 * i]),
+                             "f"(acc[4 * i + 1]), "f"(acc[4 * i + 2]), "f"(acc[4 * i + 3]) : "memory");
+            else
+                *reinterpret_cast<float4*>(o + 4 * i) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i)
         if (n0 + i < p.N) {

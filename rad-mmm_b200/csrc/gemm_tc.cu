@@ -6,7 +6,8 @@
 //                              fp32 accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
 //                              overlaps the main loop of tile i+1; tcgen05.commit releases smem slots / publishes TMEM
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue       tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue (gemm.cuh) -> HBM
+//   warps 4-11  epilogue       tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue (gemm.cuh) -> HBM
+//                              (two warps per TMEM lane quarter, each draining half of the tile's columns)
 // A k=5 dilated conv is five K-segments whose A boxes are the same activation matrix shifted by (j-2)*d rows
 // (TMA zero-fills rows outside [0,R); utterances are separated by >= 16 zero rows, so no tap crosses a sequence).
 // MODE_BF16X3 loads hi and lo planes of both operands and issues hi*hi + lo*hi + hi*lo into the same accumulator.
@@ -22,7 +23,9 @@ namespace radmmm {
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;                    // two epilogue warps per scheduler: each TMEM lane quarter is split in
+                                                // two column halves
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kMaxMaps = 4;   // unique A maps and unique B maps per launch
 
 struct TcSeg {
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -300,7 +303,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------------------------------ epilogue
-        const int q = warp - 4;                      // TMEM lane quarter of this warp (warp % 4)
+        const int q = (warp - 4) & 3;                // TMEM lane quarter of this warp (== warp % 4)
+        const int half = (warp - 4) >> 2;            // which column half of the tile this warp drains
+        constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
             int mn = tile, tap = 0, split = 0;
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             bool has_acc = true;
             if (WGRAD) { int kb0, kb1; k_range(split, kb0, kb1); has_acc = kb1 > kb0; }
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), v);
                 const int n0 = n_blk * BN + c;
@@ -509,7 +514,7 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         const int tiles0 = P.m_tiles * P.n_tiles * P.taps;
         int split = args.split_k;
         if (split < 1) {
-            split = cdiv(4 * sm_count(), tiles0);
+            split = cdiv(2 * sm_count(), tiles0);
             const int max_split = P.k_blocks_total / 8 > 1 ? P.k_blocks_total / 8 : 1;
             if (split > max_split) split = max_split;
         }
@@ -522,11 +527,15 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         P.split_k = split;
         n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
         RADMMM_REQUIRE(split == 1 || args.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
-        RADMMM_TRY(make_map(&P.a_hi[0], g0.a.ptr, g0.a.ld, args.R, g0.a.ld, 64));
-        RADMMM_TRY(make_map(&P.b_hi[0], g0.w.ptr, g0.w.ld, args.R, g0.w.ld, 64));
+        // inner extents stop at the logical widths (rounded to the 64-channel box) so that operands which are column
+        // slices of wider matrices never read past their rows
+        const long long a_in = round_up(M, 64) < g0.a.ld ? round_up(M, 64) : g0.a.ld;
+        const long long b_in = round_up(N, 64) < g0.w.ld ? round_up(N, 64) : g0.w.ld;
+        RADMMM_TRY(make_map(&P.a_hi[0], g0.a.ptr, a_in, args.R, g0.a.ld, 64));
+        RADMMM_TRY(make_map(&P.b_hi[0], g0.w.ptr, b_in, args.R, g0.w.ld, 64));
         if (x3) {
-            RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.a.ptr + g0.a.plane_stride, g0.a.ld, args.R, g0.a.ld, 64));
-            RADMMM_TRY(make_map(&P.b_lo[0], (const __nv_bfloat16*)g0.w.ptr + g0.w.plane_stride, g0.w.ld, args.R, g0.w.ld, 64));
+            RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.a.ptr + g0.a.plane_stride, a_in, args.R, g0.a.ld, 64));
+            RADMMM_TRY(make_map(&P.b_lo[0], (const __nv_bfloat16*)g0.w.ptr + g0.w.plane_stride, b_in, args.R, g0.w.ld, 64));
         }
         for (int s = 0; s < args.n_seg; ++s) {
             RADMMM_REQUIRE(args.seg[s].a.ptr == g0.a.ptr && args.seg[s].w.ptr == g0.w.ptr, "gemm_tc: weight-grad taps must share operands");

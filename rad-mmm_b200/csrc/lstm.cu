@@ -1,0 +1,305 @@
+// Persistent bidirectional LSTM recurrence for the decoder's context encoder (models/radmmm.py:137-146:
+// pack_padded_sequence -> nn.LSTM(bidirectional) -> pad_packed_sequence).
+//
+// cuDNN runs this fp32 LSTM as ~10 launch-bound kernels per time step (measured: ~4000 launches, ~45 % of the train
+// step at B=8, T'=400).  Here the input projections for all frames are one contraction (gemm_tc / gemm_ffma) and the
+// sequential part is ONE cooperative kernel per pass:
+//   * one CTA per (direction, 8 hidden units); its 32 x H slice of W_hh stays in shared memory for the whole sequence;
+//   * per step each warp owns one hidden unit: lanes split the H-long dot products (4 gates x 8 sequences = 32 FMAs per
+//     3 shared loads), a halving butterfly leaves lane v with the sum for (gate v/8, sequence v%8), lanes 0-7 apply the
+//     gate non-linearities and keep c in a register;
+//   * the new h slice goes to a double-buffered exchange array in L2 and a per-direction arrive/spin barrier
+//     (one atomic per CTA per step) publishes it to the other CTAs of that direction.
+// Both directions run concurrently; variable lengths follow the packed semantics (the reverse direction of sequence b
+// starts at frame len_b-1; frames beyond len_b stay zero).  All arithmetic fp32.
+// Latency-bound by construction: T' dependent steps of (17 KB exchange + barrier); no roofline applies.
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace radmmm {
+
+namespace {
+
+constexpr int U = 8;          // hidden units per CTA (one per warp)
+constexpr int NT = 256;
+constexpr int BT = 8;         // sequences per register tile
+
+struct LstmParams {
+    const float* xproj;       // [R][8H]  W_ih x + b_ih + b_hh, columns [dir][gate i,f,g,o][H]
+    const float* whh[2];      // [4H][H] per direction
+    const int* lens;          // [B] grouped lengths
+    float* out;               // (B, Tp, 2H)
+    float* gates;             // [R][8H] post-activation gates (saved for backward)
+    float* cstate;            // [R][2H] cell state (saved for backward)
+    const float* dout;        // backward: (B, Tp, 2H)
+    float* dgates;            // backward: [R][8H] pre-activation gate gradients
+    float* xchg;              // exchange buffers
+    unsigned int* counters;   // [2] per-direction barrier counters (zeroed before launch)
+    int B, Bp, Tp, H, pitch, G;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void dir_barrier(unsigned int* counter, unsigned int target) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1u);
+        long long spins = 0;
+        while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            if (++spins > (1ll << 26)) { printf("radmmm lstm: barrier timed out\n"); __trap(); }
+        }
+    }
+    __syncthreads();
+}
+
+// halving butterfly: in: v[32] partial sums per lane; out: the full sum of element `lane` (returned)
+__device__ __forceinline__ float reduce32(float* v, int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+__device__ __forceinline__ float reduce8(float* v, int lane) {       // 8 values -> lane (l & 7) holds element l & 7
+#pragma unroll
+    for (int half = 4; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    float r = v[0];
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    return r;
+}
+
+__global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
+    extern __shared__ float sm[];
+    const int H = p.H, Bp = p.Bp;
+    float4* Wt = reinterpret_cast<float4*>(sm);             // [U][H] float4 = the 4 gates of (unit w, input k)
+    float* hs = sm + (size_t)U * H * 4;                     // [Bp][H]
+    const int dir = blockIdx.x / p.G, slice = blockIdx.x % p.G, u0 = slice * U;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float* Whh = p.whh[dir];
+    for (int i = tid; i < U * H; i += NT) {
+        const int uu = i / H, k = i % H;
+        Wt[i] = make_float4(Whh[(size_t)(0 * H + u0 + uu) * H + k], Whh[(size_t)(1 * H + u0 + uu) * H + k],
+                            Whh[(size_t)(2 * H + u0 + uu) * H + k], Whh[(size_t)(3 * H + u0 + uu) * H + k]);
+    }
+    for (int i = tid; i < Bp * H; i += NT) hs[i] = 0.0f;
+    int tmax = 0;
+    for (int b = 0; b < p.B; ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
+    __syncthreads();
+
+    const int n_tiles = Bp / BT;
+    float c_state[8];                                       // supports Bp <= 64
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c_state[i] = 0.0f;
+    const int unit = u0 + w;
+    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H;        // [2 parity][Bp][H]
+
+    for (int s = 0; s < tmax; ++s) {
+#pragma unroll 1
+        for (int bt = 0; bt < n_tiles; ++bt) {
+            // prefetch this step's input projection for (unit, sequence bt*8 + lane) while the mat-vec runs
+            const int bb = bt * BT + (lane & 7);
+            int len = 0, t = 0;
+            if (lane < 8 && bb < p.B) { len = min(p.lens[bb], p.Tp); t = dir ? len - 1 - s : s; }
+            const bool active = lane < 8 && bb < p.B && s < len;
+            const long long r = (long long)bb * p.pitch + t;
+            float xp[4] = {0.f, 0.f, 0.f, 0.f};
+            if (active) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xp[g] = __ldg(p.xproj + r * 8 * H + (size_t)dir * 4 * H + g * H + unit);
+            }
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+            const float* hb = hs + (size_t)bt * BT * H;
+            for (int k = lane; k < H; k += 32) {
+                const float4 w4 = Wt[w * H + k];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) {
+                    const float hv = hb[b * H + k];
+                    acc[0 * 8 + b] = fmaf(w4.x, hv, acc[0 * 8 + b]);
+                    acc[1 * 8 + b] = fmaf(w4.y, hv, acc[1 * 8 + b]);
+                    acc[2 * 8 + b] = fmaf(w4.z, hv, acc[2 * 8 + b]);
+                    acc[3 * 8 + b] = fmaf(w4.w, hv, acc[3 * 8 + b]);
+                }
+            }
+            const float mine = reduce32(acc, lane);         // lane v: gate v/8, sequence v%8
+            const float a_i = __shfl_sync(0xffffffffu, mine, (lane & 7));
+            const float a_f = __shfl_sync(0xffffffffu, mine, (lane & 7) + 8);
+            const float a_g = __shfl_sync(0xffffffffu, mine, (lane & 7) + 16);
+            const float a_o = __shfl_sync(0xffffffffu, mine, (lane & 7) + 24);
+            if (lane < 8 && bb < p.Bp) {
+                float h = 0.0f;
+                if (active) {
+                    const float gi = sigmoidf_(a_i + xp[0]), gf = sigmoidf_(a_f + xp[1]);
+                    const float gg = tanhf(a_g + xp[2]), go = sigmoidf_(a_o + xp[3]);
+                    const float c = gf * c_state[bt] + gi * gg;
+                    h = go * tanhf(c);
+                    c_state[bt] = c;
+                    float* gp = p.gates + r * 8 * H + (size_t)dir * 4 * H + unit;
+                    gp[0] = gi; gp[H] = gf; gp[2 * H] = gg; gp[3 * H] = go;
+                    p.cstate[r * 2 * H + (size_t)dir * H + unit] = c;
+                    p.out[((long long)bb * p.Tp + t) * 2 * H + (size_t)dir * H + unit] = h;
+                }
+                xbuf[((size_t)(s & 1) * Bp + bb) * H + unit] = h;
+            }
+        }
+        if (s + 1 == tmax) break;
+        dir_barrier(p.counters + dir, (unsigned int)p.G * (s + 1));
+        const float* src = xbuf + (size_t)(s & 1) * Bp * H;
+        for (int i = tid; i < Bp * H; i += NT) hs[i] = __ldcg(src + i);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
+    extern __shared__ float sm[];
+    const int H = p.H, Bp = p.Bp, H4 = 4 * p.H;
+    float* Wb = sm;                                          // [U][4H]   Wb[w][rho] = Whh[rho][u0 + w]
+    float* dgs = sm + (size_t)U * H4;                        // [BT][4H]
+    const int dir = blockIdx.x / p.G, slice = blockIdx.x % p.G, u0 = slice * U;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float* Whh = p.whh[dir];
+    for (int i = tid; i < U * H4; i += NT) {
+        const int uu = i / H4, rho = i % H4;
+        Wb[i] = Whh[(size_t)rho * H + u0 + uu];
+    }
+    int tmax = 0;
+    for (int b = 0; b < p.B; ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
+    __syncthreads();
+    const int n_tiles = Bp / BT;
+    float dh_rec[8], dc_next[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dh_rec[i] = 0.0f; dc_next[i] = 0.0f; }
+    const int unit = u0 + w;
+    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H4;        // [2 parity][Bp][4H]
+
+    for (int s = tmax - 1; s >= 0; --s) {
+        // phase 1: gate gradients of this CTA's units
+#pragma unroll 1
+        for (int bt = 0; bt < n_tiles; ++bt) {
+            const int bb = bt * BT + (lane & 7);
+            if (lane < 8 && bb < Bp) {
+                int len = 0;
+                if (bb < p.B) len = min(p.lens[bb], p.Tp);
+                const bool active = bb < p.B && s < len;
+                float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
+                if (active) {
+                    const int t = dir ? len - 1 - s : s;
+                    const long long r = (long long)bb * p.pitch + t;
+                    const float* gp = p.gates + r * 8 * H + (size_t)dir * 4 * H + unit;
+                    const float gi = gp[0], gf = gp[H], gg = gp[2 * H], go = gp[3 * H];
+                    const float c = p.cstate[r * 2 * H + (size_t)dir * H + unit];
+                    const long long rp = dir ? r + 1 : r - 1;
+                    const float c_prev = (s > 0) ? p.cstate[rp * 2 * H + (size_t)dir * H + unit] : 0.0f;
+                    const float dh = p.dout[((long long)bb * p.Tp + t) * 2 * H + (size_t)dir * H + unit] + dh_rec[bt];
+                    const float tc = tanhf(c);
+                    const float dc = dh * go * (1.0f - tc * tc) + dc_next[bt];
+                    d_o = dh * tc * go * (1.0f - go);
+                    d_i = dc * gg * gi * (1.0f - gi);
+                    d_g = dc * gi * (1.0f - gg * gg);
+                    d_f = dc * c_prev * gf * (1.0f - gf);
+                    dc_next[bt] = dc * gf;
+                    float* dg = p.dgates + r * 8 * H + (size_t)dir * 4 * H + unit;
+                    dg[0] = d_i; dg[H] = d_f; dg[2 * H] = d_g; dg[3 * H] = d_o;
+                } else {
+                    dc_next[bt] = 0.0f;
+                }
+                float* x = xbuf + ((size_t)(s & 1) * Bp + bb) * H4 + unit;
+                x[0] = d_i; x[H] = d_f; x[2 * H] = d_g; x[3 * H] = d_o;
+            }
+        }
+        if (s == 0) break;
+        dir_barrier(p.counters + dir, (unsigned int)p.G * (tmax - s));
+        // phase 2: dh_rec[b][unit] = sum_rho Whh[rho][unit] * dG[b][rho]
+#pragma unroll 1
+        for (int bt = 0; bt < n_tiles; ++bt) {
+            const float* src = xbuf + ((size_t)(s & 1) * Bp + (size_t)bt * BT) * H4;
+            __syncthreads();
+            for (int i = tid; i < BT * H4; i += NT) dgs[i] = __ldcg(src + i);
+            __syncthreads();
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+            for (int rho = lane; rho < H4; rho += 32) {
+                const float wv = Wb[w * H4 + rho];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = fmaf(wv, dgs[b * H4 + rho], acc[b]);
+            }
+            const float v = reduce8(acc, lane);              // lane l holds sequence l & 7
+            dh_rec[bt] = v;
+        }
+    }
+}
+
+}  // namespace
+
+size_t lstm_workspace_bytes(int B, int H) {
+    const int Bp = (int)round_up(B, BT);
+    return 256 + sizeof(float) * 2 * 2 * (size_t)Bp * 4 * H;      // counters + the larger (backward) exchange buffers
+}
+
+static int lstm_common(LstmParams& p, const int* lens, int B, int Tp, int H, void* workspace) {
+    RADMMM_REQUIRE(H % U == 0 && H >= U, "lstm: hidden size %d must be a multiple of %d", H, U);
+    RADMMM_REQUIRE(B >= 1 && B <= 64, "lstm: batch %d must be in [1, 64] (chunk larger batches)", B);
+    RADMMM_REQUIRE(workspace != nullptr, "lstm: workspace missing");
+    p.lens = lens; p.B = B; p.Bp = (int)round_up(B, BT); p.Tp = Tp; p.H = H; p.pitch = Tp + 16; p.G = H / U;
+    p.counters = reinterpret_cast<unsigned int*>(workspace);
+    p.xchg = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    RADMMM_REQUIRE(2 * p.G <= sms, "lstm: needs %d co-resident CTAs but the device has %d SMs", 2 * p.G, sms);
+    return RADMMM_OK;
+}
+
+int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
+                 float* out, float* gates, float* cstate, void* workspace, cudaStream_t st) {
+    LstmParams p;
+    memset(&p, 0, sizeof(p));
+    RADMMM_TRY(lstm_common(p, lens, B, Tp, H, workspace));
+    p.xproj = xproj; p.whh[0] = whh_f; p.whh[1] = whh_r; p.out = out; p.gates = gates; p.cstate = cstate;
+    const size_t smem = sizeof(float) * ((size_t)U * H * 4 + (size_t)p.Bp * H);
+    RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d, B=%d)", smem, H, B);
+    RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
+    void* args[] = {&p};
+    RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
+    return RADMMM_OK;
+}
+
+int lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
+                  const int* lens, int B, int Tp, int H, float* dgates, void* workspace, cudaStream_t st) {
+    LstmParams p;
+    memset(&p, 0, sizeof(p));
+    RADMMM_TRY(lstm_common(p, lens, B, Tp, H, workspace));
+    p.dout = dout; p.gates = const_cast<float*>(gates); p.cstate = const_cast<float*>(cstate);
+    p.whh[0] = whh_f; p.whh[1] = whh_r; p.dgates = dgates;
+    const size_t smem = sizeof(float) * ((size_t)U * 4 * H + (size_t)BT * 4 * H);
+    RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d)", smem, H);
+    RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
+    void* args[] = {&p};
+    RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
+    return RADMMM_OK;
+}
+
+}  // namespace radmmm

@@ -32,6 +32,12 @@ int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const fl
 int colsum(int mode, ActMat x, const RowGeom& g, int n_cols, int dilation, int unratio, float* out, cudaStream_t st);
 int cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, cudaStream_t st);
 
+size_t lstm_workspace_bytes(int B, int H);
+int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
+                 float* out, float* gates, float* cstate, void* workspace, cudaStream_t st);
+int lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
+                  const int* lens, int B, int Tp, int H, float* dgates, void* workspace, cudaStream_t st);
+
 int spline_fwd(const float* z1, const float* q, const int* lens, float* z1_out, float* log_s, int B, int Ch, int Tp,
                int n_bins, float lo, float hi, int inverse, cudaStream_t st);
 int spline_bwd(const float* z1, const float* q, const int* lens, const float* dz1_out, const float* dlog_s, float* dz1,

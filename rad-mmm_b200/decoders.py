@@ -120,6 +120,7 @@ class RADMMMFlow(RADMMM):
         for fs in self.flows:
             if hasattr(fs.coupling_tfn, "precision"):
                 fs.coupling_tfn.precision = precision
+        self.lstm_precision = precision if precision == "fp32" else "bf16x3"    # the conditioning stays fp32-grade
         return self
 
     def is_attribute_unconditional(self):

@@ -3,8 +3,8 @@
 ``preprocess_context`` keeps the reference's semantics -- squeeze context / f0 / energy by ``n_group_size``,
 concatenate speaker (and optionally accent) vectors, run the packed bi-LSTM -- and returns the same
 ``(B, decoder_cond_dims, T')`` tensor (a transposed view of the batch-first LSTM output, exactly as the reference
-returns it).  The LSTM stays ``nn.LSTM``/cuDNN host code: it is 3 % of the FLOPs and not
-part of the flow-step kernels.
+returns it).  The LSTM parameters stay in an ``nn.LSTM`` module (state-dict compatible) but the computation runs on the
+persistent recurrence kernel of ``radmmm_b200.lstm`` -- cuDNN's fp32 LSTM is ~4000 launch-bound kernels per step.
 """
 from __future__ import annotations
 
@@ -63,6 +63,7 @@ class RADMMM(torch.nn.Module):
             decoder_cond_dims = hidden * 2
             self.context_lstm = nn.LSTM(input_size=n_in, hidden_size=hidden, num_layers=1, batch_first=True,
                                         bidirectional=True)
+            self._plain_lstm = context_lstm_norm is None
             if context_lstm_norm is not None:
                 fn = nn.utils.spectral_norm if "spectral" in context_lstm_norm else nn.utils.weight_norm
                 self.context_lstm = fn(self.context_lstm, "weight_hh_l0")
@@ -89,8 +90,15 @@ class RADMMM(torch.nn.Module):
         x = torch.cat(parts, 1)
         if not self.use_context_lstm:
             return x
-        lens_g = torch.div(out_lens, g, rounding_mode="floor").long().cpu()
-        packed = nn.utils.rnn.pack_padded_sequence(x.transpose(1, 2), lens_g, batch_first=True, enforce_sorted=False)
+        lens_g = torch.div(out_lens, g, rounding_mode="floor").long()
+        if self._plain_lstm:
+            from ..lstm import context_lstm
+            out = context_lstm(self.context_lstm, x.transpose(1, 2).contiguous(), lens_g,
+                               getattr(self, "lstm_precision", "bf16x3"))
+            return out.transpose(1, 2)
+        # spectral / weight-normed recurrent weights (context_lstm_norm): the norm lives in nn.LSTM forward hooks, so
+        # this configuration (not used by the shipped configs) keeps the library LSTM
+        packed = nn.utils.rnn.pack_padded_sequence(x.transpose(1, 2), lens_g.cpu(), batch_first=True, enforce_sorted=False)
         self.context_lstm.flatten_parameters()
         out, _ = self.context_lstm(packed)
         out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=tp)

@@ -201,3 +201,36 @@ def test_infer_api():
         c = dec.infer(spk, txt, 0.7, dur=dur, f0=f0, energy_avg=en, out_lens=out_lens)["mel"]
     assert a.shape == (B, 80, T // 2 * 2)
     assert torch.equal(a, b) and torch.isfinite(c).all() and not torch.equal(a, c)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("batch,lens", [(3, [37, 20, 5]), (2, [9, 9]), (11, [40, 33, 31, 30, 25, 17, 16, 9, 3, 2, 1])])
+def test_context_lstm_vs_torch(precision, batch, lens):
+    """Persistent bi-LSTM kernel (forward + all gradients) vs torch's packed nn.LSTM in fp64 on the CPU."""
+    from radmmm_b200.lstm import context_lstm
+    T, n_in, hid = max(lens), 20, 16
+    ref = torch.nn.LSTM(n_in, hid, 1, batch_first=True, bidirectional=True)
+    for n, p in ref.named_parameters():
+        p.data.copy_(syn.hash_uniform("lstm." + n, tuple(p.shape), -0.4, 0.4))
+    x = syn.hash_uniform("lstm.x", (batch, T, n_in), -1, 1)
+    lens_t = torch.tensor(lens)
+    mask = of.length_mask(lens_t, T)[..., None].float()
+    gout = syn.hash_uniform("lstm.g", (batch, T, 2 * hid)) * mask
+    ref64 = torch.nn.LSTM(n_in, hid, 1, batch_first=True, bidirectional=True).double()
+    ref64.load_state_dict(ref.state_dict())
+    xc = (x * mask).double().requires_grad_(True)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(xc, lens_t, batch_first=True, enforce_sorted=False)
+    yo, _ = ref64(packed)
+    yo, _ = torch.nn.utils.rnn.pad_packed_sequence(yo, batch_first=True, total_length=T)
+    (yo * gout.double()).sum().backward()
+    mine = torch.nn.LSTM(n_in, hid, 1, batch_first=True, bidirectional=True)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV)
+    xg = (x * mask).to(DEV).requires_grad_(True)
+    y = context_lstm(mine, xg, lens_t.to(DEV), precision)
+    tol = 2e-5 if precision == "fp32" else 2e-4
+    close(y, yo.detach(), tol, what="lstm out")
+    (y * gout.to(DEV)).sum().backward()
+    close(xg.grad.cpu().double() * mask.double(), xc.grad * mask.double(), tol * 5, what="lstm dx")
+    for (n, p), (_, q) in zip(mine.named_parameters(), ref64.named_parameters()):
+        close(p.grad, q.grad, tol * 10 * max(1.0, q.grad.abs().max().item()), what="lstm grad " + n)

@@ -64,7 +64,7 @@ def test_wgrad_rows(precision, taps, dil, M, Nx):
     xb, xld, xpl = cast_rows(x, mode)
     out = torch.full((taps, M, Nx), float("nan"), device=DEV)
     N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dyb), dld, dpl, N.ptr(xb), xld, xpl, N.fptr(out), Nx,
-                                  M * Nx, R, M, Nx, taps, dil, N.stream()))
+                                  M * Nx, R, M, Nx, taps, dil, 0, N.stream()))
     torch.cuda.synchronize()
     dyd, xd = dy.double().cpu(), x.double().cpu()
     ref = torch.zeros(taps, M, Nx, dtype=torch.float64)
