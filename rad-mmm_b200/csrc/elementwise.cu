@@ -178,8 +178,9 @@ int coupling_bwd(const float* dz_out, const float* dlog_s, const float* z, const
 
 // =========================================================================================================
 // Invertible 1x1 convolution (common.py:540-548, 605-617):  out[b,co,t] = sum_ci W[co,ci]*(in[b,ci,t]-pre[ci]) + post[co]
-// One CTA per (32-frame tile, batch): W streamed through shared memory in 32-column panels; x tile resident.
-// fp32 FFMA; HBM-bound: 2*C*4 bytes per grouped frame.
+// One CTA per (32-frame tile, batch): W^T (padded rows) and the x tile are resident in shared memory; a thread owns
+// 4 consecutive frames x up to 8 output channels (co = ty + 32 i): per input channel 1 LDS.128 + <=8 LDS for <=32 FMAs.
+// fp32 FFMA; HBM-bound: 2*C*4 bytes per grouped frame (W, 100 KB, is re-read from L2 by every CTA).
 // =========================================================================================================
 constexpr int INV_TT = 32;
 __global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
@@ -187,52 +188,59 @@ __global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ i
                                                      const float* __restrict__ post, float* __restrict__ out,
                                                      long long out_bs, int Cin, int Cout, int Tp) {
     extern __shared__ float sm[];
-    float* xs = sm;                    // [Cin][INV_TT]
-    float* ws = sm + Cin * INV_TT;     // [Cout][33] panel of 32 input channels
+    const int ldw = Cout + 1;
+    float* xs = sm;                          // [Cin][INV_TT]
+    float* wt = sm + (size_t)Cin * INV_TT;   // [Cin][Cout + 1]  (transposed W)
     const int t0 = blockIdx.x * INV_TT, b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;     // 8 x 32
     for (int i = tid; i < Cin * INV_TT; i += 256) {
         const int c = i / INV_TT, t = t0 + (i % INV_TT);
-        float v = 0.0f;
-        if (t < Tp) v = in[(long long)b * in_bs + (long long)c * Tp + t] - (pre ? pre[c] : 0.0f);
-        xs[i] = v;
+        xs[i] = (t < Tp) ? in[(long long)b * in_bs + (long long)c * Tp + t] - (pre ? pre[c] : 0.0f) : 0.0f;
     }
-    // each warp owns output channels wid, wid+8, ...; lane = frame
-    constexpr int MAXO = 32;           // supports Cout <= 256
-    float acc[MAXO];
+    for (int i = tid; i < Cout * Cin; i += 256) {
+        const int co = i / Cin, ci = i % Cin;
+        wt[ci * ldw + co] = W[i];
+    }
+    __syncthreads();
+    constexpr int MAXO = 8;                  // Cout <= 256
+    float acc[MAXO][4];
 #pragma unroll
-    for (int i = 0; i < MAXO; ++i) acc[i] = 0.0f;
-    for (int k0 = 0; k0 < Cin; k0 += 32) {
-        __syncthreads();
-        for (int i = tid; i < Cout * 32; i += 256) {
-            const int co = i >> 5, k = i & 31;
-            ws[co * 33 + k] = (k0 + k < Cin) ? W[(long long)co * Cin + k0 + k] : 0.0f;
-        }
-        __syncthreads();
-        const int kmax = min(32, Cin - k0);
-        for (int k = 0; k < kmax; ++k) {
-            const float xv = xs[(k0 + k) * INV_TT + lane];
+    for (int i = 0; i < MAXO; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
+    for (int k = 0; k < Cin; ++k) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + k * INV_TT + 4 * tx);
+        const float* wr = wt + k * ldw + ty;
 #pragma unroll
-            for (int i = 0; i < MAXO; ++i) {
-                const int co = wid + 8 * i;
-                if (co < Cout) acc[i] = fmaf(ws[co * 33 + k], xv, acc[i]);
+        for (int i = 0; i < MAXO; ++i) {
+            if (ty + 32 * i < Cout) {
+                const float w = wr[32 * i];
+                acc[i][0] = fmaf(w, x4.x, acc[i][0]); acc[i][1] = fmaf(w, x4.y, acc[i][1]);
+                acc[i][2] = fmaf(w, x4.z, acc[i][2]); acc[i][3] = fmaf(w, x4.w, acc[i][3]);
             }
         }
     }
-    const int t = t0 + lane;
-    if (t < Tp) {
+    const int t = t0 + 4 * tx;
 #pragma unroll
-        for (int i = 0; i < MAXO; ++i) {
-            const int co = wid + 8 * i;
-            if (co < Cout) out[(long long)b * out_bs + (long long)co * Tp + t] = acc[i] + (post ? post[co] : 0.0f);
+    for (int i = 0; i < MAXO; ++i) {
+        const int co = ty + 32 * i;
+        if (co < Cout) {
+            const float pb = post ? post[co] : 0.0f;
+            float* o = out + (long long)b * out_bs + (long long)co * Tp + t;
+            if (t + 3 < Tp && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                *reinterpret_cast<float4*>(o) = make_float4(acc[i][0] + pb, acc[i][1] + pb, acc[i][2] + pb, acc[i][3] + pb);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (t + j < Tp) o[j] = acc[i][j] + pb;
+            }
         }
     }
 }
 
 int inv1x1(const float* in, long long in_bs, const float* W, const float* pre, const float* post, float* out,
            long long out_bs, int B, int Cin, int Cout, int Tp, cudaStream_t st) {
-    RADMMM_REQUIRE(Cout <= 256 && Cin <= 1024, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
-    size_t smem = ((size_t)Cin * INV_TT + (size_t)Cout * 33) * sizeof(float);
+    RADMMM_REQUIRE(Cout <= 256 && Cin <= 256, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
+    size_t smem = ((size_t)Cin * INV_TT + (size_t)Cin * (Cout + 1)) * sizeof(float);
+    RADMMM_REQUIRE(smem <= 220 * 1024, "inv1x1: shared memory %zu B too large", smem);
     if (smem > 48 * 1024) RADMMM_CUDA(cudaFuncSetAttribute(inv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(Tp, INV_TT), B);
     inv1x1_kernel<<<grid, 256, smem, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);

@@ -16,9 +16,9 @@ namespace radmmm {
 enum {
     EPI_START = 0,  // h0 = (acc + bias) masked                               (common.py:820)
     EPI_IN = 1,     // h = softplus(acc * ratio + bias) masked                 (partialconv1d.py:84-94, common.py:190,830)
-    EPI_RS = 2,     // s = softplus(acc + bias); out += s; sig = 1-exp(-s)     (common.py:831-832)
+    EPI_RS = 2,     // s_i = softplus(acc + bias) stored per layer               (common.py:831-832)
     EPI_END = 3,    // params = acc + bias -> channels-first fp32              (common.py:834)
-    EPI_DOUT = 4,   // d_out = acc; dq_i = d_out * sig_i  for every layer i
+    EPI_DOUT = 4,   // d_out = acc; dq_i = d_out * (1 - exp(-s_i))  for every layer i
     EPI_DH = 5,     // dacc = acc * softplus'(p) * ratio, masked
     EPI_DH0 = 6,    // dh0 = acc masked
     EPI_DZ0 = 7,    // dz0 -> channels-first fp32 (accumulate)
@@ -50,7 +50,7 @@ struct EpiParams {
     long long f32_ld;
     long long f32_tap_stride;    // weight-grad: elements between taps
     const float* padq;
-    ActMat sig[kMaxLayers];
+    ActMat sig[kMaxLayers];      // the stored s_i (EPI_DOUT input)
     ActMat dq[kMaxLayers];
     ActMat h;
     float* cf_out;               // channels-first (B, cf_C, Tp) fp32
@@ -70,11 +70,85 @@ struct GemmArgs {
 
 // ---------------------------------------------------------------------------------------------------------
 // Epilogue for one row r and NV consecutive columns n0..n0+NV-1 (n0 % NV == 0, NV in {4, 8, 16, 32}).
-// `lane_rows` tells whether consecutive lanes hold consecutive rows (tcgen05 path) -- only a perf hint.
+//
+// On the tcgen05 path a warp holds 32 consecutive rows (lane = row), so a per-thread 64-byte row store would touch 32
+// different lines per instruction.  `Stager` gives each epilogue warp a small shared-memory tile: values are written
+// there row-wise, then the warp moves 8 rows x 64 B per instruction (full sectors, 4x fewer line transactions); loads
+// of saved activations go the same way in reverse.  The FFMA path passes a null stager (its thread tile is already
+// 8 columns x 8 rows per thread with 16 lanes side by side).
 // ---------------------------------------------------------------------------------------------------------
+struct Stager {
+    __nv_bfloat16* buf;   // [32 rows][kStageLd] per warp, or nullptr
+    int lane;
+};
+constexpr int kStageLd = 40;   // 32 bf16 + 8 pad (80 B rows: conflict-light 16-byte accesses)
+
+template <int MODE>
+__device__ __forceinline__ void staged_store32(const Stager& st, const ActMat& m, int r, int n0, const float* v) {
+    // r = row of THIS thread (row_base + lane); all 32 lanes call together
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(m.ptr);
+    const int row_base = r - st.lane;
+#pragma unroll
+    for (int plane = 0; plane < (MODE == MODE_BF16X3 ? 2 : 1); ++plane) {
+        __nv_bfloat162 h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float a = v[2 * j], b = v[2 * j + 1];
+            if (plane == 1) {
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+                a -= __bfloat162float(hi.x); b -= __bfloat162float(hi.y);
+            }
+            h[j] = __floats2bfloat162_rn(a, b);
+        }
+        uint4* mine = reinterpret_cast<uint4*>(st.buf + st.lane * kStageLd);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mine[j] = reinterpret_cast<uint4*>(h)[j];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (st.lane >> 2), seg = st.lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(st.buf + rr * kStageLd + seg * 8);
+            *reinterpret_cast<uint4*>(base + (long long)plane * m.plane_stride + (long long)(row_base + rr) * m.ld + n0 + seg * 8) = val;
+        }
+        __syncwarp();
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void staged_load32(const Stager& st, const ActMat& m, int r, int n0, float* v) {
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.ptr);
+    const int row_base = r - st.lane;
+#pragma unroll
+    for (int plane = 0; plane < (MODE == MODE_BF16X3 ? 2 : 1); ++plane) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (st.lane >> 2), seg = st.lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(base + (long long)plane * m.plane_stride + (long long)(row_base + rr) * m.ld + n0 + seg * 8);
+            *reinterpret_cast<uint4*>(st.buf + rr * kStageLd + seg * 8) = val;
+        }
+        __syncwarp();
+        const uint4* mine = reinterpret_cast<const uint4*>(st.buf + st.lane * kStageLd);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 q = mine[j];
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h2[k]);
+                if (plane == 0) { v[8 * j + 2 * k] = f.x; v[8 * j + 2 * k + 1] = f.y; }
+                else { v[8 * j + 2 * k] += f.x; v[8 * j + 2 * k + 1] += f.y; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <int MODE, int NV>
-__device__ __forceinline__ void store_row_vec(const ActMat& m, int r, int n0, const float* v) {
+__device__ __forceinline__ void store_row_vec(const Stager& st, const ActMat& m, int r, int n0, const float* v) {
     if (m.ptr == nullptr) return;
+    if constexpr (MODE != MODE_F32 && NV == 32) {
+        if (st.buf != nullptr) { staged_store32<MODE>(st, m, r, n0, v); return; }
+    }
     long long idx = (long long)r * m.ld + n0;
     if constexpr (MODE == MODE_F32) {
         float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(m.ptr) + idx);
@@ -105,7 +179,10 @@ __device__ __forceinline__ void store_row_vec(const ActMat& m, int r, int n0, co
 }
 
 template <int MODE, int NV>
-__device__ __forceinline__ void load_row_vec(const ActMat& m, int r, int n0, float* v) {
+__device__ __forceinline__ void load_row_vec(const Stager& st, const ActMat& m, int r, int n0, float* v) {
+    if constexpr (MODE != MODE_F32 && NV == 32) {
+        if (st.buf != nullptr) { staged_load32<MODE>(st, m, r, n0, v); return; }
+    }
     long long idx = (long long)r * m.ld + n0;
     if constexpr (MODE == MODE_F32) {
         const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(m.ptr) + idx);
@@ -148,7 +225,7 @@ __device__ __forceinline__ void load_vec_f32(const float* __restrict__ src, floa
 }
 
 template <int MODE, int KIND, int NV>
-__device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, float* acc) {
+__device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, int r, int n0, float* acc) {
     constexpr bool FAST = MODE != MODE_F32;
     int b, t, len;
     row_decode(p.geom, r, b, t, len);
@@ -159,35 +236,22 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, flo
         load_vec_f32<NV>(p.bias + n0, bias);
 #pragma unroll
         for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] + bias[i] : 0.0f;
-        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_IN) {
         const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
         float bias[NV];
         load_vec_f32<NV>(p.bias + n0, bias);
 #pragma unroll
         for (int i = 0; i < NV; ++i) out[i] = valid ? softplus_f<FAST>(acc[i] * ratio + bias[i]) : 0.0f;
-        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_RS) {
+        // s_i = softplus(res_skip_i(h)); frames beyond the length carry the reference's constant softplus(padq).
+        // The skip sum is never materialised: the `end` GEMM contracts over the L stored s_i as K-segments.
         float s[NV];
         load_vec_f32<NV>((valid ? p.bias : p.padq) + n0, s);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const float q = valid ? acc[i] + s[i] : s[i];
-            s[i] = softplus_f<FAST>(q);
-            out[i] = valid ? sigmoid_from_softplus<FAST>(s[i]) : 0.0f;
-        }
-        store_row_vec<MODE, NV>(p.out0, r, n0, out);           // sig_i (training only)
-        float* o = p.f32_out + (long long)r * p.f32_ld + n0;
-#pragma unroll
-        for (int i = 0; i < NV / 4; ++i) {
-            float4 prev = p.first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(o)[i];
-            prev.x += s[4 * i]; prev.y += s[4 * i + 1]; prev.z += s[4 * i + 2]; prev.w += s[4 * i + 3];
-            reinterpret_cast<float4*>(o)[i] = prev;
-            s[4 * i] = prev.x; s[4 * i + 1] = prev.y; s[4 * i + 2] = prev.z; s[4 * i + 3] = prev.w;
-        }
-        if (p.last) {
-            store_row_vec<MODE, NV>(p.out1, r, n0, s);
-        }
+        for (int i = 0; i < NV; ++i) out[i] = softplus_f<FAST>(valid ? acc[i] + s[i] : s[i]);
+        store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_END || KIND == EPI_DZ0) {
         if (b < p.geom.B && t < p.geom.Tp) {
 #pragma unroll
@@ -203,28 +267,23 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int r, int n0, flo
         }
     } else if constexpr (KIND == EPI_DOUT) {
         for (int l = 0; l < p.n_layers; ++l) {
-            float sg[NV];
-            load_row_vec<MODE, NV>(p.sig[l], r, n0, sg);
+            float sv[NV];
+            load_row_vec<MODE, NV>(st, p.sig[l], r, n0, sv);          // s_l = softplus(q_l); d softplus = 1 - exp(-s)
 #pragma unroll
-            for (int i = 0; i < NV; ++i) out[i] = acc[i] * sg[i];
-            store_row_vec<MODE, NV>(p.dq[l], r, n0, out);
+            for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<FAST>(sv[i]) : 0.0f;
+            store_row_vec<MODE, NV>(st, p.dq[l], r, n0, out);
         }
     } else if constexpr (KIND == EPI_DH) {
-        if (valid) {
-            float hv[NV];
-            load_row_vec<MODE, NV>(p.h, r, n0, hv);
-            const float ratio = pconv_ratio(t, len, p.dilation);
+        float hv[NV];
+        load_row_vec<MODE, NV>(st, p.h, r, n0, hv);             // all lanes take part (staged, warp-cooperative)
+        const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) out[i] = acc[i] * sigmoid_from_softplus<FAST>(hv[i]) * ratio;
-        } else {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) out[i] = 0.0f;
-        }
-        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<FAST>(hv[i]) * ratio : 0.0f;
+        store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_DH0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] : 0.0f;
-        store_row_vec<MODE, NV>(p.out0, r, n0, out);
+        store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_DCTX || KIND == EPI_F32) {
         float* o = p.f32_out + (long long)r * p.f32_ld + n0;
 #pragma unroll

@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(NT) gemm_ffma_kernel(const GemmArgs args) {
                     const int k = idx >> 5, q = idx & 31;
                     const int r = k0 + k;
                     const int mc = m0 + 4 * q, nc = n0 + 4 * q;
-                    ra[i] = (r < args.R && mc < lda && mc < args.epi.M) ? *reinterpret_cast<const float4*>(A + (long long)r * lda + mc)
+                    ra[i] = (r < args.R && mc < lda && mc < ((args.epi.M + 3) & ~3)) ? *reinterpret_cast<const float4*>(A + (long long)r * lda + mc)
                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                     const int rx = r + sg.shift;
-                    rb[i] = (rx >= 0 && rx < args.R && nc < ldw && nc < args.epi.N)
+                    rb[i] = (rx >= 0 && rx < args.R && nc < ldw && nc < ((args.epi.N + 3) & ~3))
                                 ? *reinterpret_cast<const float4*>(W + (long long)rx * ldw + nc)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -117,8 +117,9 @@ __global__ void __launch_bounds__(NT) gemm_ffma_kernel(const GemmArgs args) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) epi_wgrad<8>(args.epi, tap, m0 + ty * 8 + i, n0 + tx * 8, acc[i]);
     } else {
+        const Stager none{nullptr, 0};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) epi_apply<MODE_F32, KIND, 8>(args.epi, m0 + ty * 8 + i, n0 + tx * 8, acc[i]);
+        for (int i = 0; i < 8; ++i) epi_apply<MODE_F32, KIND, 8>(args.epi, none, m0 + ty * 8 + i, n0 + tx * 8, acc[i]);
     }
 }
 
@@ -138,7 +139,6 @@ int launch_gemm_ffma(const GemmArgs& args, cudaStream_t stream) {
     for (int s = 0; s < args.n_seg; ++s)
         RADMMM_REQUIRE(args.wgrad || args.seg[s].K % BK == 0, "gemm_ffma: K=%d must be a multiple of %d", args.seg[s].K, BK);
     if (args.wgrad) {
-        RADMMM_REQUIRE(args.epi.M % 4 == 0 && args.epi.N % 4 == 0, "gemm_ffma: weight-grad M=%d, N=%d must be multiples of 4", args.epi.M, args.epi.N);
         GemmArgs a2 = args;
         if (a2.split_k < 1) {      // auto: aim for >= ~300 CTAs
             const long long tiles = (long long)cdiv(args.epi.M, BM) * cdiv(args.epi.N, BN) * args.n_seg;

@@ -150,7 +150,8 @@ struct Cfg {
     static constexpr int stage_bytes = planes * (a_bytes + b_bytes);
     static constexpr int stages = (200 * 1024) / stage_bytes > 8 ? 8 : (200 * 1024) / stage_bytes;
     static constexpr int tmem_cols = 2 * BN;      // 256 or 512: powers of two
-    static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int stage_tile_bytes = 32 * kStageLd * 2;     // epilogue staging tile, per epilogue warp
+    static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * stage_tile_bytes;
 };
 
 template <int MODE, int KIND, int BN, bool WGRAD>
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint64_t* tfull = bars + 2 * C::stages;      // [2]
     uint64_t* tempty = bars + 2 * C::stages + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::stages + 4);
+    __nv_bfloat16* stage_tiles = reinterpret_cast<__nv_bfloat16*>(smem + C::stages * C::stage_bytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -306,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int q = (warp - 4) & 3;                // TMEM lane quarter of this warp (== warp % 4)
         const int half = (warp - 4) >> 2;            // which column half of the tile this warp drains
         constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+        const Stager stager{stage_tiles + (warp - 4) * (32 * kStageLd), lane};
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
             int mn = tile, tap = 0, split = 0;
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     if (has_acc) epi_wgrad<32>(P.epi, tap, row, n0, v);
                 } else {
                     if (n0 < P.epi.N || KIND == EPI_RS || KIND == EPI_START || KIND == EPI_IN)
-                        epi_apply<MODE, KIND, 32>(P.epi, row, n0, v);
+                        epi_apply<MODE, KIND, 32>(P.epi, stager, row, n0, v);
                 }
             }
             tc_fence_before();

@@ -90,9 +90,7 @@ static ActMat sub_mode(const ActMat& m, long long elem_off, size_t es) {
 struct Workspace {
     ActMat Z0;
     ActMat Hs[RADMMM_MAX_LAYERS + 1];
-    ActMat SIG[RADMMM_MAX_LAYERS];
-    float* OUT;
-    ActMat OUTa;
+    ActMat S[RADMMM_MAX_LAYERS];      // s_i = softplus(res_skip_i(h_{i+1})), kept per layer (the skip sum is implicit)
 };
 
 static size_t layout_workspace(const Dims& d, int training, void* base, Workspace* w) {
@@ -107,9 +105,7 @@ static size_t layout_workspace(const Dims& d, int training, void* base, Workspac
             q.Hs[i] = q.Hs[i & 1];
         }
     }
-    for (int i = 0; i < d.L; ++i) q.SIG[i] = training ? take_act(b, d, d.R, d.H) : null_act();
-    q.OUT = (float*)b.take(sizeof(float) * (size_t)d.R * d.H);
-    q.OUTa = take_act(b, d, d.R, d.H);
+    for (int i = 0; i < d.L; ++i) q.S[i] = take_act(b, d, d.R, d.H);
     if (w) *w = q;
     return (size_t)round_up((long long)b.off, 1024);
 }
@@ -201,7 +197,6 @@ static void add_seg(GemmArgs& a, const ActMat& act, const ActMat& w, int K, int 
 static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepared& p, const Workspace& w,
                            const float* z_mid, float* params, cudaStream_t st) {
     const RowGeom g = geom_of(d, f->lens);
-    const bool tr = f->training != 0;
     ActMat ctx; ctx.ptr = const_cast<void*>(f->ctx_rows); ctx.ld = d.Dp; ctx.plane_stride = (long long)d.R * d.Dp;
     // z0 = z_mid[:, :Ch] -> rows
     RADMMM_TRY(rows_from_cf(d.mode, z_mid, (long long)d.C * d.Tp, d.Ch, g, w.Z0, d.Kz, 1, st));
@@ -226,15 +221,12 @@ static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepa
         add_seg(a, w.Hs[i + 1], sub_mode(p.Wrs, (long long)i * p.HH, d.es), d.H, 0);
         a.epi.bias = f->rs_b[i];
         a.epi.padq = p.padq + (size_t)i * d.H;
-        a.epi.first = (i == 0);
-        a.epi.last = (i == d.L - 1);
-        a.epi.out0 = tr ? w.SIG[i] : null_act();
-        a.epi.f32_out = w.OUT; a.epi.f32_ld = d.H;
-        a.epi.out1 = w.OUTa;
+        a.epi.out0 = w.S[i];
         RADMMM_TRY(launch_gemm(a, d.mode, st));
     }
+    // end(sum_i s_i) = sum_i end(s_i): one GEMM whose K runs over the L stored s_i
     init_args(a, d, f->lens, EPI_END, d.C);
-    add_seg(a, w.OUTa, p.Wend, d.H, 0);
+    for (int i = 0; i < d.L; ++i) add_seg(a, w.S[i], p.Wend, d.H, 0);
     a.epi.bias = f->end_b;
     a.epi.cf_out = params; a.epi.cf_C = d.C; a.epi.cf_c0 = 0;
     RADMMM_TRY(launch_gemm(a, d.mode, st));
@@ -275,7 +267,8 @@ int flow_inverse(const radmmm_flow_desc* f, const float* z_in, float* params, fl
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat& X, int M, int N, int taps, int dil, float* out, long long ld, long long tap_stride, cudaStream_t st) {
+static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat& X, int M, int N, int taps, int dil, float* out, long long ld, long long tap_stride, cudaStream_t st,
+                 bool zero_out = true) {
     GemmArgs a;
     init_args(a, d, lens, EPI_WGRAD, N);
     a.wgrad = 1;
@@ -289,8 +282,9 @@ static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat&
     // every launcher picks its own split-K; partial tiles are reduced with fp32 atomics into a zeroed output
     a.split_k = 0;
     a.epi.atomic = 1;
-    for (int j = 0; j < taps; ++j)
-        RADMMM_CUDA(cudaMemset2DAsync(out + j * tap_stride, sizeof(float) * ld, 0, sizeof(float) * N, M, st));
+    if (zero_out)
+        for (int j = 0; j < taps; ++j)
+            RADMMM_CUDA(cudaMemset2DAsync(out + j * tap_stride, sizeof(float) * ld, 0, sizeof(float) * N, M, st));
     return launch_gemm(a, d.mode, st);
 }
 
@@ -314,10 +308,11 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
     RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, d.Cp, 1, st));
     // 2. end conv: bias, weight, input gradients
     RADMMM_TRY(colsum(d.mode, s.DP, g, d.C, 1, 0, gr->end_b, st));
-    RADMMM_TRY(wgrad(d, f->lens, s.DP, w.OUTa, d.C, H, 1, 1, gr->end_w, H, 0, st));
+    for (int i = 0; i < L; ++i)      // dW_end = dP^T (sum_i s_i): L accumulating launches
+        RADMMM_TRY(wgrad(d, f->lens, s.DP, w.S[i], d.C, H, 1, 1, gr->end_w, H, 0, st, i == 0));
     init_args(a, d, f->lens, EPI_DOUT, H);
     add_seg(a, s.DP, p.WendT, d.Cp, 0);
-    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.SIG[i]; a.epi.dq[i] = s.DQ[i]; }
+    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.S[i]; a.epi.dq[i] = s.DQ[i]; }
     RADMMM_TRY(launch_gemm(a, d.mode, st));
     // 3. layers, last to first
     for (int i = L - 1; i >= 0; --i) {
