@@ -63,7 +63,8 @@ struct GemmArgs {
     GemmSeg seg[kMaxSeg];
     int R;          // rows (multiple of 128)
     int n_tiles_n;  // informational
-    int wgrad;      // 0 row GEMM, 1 weight-grad GEMM (n_seg = number of taps, one output tile set per tap)
+    int wgrad;      // 0 row GEMM; 1 weight-grad GEMM, one output tile set per segment (= conv tap);
+                    // 2 weight-grad GEMM, all segments (same dY, different X) accumulate into ONE output
     int split_k;    // weight-grad only
     EpiParams epi;
 };

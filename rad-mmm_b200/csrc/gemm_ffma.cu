@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(NT) gemm_ffma_kernel(const GemmArgs args) {
     const int n0 = blockIdx.y * BN;
     int tap = 0, split = 0;
     if (WGRAD) { tap = blockIdx.z / args.split_k; split = blockIdx.z % args.split_k; }
+    const bool acc_segs = WGRAD && args.wgrad == 2;      // all segments accumulate into one output
 
     float acc[8][8];
 #pragma unroll
@@ -30,8 +31,8 @@ __global__ void __launch_bounds__(NT) gemm_ffma_kernel(const GemmArgs args) {
 
     float4 ra[2], rb[2];
 
-    const int seg_begin = WGRAD ? tap : 0;
-    const int seg_end = WGRAD ? tap + 1 : args.n_seg;
+    const int seg_begin = (WGRAD && !acc_segs) ? tap : 0;
+    const int seg_end = (WGRAD && !acc_segs) ? tap + 1 : args.n_seg;
     for (int s = seg_begin; s < seg_end; ++s) {
         const GemmSeg& sg = args.seg[s];
         const float* A = reinterpret_cast<const float*>(sg.a.ptr);
@@ -141,14 +142,14 @@ int launch_gemm_ffma(const GemmArgs& args, cudaStream_t stream) {
     if (args.wgrad) {
         GemmArgs a2 = args;
         if (a2.split_k < 1) {      // auto: aim for >= ~300 CTAs
-            const long long tiles = (long long)cdiv(args.epi.M, BM) * cdiv(args.epi.N, BN) * args.n_seg;
+            const long long tiles = (long long)cdiv(args.epi.M, BM) * cdiv(args.epi.N, BN) * (args.wgrad == 2 ? 1 : args.n_seg);
             int split = tiles < 256 ? (int)((296 + tiles - 1) / tiles) : 1;
             if (split > 16) split = 16;
             if (split > args.R / 128) split = args.R / 128;
             a2.split_k = split < 1 ? 1 : split;
         }
         RADMMM_REQUIRE(a2.split_k == 1 || a2.epi.atomic, "gemm_ffma: split-K needs the atomic epilogue");
-        dim3 grid(cdiv(args.epi.M, BM), cdiv(args.epi.N, BN), args.n_seg * a2.split_k);
+        dim3 grid(cdiv(args.epi.M, BM), cdiv(args.epi.N, BN), (args.wgrad == 2 ? 1 : args.n_seg) * a2.split_k);
         gemm_ffma_kernel<EPI_WGRAD, true><<<grid, NT, 0, stream>>>(a2);
         RADMMM_LAUNCH_CHECK();
         return RADMMM_OK;

@@ -40,6 +40,7 @@ struct TcParams {
     TcSeg seg[kMaxSeg];
     int n_seg, n_a_maps, n_b_maps;
     int m_tiles, n_tiles, taps, split_k, k_blocks_total;   // weight-grad: k_blocks_total = R/64
+    int acc_segs;                                          // weight-grad: all segments accumulate into one output
     EpiParams epi;
 };
 
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 int mn = tile, tap = 0, split = 0;
                 if (WGRAD) { mn = tile % tiles_mn; const int ts = tile / tiles_mn; tap = ts / P.split_k; split = ts % P.split_k; }
                 const int m_blk = mn / P.n_tiles, n_blk = mn % P.n_tiles;
-                const int seg_begin = WGRAD ? tap : 0, seg_end = WGRAD ? tap + 1 : P.n_seg;
+                const int seg_begin = (WGRAD && !P.acc_segs) ? tap : 0, seg_end = (WGRAD && !P.acc_segs) ? tap + 1 : P.n_seg;
                 for (int s = seg_begin; s < seg_end; ++s) {
                     const TcSeg sg = P.seg[s];
                     int kb0 = 0, kb1 = sg.k_blocks;
@@ -238,8 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             }
 #pragma unroll
                             for (int i = 0; i < BN / 64; ++i) {
-                                tma_load_2d(sb_hi + i * (BK * 128), &P.b_hi[0], &full[stage], n_blk * BN + i * 64, rb);
-                                if (C::planes == 2) tma_load_2d(sb_lo + i * (BK * 128), &P.b_lo[0], &full[stage], n_blk * BN + i * 64, rb);
+                                tma_load_2d(sb_hi + i * (BK * 128), &P.b_hi[sg.b_map], &full[stage], n_blk * BN + i * 64, rb);
+                                if (C::planes == 2) tma_load_2d(sb_lo + i * (BK * 128), &P.b_lo[sg.b_map], &full[stage], n_blk * BN + i * 64, rb);
                             }
                         }
                         if (++stage == C::stages) { stage = 0; phase ^= 1; }
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int split = (tile / tiles_mn) % P.split_k;
                 int kb0, kb1;
                 k_range(split, kb0, kb1);
-                total_kb = kb1 - kb0;
+                total_kb = (kb1 - kb0) * (P.acc_segs ? P.n_seg : 1);
             }
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
@@ -511,7 +512,8 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         RADMMM_REQUIRE(g0.a.ld % 64 == 0 && g0.w.ld % 64 == 0, "gemm_tc: weight-grad operands need ld %% 64 == 0");
         const int M = args.epi.M;
         P.m_tiles = cdiv(M, BM);
-        P.taps = args.n_seg;
+        P.acc_segs = args.wgrad == 2;
+        P.taps = P.acc_segs ? 1 : args.n_seg;
         P.k_blocks_total = args.R / BK;
         // split K (= rows) so that the persistent grid sees >= ~4 tiles per SM while every tile keeps >= 8 K blocks
         const int tiles0 = P.m_tiles * P.n_tiles * P.taps;
@@ -535,16 +537,20 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         const long long a_in = round_up(M, 64) < g0.a.ld ? round_up(M, 64) : g0.a.ld;
         const long long b_in = round_up(N, 64) < g0.w.ld ? round_up(N, 64) : g0.w.ld;
         RADMMM_TRY(make_map(&P.a_hi[0], g0.a.ptr, a_in, args.R, g0.a.ld, 64));
-        RADMMM_TRY(make_map(&P.b_hi[0], g0.w.ptr, b_in, args.R, g0.w.ld, 64));
-        if (x3) {
-            RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.a.ptr + g0.a.plane_stride, a_in, args.R, g0.a.ld, 64));
-            RADMMM_TRY(make_map(&P.b_lo[0], (const __nv_bfloat16*)g0.w.ptr + g0.w.plane_stride, b_in, args.R, g0.w.ld, 64));
-        }
+        if (x3) RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.a.ptr + g0.a.plane_stride, a_in, args.R, g0.a.ld, 64));
+        n_a = 1;
         for (int s = 0; s < args.n_seg; ++s) {
-            RADMMM_REQUIRE(args.seg[s].a.ptr == g0.a.ptr && args.seg[s].w.ptr == g0.w.ptr, "gemm_tc: weight-grad taps must share operands");
-            P.seg[s] = TcSeg{0, 0, 0, args.seg[s].shift, P.k_blocks_total};
+            const GemmSeg& g = args.seg[s];
+            RADMMM_REQUIRE(g.a.ptr == g0.a.ptr, "gemm_tc: weight-grad segments must share dY");
+            RADMMM_REQUIRE(P.acc_segs || g.w.ptr == g0.w.ptr, "gemm_tc: weight-grad taps must share X");
+            int bi = find_or_add(b_keys, n_b, g.w.ptr, g.w.ld, g.w.plane_stride);
+            RADMMM_REQUIRE(bi >= 0, "gemm_tc: too many distinct X operands");
+            P.seg[s] = TcSeg{0, bi, 0, g.shift, P.k_blocks_total};
         }
-        n_a = n_b = 1;
+        for (int i = 0; i < n_b; ++i) {
+            RADMMM_TRY(make_map(&P.b_hi[i], b_keys[i].ptr, b_in, args.R, b_keys[i].ld, 64));
+            if (x3) RADMMM_TRY(make_map(&P.b_lo[i], (const __nv_bfloat16*)b_keys[i].ptr + b_keys[i].plane, b_in, args.R, b_keys[i].ld, 64));
+        }
     }
     P.n_a_maps = n_a;
     P.n_b_maps = n_b;

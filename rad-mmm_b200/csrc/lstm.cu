@@ -8,9 +8,8 @@
 //   * per step each warp owns one hidden unit: lanes split the H-long dot products (4 gates x 8 sequences = 32 FMAs per
 //     3 shared loads), a halving butterfly leaves lane v with the sum for (gate v/8, sequence v%8), lanes 0-7 apply the
 //     gate non-linearities and keep c in a register;
-//   * the new h slice is published through a double-buffered exchange array in L2 whose 64-bit words carry
-//     {value, step tag}: consumers poll the data words themselves (ld.relaxed.gpu) until the tag matches, so one L2
-//     round trip replaces fence + atomic barrier + reload.
+//   * the new h slice goes to a double-buffered exchange array in L2 and a per-direction arrive/spin barrier
+//     (one atomic per CTA per step) publishes it to the other CTAs of that direction.
 // Both directions run concurrently; variable lengths follow the packed semantics (the reverse direction of sequence b
 // starts at frame len_b-1; frames beyond len_b stay zero).  All arithmetic fp32.
 // Latency-bound by construction: T' dependent steps of (17 KB exchange + barrier); no roofline applies.
@@ -34,27 +33,27 @@ struct LstmParams {
     float* cstate;            // [R][2H] cell state (saved for backward)
     const float* dout;        // backward: (B, Tp, 2H)
     float* dgates;            // backward: [R][8H] pre-activation gate gradients
-    unsigned long long* xchg; // tagged exchange buffers (zeroed before launch)
+    float* xchg;              // exchange buffers
+    unsigned int* counters;   // [2] per-direction barrier counters (zeroed before launch)
     int B, Bp, Tp, H, pitch, G;
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// 64-bit exchange word = {fp32 value, step tag}: one aligned 8-byte store is single-copy atomic, so a consumer that
-// sees the expected tag also sees the value -- no fence, no separate flag.
-__device__ __forceinline__ void xchg_put(unsigned long long* slot, float v, unsigned int tag) {
-    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
-    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(slot), "l"(w) : "memory");
-}
-__device__ __forceinline__ float xchg_get(const unsigned long long* slot, unsigned int tag) {
-    unsigned long long w;
-    long long spins = 0;
-    while (true) {
-        asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
-        if ((unsigned int)(w >> 32) == tag) break;
-        if (++spins > (1ll << 24)) { printf("radmmm lstm: exchange wait timed out\n"); __trap(); }
+__device__ __forceinline__ void dir_barrier(unsigned int* counter, unsigned int target) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1u);
+        long long spins = 0;
+        while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            if (++spins > (1ll << 26)) { printf("radmmm lstm: barrier timed out\n"); __trap(); }
+        }
     }
-    return __uint_as_float((unsigned int)(w & 0xffffffffull));
+    __syncthreads();
 }
 
 // halving butterfly: in: v[32] partial sums per lane; out: the full sum of element `lane` (returned)
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) c_state[i] = 0.0f;
     const int unit = u0 + w;
-    unsigned long long* xbuf = p.xchg + (size_t)dir * 2 * Bp * H;        // [2 parity][Bp][H]
+    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H;        // [2 parity][Bp][H]
 
     for (int s = 0; s < tmax; ++s) {
 #pragma unroll 1
@@ -160,13 +159,13 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
                     p.cstate[r * 2 * H + (size_t)dir * H + unit] = c;
                     p.out[((long long)bb * p.Tp + t) * 2 * H + (size_t)dir * H + unit] = h;
                 }
-                xchg_put(xbuf + ((size_t)(s & 1) * Bp + bb) * H + unit, h, (unsigned int)(s + 1));
+                xbuf[((size_t)(s & 1) * Bp + bb) * H + unit] = h;
             }
         }
         if (s + 1 == tmax) break;
-        __syncthreads();                                    // every warp is done reading hs for this step
-        const unsigned long long* src = xbuf + (size_t)(s & 1) * Bp * H;
-        for (int i = tid; i < Bp * H; i += NT) hs[i] = xchg_get(src + i, (unsigned int)(s + 1));
+        dir_barrier(p.counters + dir, (unsigned int)p.G * (s + 1));
+        const float4* src = reinterpret_cast<const float4*>(xbuf + (size_t)(s & 1) * Bp * H);
+        for (int i = tid; i < Bp * H / 4; i += NT) reinterpret_cast<float4*>(hs)[i] = __ldcg(src + i);
         __syncthreads();
     }
 }
@@ -191,7 +190,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dh_rec[i] = 0.0f; dc_next[i] = 0.0f; }
     const int unit = u0 + w;
-    unsigned long long* xbuf = p.xchg + (size_t)dir * 2 * Bp * H4;        // [2 parity][Bp][4H]
+    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H4;        // [2 parity][Bp][4H]
 
     for (int s = tmax - 1; s >= 0; --s) {
         // phase 1: gate gradients of this CTA's units
@@ -224,18 +223,18 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
                 } else {
                     dc_next[bt] = 0.0f;
                 }
-                unsigned long long* x = xbuf + ((size_t)(s & 1) * Bp + bb) * H4 + unit;
-                const unsigned int tag = (unsigned int)(tmax - s);
-                xchg_put(x, d_i, tag); xchg_put(x + H, d_f, tag); xchg_put(x + 2 * H, d_g, tag); xchg_put(x + 3 * H, d_o, tag);
+                float* x = xbuf + ((size_t)(s & 1) * Bp + bb) * H4 + unit;
+                x[0] = d_i; x[H] = d_f; x[2 * H] = d_g; x[3 * H] = d_o;
             }
         }
         if (s == 0) break;
+        dir_barrier(p.counters + dir, (unsigned int)p.G * (tmax - s));
         // phase 2: dh_rec[b][unit] = sum_rho Whh[rho][unit] * dG[b][rho]
 #pragma unroll 1
         for (int bt = 0; bt < n_tiles; ++bt) {
-            const unsigned long long* src = xbuf + ((size_t)(s & 1) * Bp + (size_t)bt * BT) * H4;
+            const float4* src = reinterpret_cast<const float4*>(xbuf + ((size_t)(s & 1) * Bp + (size_t)bt * BT) * H4);
             __syncthreads();
-            for (int i = tid; i < BT * H4; i += NT) dgs[i] = xchg_get(src + i, (unsigned int)(tmax - s));
+            for (int i = tid; i < BT * H4 / 4; i += NT) reinterpret_cast<float4*>(dgs)[i] = __ldcg(src + i);
             __syncthreads();
             float acc[8];
 #pragma unroll
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
 
 size_t lstm_workspace_bytes(int B, int H) {
     const int Bp = (int)round_up(B, BT);
-    return sizeof(unsigned long long) * 2 * 2 * (size_t)Bp * 4 * H;      // the larger (backward) tagged exchange buffers
+    return 256 + sizeof(float) * 2 * 2 * (size_t)Bp * 4 * H;      // counters + the larger (backward) exchange buffers
 }
 
 static int lstm_common(LstmParams& p, const int* lens, int B, int Tp, int H, void* workspace) {
@@ -263,7 +262,8 @@ static int lstm_common(LstmParams& p, const int* lens, int B, int Tp, int H, voi
     RADMMM_REQUIRE(B >= 1 && B <= 64, "lstm: batch %d must be in [1, 64] (chunk larger batches)", B);
     RADMMM_REQUIRE(workspace != nullptr, "lstm: workspace missing");
     p.lens = lens; p.B = B; p.Bp = (int)round_up(B, BT); p.Tp = Tp; p.H = H; p.pitch = Tp + 16; p.G = H / U;
-    p.xchg = reinterpret_cast<unsigned long long*>(workspace);
+    p.counters = reinterpret_cast<unsigned int*>(workspace);
+    p.xchg = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -280,7 +280,7 @@ int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, con
     const size_t smem = sizeof(float) * ((size_t)U * H * 4 + (size_t)p.Bp * H);
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d, B=%d)", smem, H, B);
     RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RADMMM_CUDA(cudaMemsetAsync(p.xchg, 0, sizeof(unsigned long long) * 2 * 2 * (size_t)p.Bp * H, st));
+    RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
     void* args[] = {&p};
     RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
     return RADMMM_OK;
@@ -296,7 +296,7 @@ int lstm_backward(const float* dout, const float* gates, const float* cstate, co
     const size_t smem = sizeof(float) * ((size_t)U * 4 * H + (size_t)BT * 4 * H);
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d)", smem, H);
     RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RADMMM_CUDA(cudaMemsetAsync(p.xchg, 0, sizeof(unsigned long long) * 2 * 2 * (size_t)p.Bp * 4 * H, st));
+    RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
     void* args[] = {&p};
     RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
     return RADMMM_OK;

@@ -308,8 +308,16 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
     RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, d.Cp, 1, st));
     // 2. end conv: bias, weight, input gradients
     RADMMM_TRY(colsum(d.mode, s.DP, g, d.C, 1, 0, gr->end_b, st));
-    for (int i = 0; i < L; ++i)      // dW_end = dP^T (sum_i s_i): L accumulating launches
-        RADMMM_TRY(wgrad(d, f->lens, s.DP, w.S[i], d.C, H, 1, 1, gr->end_w, H, 0, st, i == 0));
+    {   // dW_end = dP^T (sum_i s_i): one weight-grad GEMM accumulating over the L stored s_i
+        GemmArgs wa;
+        init_args(wa, d, f->lens, EPI_WGRAD, H);
+        wa.wgrad = 2;
+        for (int i = 0; i < L; ++i) { GemmSeg& sg = wa.seg[wa.n_seg++]; sg.a = s.DP; sg.w = w.S[i]; sg.K = d.R; sg.shift = 0; }
+        wa.epi.M = d.C; wa.epi.f32_out = gr->end_w; wa.epi.f32_ld = H; wa.epi.f32_tap_stride = 0;
+        wa.split_k = 0; wa.epi.atomic = 1;
+        RADMMM_CUDA(cudaMemsetAsync(gr->end_w, 0, sizeof(float) * (size_t)d.C * H, st));
+        RADMMM_TRY(launch_gemm(wa, d.mode, st));
+    }
     init_args(a, d, f->lens, EPI_DOUT, H);
     add_seg(a, s.DP, p.WendT, d.Cp, 0);
     for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.S[i]; a.epi.dq[i] = s.DQ[i]; }
