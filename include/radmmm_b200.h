@@ -11,7 +11,7 @@
  *
  * Tensor layouts at the boundary are the reference's: fp32, (batch, channel, time) contiguous, time fastest
  * ("channels-first", cf).  Internally the WN stack works on "rows": row r = b*pitch + t with pitch = Tp + gap
- * zero rows between utterances, R = round_up(B*pitch, 128) rows in total (radmmm_rows()).
+ * zero rows between utterances, R = round_up(B*pitch, 256) rows in total (radmmm_rows()).
  */
 #ifndef RADMMM_B200_H
 #define RADMMM_B200_H

@@ -140,7 +140,7 @@ def stream() -> int:
 
 
 def rows(batch: int, tp: int) -> int:
-    return (batch * (tp + ROW_GAP) + 127) // 128 * 128
+    return (batch * (tp + ROW_GAP) + 255) // 256 * 256
 
 
 def round_up(a: int, b: int) -> int:

@@ -101,7 +101,7 @@ const char* radmmm_last_error(void) { return last_error(); }
 size_t radmmm_sizeof_flow_desc(void) { return sizeof(radmmm_flow_desc); }
 size_t radmmm_sizeof_flow_grads(void) { return sizeof(radmmm_flow_grads); }
 int radmmm_pitch(int Tp) { return Tp + RADMMM_ROW_GAP; }
-int radmmm_rows(int B, int Tp) { return (int)round_up((long long)B * (Tp + RADMMM_ROW_GAP), 128); }
+int radmmm_rows(int B, int Tp) { return (int)round_up((long long)B * (Tp + RADMMM_ROW_GAP), 256); }
 
 size_t radmmm_flow_prepared_bytes(int mode, int C, int D, int H, int L) { return flow_prepared_bytes(mode, C, D, H, L); }
 size_t radmmm_flow_workspace_bytes(int mode, int training, int B, int Tp, int C, int D, int H, int L) {

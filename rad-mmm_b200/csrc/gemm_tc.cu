@@ -14,6 +14,11 @@
 // The weight-grad GEMM contracts over rows: dY [R][M] and X [R][N] are read as MN-major UMMA operands straight from the
 // row matrices (64-channel x 64-row boxes, 128B swizzle), so the tap shift is an outer (row) TMA coordinate and no
 // transposed copies exist; split-K partial tiles are reduced with fp32 atomics.
+// Cluster variant (CL = 4, a 2x2 group of tiles): the two CTAs that share a row tile each load half of the A box and
+// multicast it to both, the two CTAs that share a column tile do the same for B, so every operand byte crosses the
+// L2 -> SM fabric once per CTA pair instead of once per CTA (the k=5 conv at B=8, T=800 moves 400 MB per launch without
+// it and is L2-bandwidth bound at ~730 TFLOP/s).  Stage release is a multicast tcgen05.commit to the three CTAs that
+// write into this CTA's stage.
 // Roofline: tensor pipe (dense bf16, MEASURED_PEAKS.json); BF16X3 has one third of it.
 #include <cuda.h>
 #include "gemm.cuh"
@@ -77,6 +82,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -155,9 +178,16 @@ struct Cfg {
     static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * stage_tile_bytes;
 };
 
-template <int MODE, int KIND, int BN, bool WGRAD>
+template <int MODE, int KIND, int BN, bool WGRAD, int CL>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
     using C = Cfg<MODE, BN>;
+    static_assert(CL == 1 || CL == 4, "cluster size");
+    // 2x2 cluster geometry: rank = cm + 2*cn; cm selects the row tile of the pair, cn the column tile
+    const uint32_t crank = (CL == 4) ? cluster_rank() : 0u;
+    const int cm = crank & 1, cn = crank >> 1;
+    const uint16_t mask_a = (uint16_t)((1u << crank) | (1u << (crank ^ 2)));     // CTAs sharing my row tile (same cm)
+    const uint16_t mask_b = (uint16_t)((1u << crank) | (1u << (crank ^ 1)));     // CTAs sharing my column tile (same cn)
+    const uint16_t mask_rel = (uint16_t)(mask_a | mask_b);                        // CTAs that write into my stages
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
@@ -175,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         for (int i = 0; i < P.n_b_maps; ++i) { prefetch_tmap(&P.b_hi[i]); if (C::planes == 2) prefetch_tmap(&P.b_lo[i]); }
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < C::stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < C::stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL == 4 ? 3 : 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -185,11 +215,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 4) cluster_sync_all();          // peers' barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Tile walk.  CL == 1: CTA b takes tiles b, b + grid, ...  CL == 4: cluster c takes 2x2 super-tiles c, c + #clusters, ...
+    // and CTA (cm, cn) of the cluster works on tile (2*sm + cm, 2*sn + cn); `tile` below always is the CTA's own linear
+    // tile index in the (m_tiles x n_tiles [x taps x split]) space, `walk` the scheduler position.
     const int tiles_mn = P.m_tiles * P.n_tiles;
     const int n_tiles_total = WGRAD ? tiles_mn * P.taps * P.split_k : tiles_mn;
+    const int walk_begin = (CL == 4) ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
+    const int walk_step = (CL == 4) ? (int)(gridDim.x >> 2) : (int)gridDim.x;
+    const int walk_end = (CL == 4) ? n_tiles_total / 4 : n_tiles_total;
+    auto tile_of = [&](int walk) -> int {
+        if (CL == 1) return walk;
+        const int sn_tiles = P.n_tiles >> 1, smn = (P.m_tiles >> 1) * sn_tiles;
+        const int outer = walk / smn, inner = walk % smn;          // outer = (tap, split) for weight-grad
+        const int sm = inner / sn_tiles, sn = inner % sn_tiles;
+        return outer * tiles_mn + (2 * sm + cm) * P.n_tiles + (2 * sn + cn);
+    };
 
     // weight-grad split-K range (in 64-row K blocks)
     auto k_range = [&](int split, int& kb0, int& kb1) {
@@ -203,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+            for (int walk = walk_begin; walk < walk_end; walk += walk_step) {
+                const int tile = tile_of(walk);
                 int mn = tile, tap = 0, split = 0;
                 if (WGRAD) { mn = tile % tiles_mn; const int ts = tile / tiles_mn; tap = ts / P.split_k; split = ts % P.split_k; }
                 const int m_blk = mn / P.n_tiles, n_blk = mn % P.n_tiles;
@@ -220,7 +265,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         uint8_t* sb_hi = st + C::planes * C::a_bytes;
                         uint8_t* sa_lo = st + C::a_bytes;
                         uint8_t* sb_lo = st + 2 * C::a_bytes + C::b_bytes;
-                        if (!WGRAD) {
+                        if (!WGRAD && CL == 4) {
+                            // my half of each box (A: 64 of the 128 rows, B: BN/2 rows), multicast to the sharing pair
+                            const int a_c0 = kb * BK, a_c1 = m_blk * BM + cn * (BM / 2) + sg.a_row_shift;
+                            const int b_c0 = kb * BK, b_c1 = n_blk * BN + cm * (BN / 2) + sg.b_row_off;
+                            const int a_off = cn * (BM / 2) * 128, b_off = cm * (BN / 2) * 128;
+                            tma_load_2d_mc(sa_hi + a_off, &P.a_hi[sg.a_map], &full[stage], a_c0, a_c1, mask_a);
+                            tma_load_2d_mc(sb_hi + b_off, &P.b_hi[sg.b_map], &full[stage], b_c0, b_c1, mask_b);
+                            if (C::planes == 2) {
+                                tma_load_2d_mc(sa_lo + a_off, &P.a_lo[sg.a_map], &full[stage], a_c0, a_c1, mask_a);
+                                tma_load_2d_mc(sb_lo + b_off, &P.b_lo[sg.b_map], &full[stage], b_c0, b_c1, mask_b);
+                            }
+                        } else if (!WGRAD) {
                             const int a_c0 = kb * BK, a_c1 = m_blk * BM + sg.a_row_shift;
                             const int b_c0 = kb * BK, b_c1 = n_blk * BN + sg.b_row_off;
                             tma_load_2d(sa_hi, &P.a_hi[sg.a_map], &full[stage], a_c0, a_c1);
@@ -228,6 +284,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             if (C::planes == 2) {
                                 tma_load_2d(sa_lo, &P.a_lo[sg.a_map], &full[stage], a_c0, a_c1);
                                 tma_load_2d(sb_lo, &P.b_lo[sg.b_map], &full[stage], b_c0, b_c1);
+                            }
+                        } else if (CL == 4) {
+                            // weight-grad: 64-channel x 64-row boxes; I load box cn of A and boxes [cm*BN/128, ...) of B
+                            const int ra = kb * BK, rb = kb * BK + sg.b_row_off;
+                            tma_load_2d_mc(sa_hi + cn * (BK * 128), &P.a_hi[0], &full[stage], m_blk * BM + cn * 64, ra, mask_a);
+                            if (C::planes == 2) tma_load_2d_mc(sa_lo + cn * (BK * 128), &P.a_lo[0], &full[stage], m_blk * BM + cn * 64, ra, mask_a);
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j) {
+                                const int i = cm * (BN / 128) + j;
+                                tma_load_2d_mc(sb_hi + i * (BK * 128), &P.b_hi[sg.b_map], &full[stage], n_blk * BN + i * 64, rb, mask_b);
+                                if (C::planes == 2) tma_load_2d_mc(sb_lo + i * (BK * 128), &P.b_lo[sg.b_map], &full[stage], n_blk * BN + i * 64, rb, mask_b);
                             }
                         } else {
                             // 64-channel x 64-row boxes; inner coordinate = channel, outer = row (tap shift on X)
@@ -254,7 +321,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+        for (int walk = walk_begin; walk < walk_end; walk += walk_step, ++it) {
+            const int tile = tile_of(walk);
             int total_kb = 0;
             if (!WGRAD) {
                 for (int s = 0; s < P.n_seg; ++s) total_kb += P.seg[s].k_blocks;
@@ -295,7 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
                         }
                     }
-                    tc_commit(&empty[stage]);                       // smem slot reusable once these MMAs retire
+                    if (CL == 4) tc_commit_mc(&empty[stage], mask_rel);   // release the slot to every CTA that writes into it
+                    else tc_commit(&empty[stage]);                  // smem slot reusable once these MMAs retire
                     if (kb == total_kb - 1) tc_commit(&tfull[as]);  // accumulator complete
                 }
                 __syncwarp();
@@ -311,7 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
         const Stager stager{stage_tiles + (warp - 4) * (32 * kStageLd), lane};
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+        for (int walk = walk_begin; walk < walk_end; walk += walk_step, ++it) {
+            const int tile = tile_of(walk);
             int mn = tile, tap = 0, split = 0;
             if (WGRAD) { mn = tile % tiles_mn; const int ts = tile / tiles_mn; tap = ts / P.split_k; split = ts % P.split_k; }
             const int m_blk = mn / P.n_tiles, n_blk = mn % P.n_tiles;
@@ -341,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if (CL == 4) cluster_sync_all();          // no CTA may exit while a peer can still arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::tmem_cols) : "memory");
@@ -392,36 +463,62 @@ static int sm_count() {
     return n;
 }
 
-template <int MODE, int KIND, int BN, bool WGRAD>
+template <int MODE, int KIND, int BN, bool WGRAD, int CL>
 static int launch_inst(const TcParams& P, int n_tiles_total, cudaStream_t st) {
     using C = Cfg<MODE, BN>;
-    auto kern = gemm_tc_kernel<MODE, KIND, BN, WGRAD>;
+    auto kern = gemm_tc_kernel<MODE, KIND, BN, WGRAD, CL>;
     static bool configured = false;
+    static int max_clusters = 0;
     if (!configured) {
         RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+        if (CL > 1) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(CL * 32); q.blockDim = dim3(kThreads); q.dynamicSmemBytes = C::smem_bytes;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q) != cudaSuccess || max_clusters < 1) {
+                cudaGetLastError();
+                max_clusters = sm_count() / CL / 2;
+            }
+        }
         configured = true;
     }
-    int grid = n_tiles_total < sm_count() ? n_tiles_total : sm_count();
-    if (grid < 1) grid = 1;
-    kern<<<grid, kThreads, C::smem_bytes, st>>>(P);
-    RADMMM_LAUNCH_CHECK();
+    if (CL == 1) {
+        int grid = n_tiles_total < sm_count() ? n_tiles_total : sm_count();
+        if (grid < 1) grid = 1;
+        kern<<<grid, kThreads, C::smem_bytes, st>>>(P);
+        RADMMM_LAUNCH_CHECK();
+        return RADMMM_OK;
+    }
+    int clusters = n_tiles_total / CL;
+    if (clusters > max_clusters) clusters = max_clusters;
+    if (clusters < 1) clusters = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    RADMMM_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     return RADMMM_OK;
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, int CL>
 static int launch_kind(const TcParams& P, int n_tiles_total, bool wgrad, cudaStream_t st) {
-    if (wgrad) return launch_inst<MODE, EPI_WGRAD, BN, true>(P, n_tiles_total, st);
+    if (wgrad) return launch_inst<MODE, EPI_WGRAD, BN, true, CL>(P, n_tiles_total, st);
     switch (P.epi.kind) {
-        case EPI_START: return launch_inst<MODE, EPI_START, BN, false>(P, n_tiles_total, st);
-        case EPI_IN: return launch_inst<MODE, EPI_IN, BN, false>(P, n_tiles_total, st);
-        case EPI_RS: return launch_inst<MODE, EPI_RS, BN, false>(P, n_tiles_total, st);
-        case EPI_END: return launch_inst<MODE, EPI_END, BN, false>(P, n_tiles_total, st);
-        case EPI_DOUT: return launch_inst<MODE, EPI_DOUT, BN, false>(P, n_tiles_total, st);
-        case EPI_DH: return launch_inst<MODE, EPI_DH, BN, false>(P, n_tiles_total, st);
-        case EPI_DH0: return launch_inst<MODE, EPI_DH0, BN, false>(P, n_tiles_total, st);
-        case EPI_DZ0: return launch_inst<MODE, EPI_DZ0, BN, false>(P, n_tiles_total, st);
-        case EPI_DCTX: return launch_inst<MODE, EPI_DCTX, BN, false>(P, n_tiles_total, st);
-        case EPI_F32: return launch_inst<MODE, EPI_F32, BN, false>(P, n_tiles_total, st);
+        case EPI_START: return launch_inst<MODE, EPI_START, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_IN: return launch_inst<MODE, EPI_IN, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_RS: return launch_inst<MODE, EPI_RS, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_END: return launch_inst<MODE, EPI_END, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_DOUT: return launch_inst<MODE, EPI_DOUT, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_DH: return launch_inst<MODE, EPI_DH, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_DH0: return launch_inst<MODE, EPI_DH0, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_DZ0: return launch_inst<MODE, EPI_DZ0, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_DCTX: return launch_inst<MODE, EPI_DCTX, BN, false, CL>(P, n_tiles_total, st);
+        case EPI_F32: return launch_inst<MODE, EPI_F32, BN, false, CL>(P, n_tiles_total, st);
     }
     set_error("gemm_tc: unknown epilogue kind %d", P.epi.kind);
     return RADMMM_ERR_ARG;
@@ -458,9 +555,12 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         return n++;
     };
 
+    bool use_cl = false;
     if (!args.wgrad) {
         P.m_tiles = args.R / BM;
         n_tiles_total = P.m_tiles * P.n_tiles;
+        use_cl = (P.m_tiles % 2 == 0) && (P.n_tiles % 2 == 0);
+        const int a_box = use_cl ? BM / 2 : BM, b_box = use_cl ? BN / 2 : BN;
         // B maps: segments whose weight matrices sit in one allocation (same ld / plane stride, row-aligned offsets)
         // share a map anchored at the lowest pointer; the segment carries its row offset.
         for (int s = 0; s < args.n_seg; ++s) {
@@ -490,8 +590,8 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         for (int i = 0; i < n_a; ++i) {
             long long kmax = 0;
             for (int s = 0; s < args.n_seg; ++s) if (P.seg[s].a_map == i) kmax = kmax > args.seg[s].K ? kmax : args.seg[s].K;
-            RADMMM_TRY(make_map(&P.a_hi[i], a_keys[i].ptr, kmax, args.R, a_keys[i].ld, BM));
-            if (x3) RADMMM_TRY(make_map(&P.a_lo[i], (const __nv_bfloat16*)a_keys[i].ptr + a_keys[i].plane, kmax, args.R, a_keys[i].ld, BM));
+            RADMMM_TRY(make_map(&P.a_hi[i], a_keys[i].ptr, kmax, args.R, a_keys[i].ld, a_box));
+            if (x3) RADMMM_TRY(make_map(&P.a_lo[i], (const __nv_bfloat16*)a_keys[i].ptr + a_keys[i].plane, kmax, args.R, a_keys[i].ld, a_box));
         }
         for (int i = 0; i < n_b; ++i) {
             long long kmax = 0, rows = 0;
@@ -501,8 +601,8 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
                     const long long need = (long long)P.seg[s].b_row_off + n_pad;
                     rows = rows > need ? rows : need;
                 }
-            RADMMM_TRY(make_map(&P.b_hi[i], b_keys[i].ptr, kmax, rows, b_keys[i].ld, BN));
-            if (x3) RADMMM_TRY(make_map(&P.b_lo[i], (const __nv_bfloat16*)b_keys[i].ptr + b_keys[i].plane, kmax, rows, b_keys[i].ld, BN));
+            RADMMM_TRY(make_map(&P.b_hi[i], b_keys[i].ptr, kmax, rows, b_keys[i].ld, b_box));
+            if (x3) RADMMM_TRY(make_map(&P.b_lo[i], (const __nv_bfloat16*)b_keys[i].ptr + b_keys[i].plane, kmax, rows, b_keys[i].ld, b_box));
         }
     } else {
         // weight-grad: A = dY [R][M], B = X [R][N] as MN-major operands; one output tile set per tap, K = rows split
@@ -531,6 +631,7 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         }
         P.split_k = split;
         n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
+        use_cl = (P.m_tiles % 2 == 0) && (P.n_tiles % 2 == 0);
         RADMMM_REQUIRE(split == 1 || args.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
         // inner extents stop at the logical widths (rounded to the 64-channel box) so that operands which are column
         // slices of wider matrices never read past their rows
@@ -555,9 +656,15 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     P.n_a_maps = n_a;
     P.n_b_maps = n_b;
 
-    if (x3) return launch_kind<MODE_BF16X3, 128>(P, n_tiles_total, args.wgrad != 0, stream);
-    if (BN == 256) return launch_kind<MODE_BF16, 256>(P, n_tiles_total, args.wgrad != 0, stream);
-    return launch_kind<MODE_BF16, 128>(P, n_tiles_total, args.wgrad != 0, stream);
+    const bool wg = args.wgrad != 0;
+    if (use_cl) {
+        if (x3) return launch_kind<MODE_BF16X3, 128, 4>(P, n_tiles_total, wg, stream);
+        if (BN == 256) return launch_kind<MODE_BF16, 256, 4>(P, n_tiles_total, wg, stream);
+        return launch_kind<MODE_BF16, 128, 4>(P, n_tiles_total, wg, stream);
+    }
+    if (x3) return launch_kind<MODE_BF16X3, 128, 1>(P, n_tiles_total, wg, stream);
+    if (BN == 256) return launch_kind<MODE_BF16, 256, 1>(P, n_tiles_total, wg, stream);
+    return launch_kind<MODE_BF16, 128, 1>(P, n_tiles_total, wg, stream);
 }
 
 }  // namespace radmmm

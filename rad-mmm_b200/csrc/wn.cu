@@ -16,7 +16,7 @@ static Dims make_dims(int mode, int B, int C, int Tp, int D, int H, int L) {
     Dims d;
     d.mode = mode; d.B = B; d.C = C; d.Ch = C / 2; d.Tp = Tp; d.D = D; d.H = H; d.L = L;
     d.pitch = Tp + RADMMM_ROW_GAP;
-    d.R = (int)round_up((long long)B * d.pitch, 128);
+    d.R = (int)round_up((long long)B * d.pitch, 256);      // even number of 128-row tiles: 2x2 cluster tiling
     // every padded channel count is a multiple of 128 so that TMA boxes (128 rows) never exceed a tensor extent
     d.Kz = (int)round_up(d.Ch, 128);
     d.KzR = d.Kz;

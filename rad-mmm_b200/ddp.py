@@ -33,6 +33,8 @@ class BucketedGradReducer:
         loss.backward(); reducer.finish()           # .grad of every parameter now holds the cross-rank mean
     """
 
+    ALIGN = 64      # elements
+
     def __init__(self, module: torch.nn.Module, bucket_key: Callable[[str], str] = default_bucket_key,
                  process_group=None, average: bool = True):
         self.group = process_group
@@ -47,14 +49,15 @@ class BucketedGradReducer:
             b["params"].append(p)
             b["names"].append(name)
         for key, b in self.buckets.items():
-            n = sum(p.numel() for p in b["params"])
+            # every slot starts on a 256-byte boundary: the kernels write gradients with 16-byte vector stores / atomics
+            b["offsets"] = []
+            n = 0
+            for p in b["params"]:
+                b["offsets"].append(n)
+                n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
             p0 = b["params"][0]
             b["flat"] = torch.zeros(n, dtype=p0.dtype, device=p0.device)
-            b["views"] = []
-            off = 0
-            for p in b["params"]:
-                b["views"].append(b["flat"][off:off + p.numel()].view_as(p))
-                off += p.numel()
+            b["views"] = [b["flat"][off:off + p.numel()].view_as(p) for p, off in zip(b["params"], b["offsets"])]
             b["pending"] = len(b["params"])
             for p, v in zip(b["params"], b["views"]):
                 p.register_post_accumulate_grad_hook(self._make_hook(key, v))
@@ -87,11 +90,9 @@ class BucketedGradReducer:
         self._slot_of = {}
         for b in self.buckets.values():
             b["pending"] = len(b["params"])
-            off = 0
-            for p, v in zip(b["params"], b["views"]):
+            for p, v, off in zip(b["params"], b["views"], b["offsets"]):
                 self._view_of[id(p)] = v
                 self._slot_of[p.data_ptr()] = (b["flat"], off, tuple(p.shape))
-                off += p.numel()
         self._handles = []
 
     def _make_hook(self, key: str, view: torch.Tensor):

@@ -18,13 +18,14 @@ MODE_TOL = {"fp32": 2e-5, "bf16x3": 2e-4, "bf16": 3e-2}
 
 # ------------------------------------------------------------------------------------------------ contractions
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
-@pytest.mark.parametrize("taps,dil,K,Nout", [(1, 1, 128, 256), (5, 1, 128, 256), (5, 8, 256, 128), (1, 1, 192, 160),
-                                              (5, 4, 64, 1024)])
-def test_conv_rows(precision, taps, dil, K, Nout):
+@pytest.mark.parametrize("taps,dil,K,Nout,R", [(1, 1, 128, 256, 384), (5, 1, 128, 256, 384), (5, 8, 256, 128, 384),
+                                                (1, 1, 192, 160, 384), (5, 4, 64, 1024, 384),
+                                                # even tile counts -> 2x2 cluster multicast variant
+                                                (5, 2, 256, 1024, 512), (1, 1, 1024, 512, 1024), (5, 8, 128, 256, 256)])
+def test_conv_rows(precision, taps, dil, K, Nout, R):
     """Row GEMM (the WN conv): y[r] = sum_j W_j x[r + (j-c)d] + bias, zero outside [0,R)."""
     lib = N.lib()
     mode = N.MODES[precision]
-    R = 384
     npad = N.round_up(Nout, 128)
     x = syn.hash_uniform(f"cr.x{K}", (R, K)).to(DEV)
     w = torch.zeros(taps, npad, K)

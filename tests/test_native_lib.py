@@ -44,7 +44,7 @@ def test_struct_layouts(lib):
 def test_size_queries(lib):
     assert lib.radmmm_pitch(400) == 416
     assert lib.radmmm_rows(8, 400) == 3328
-    assert lib.radmmm_rows(1, 1) == 128
+    assert lib.radmmm_rows(1, 1) == 256
     for mode in (0, 1, 2):
         p = lib.radmmm_flow_prepared_bytes(mode, 160, 1056, 1024, 4)
         w_train = lib.radmmm_flow_workspace_bytes(mode, 1, 8, 400, 160, 1056, 1024, 4)

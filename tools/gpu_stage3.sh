@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+PT="python -m pytest -q -p no:cacheprovider --timeout=300 -m gpu"
+run() { name=$1; shift; echo "=== $name"; timeout 900 "$@" > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -n 8 gpurun_out/$name.log; }
+run gemm      $PT tests/test_gpu_ops.py -k "conv_rows or wgrad_rows"
+run dec       $PT tests/test_gpu_decoder.py -k "not context_lstm and not small"
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench3_bf16.json 2> gpurun_out/bench3_bf16.err; echo "bf16 exit $?"; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench3_bf16.json'))
+print(d['ms_per_step'], d['value'], d['roofline']['per_launch_ms'], d['roofline']['executed_tflops'], d['contraction_ms_one_step'])
+for k,v in d['contraction_kernels_one_step'].items(): print(k, v)
+PY
+tail -3 gpurun_out/bench3_bf16.err
+python bench.py --steps 5 --warmup 3 --precision bf16x3 --no-cpu-baseline > gpurun_out/bench3_bf16x3.json 2> gpurun_out/bench3_bf16x3.err; echo "x3 exit $?"
