@@ -176,6 +176,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the single JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = False          # keep the (cuDNN) context LSTM in fp32 like the reference default
     precision = args.precision

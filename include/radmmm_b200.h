@@ -191,6 +191,14 @@ int radmmm_soft_attention(const float* q, const float* k, const float* prior, co
                           float* attn_logprob, const float* txt_enc, float* context, int B, int Ca, int T1, int T2,
                           int Dt, float temperature, void* stream);
 
+/* Backward of radmmm_soft_attention: gradients w.r.t. the projected queries / keys (dq (B,Ca,T1), dk (B,Ca,T2)) and, when
+ * the context matmul was fused (txt_enc/dcontext != NULL), w.r.t. txt_enc (dtxt (B,Dt,T2)).  dattn / dlogprob are the
+ * incoming gradients of attn / attn_logprob (either may be NULL). */
+int radmmm_soft_attention_backward(const float* q, const float* k, const float* prior, const int32_t* in_lens,
+                                   const float* attn, const float* dattn, const float* dlogprob, const float* txt_enc,
+                                   const float* dcontext, float* dq, float* dk, float* dtxt, int B, int Ca, int T1, int T2,
+                                   int Dt, float temperature, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

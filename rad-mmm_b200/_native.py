@@ -87,6 +87,7 @@ SIGNATURES = {
     "radmmm_spline_backward": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _fp]),
     "radmmm_stft_mel": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
     "radmmm_soft_attention": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
+    "radmmm_soft_attention_backward": (_i, [_fp] * 12 + [_i, _i, _i, _i, _i, _f, _fp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -558,3 +558,98 @@ class Invertible1x1Conv(nn.Module):
                 self.W_inverse = None
             return _Inv1x1Function.apply(z, w_inv, None, None, ln)
         return _Inv1x1Function.apply(z, W, None, None, ln), torch.logdet(W).clone()
+
+
+# --------------------------------------------------------------------------------------------- soft attention
+class _SoftAttentionFunction(torch.autograd.Function):
+    """(q (B,Ca,T1), k (B,Ca,T2), prior (B,T1,T2) | None, in_lens, txt_enc (B,Dt,T2) | None) ->
+    (attn (B,1,T1,T2), attn_logprob (B,1,T1,T2), context (B,Dt,T1) | empty).  common.py:1259-1276 +
+    tts_lightning_modules.py:670 in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, q, k, prior, in_lens, txt_enc, temperature: float):
+        lib = N.lib()
+        q, k = q.contiguous().float(), k.contiguous().float()
+        b, ca, t1 = q.shape
+        t2 = k.shape[2]
+        prior_c = prior.contiguous().float() if prior is not None else None
+        txt_c = txt_enc.contiguous().float() if txt_enc is not None else None
+        dt = txt_c.shape[1] if txt_c is not None else 0
+        attn = torch.empty(b, 1, t1, t2, device=q.device)
+        logp = torch.empty(b, 1, t1, t2, device=q.device)
+        context = torch.empty(b, dt, t1, device=q.device) if txt_c is not None else q.new_empty(0)
+        N.check(lib.radmmm_soft_attention(N.fptr(q), N.fptr(k), N.fptr(prior_c), N.ptr(in_lens), N.fptr(attn), N.fptr(logp),
+                                          N.fptr(txt_c), N.fptr(context) if txt_c is not None else None, b, ca, t1, t2, dt,
+                                          temperature, N.stream()))
+        ctx.save_for_backward(q, k, prior_c if prior_c is not None else q.new_empty(0), in_lens, attn,
+                              txt_c if txt_c is not None else q.new_empty(0))
+        ctx.has_prior, ctx.has_txt, ctx.temperature = prior_c is not None, txt_c is not None, temperature
+        return attn, logp, context
+
+    @staticmethod
+    def backward(ctx, dattn, dlogp, dcontext):
+        lib = N.lib()
+        q, k, prior, in_lens, attn, txt = ctx.saved_tensors
+        b, ca, t1 = q.shape
+        t2 = k.shape[2]
+        dt = txt.shape[1] if ctx.has_txt else 0
+        dattn = dattn.contiguous() if dattn is not None else None
+        dlogp = dlogp.contiguous() if dlogp is not None else None
+        dctx = dcontext.contiguous() if (ctx.has_txt and dcontext is not None) else None
+        use_txt = ctx.has_txt and dctx is not None
+        dq, dk = torch.empty_like(q), torch.empty_like(k)
+        dtxt = torch.empty_like(txt) if use_txt else None
+        N.check(lib.radmmm_soft_attention_backward(
+            N.fptr(q), N.fptr(k), N.fptr(prior) if ctx.has_prior else None, N.ptr(in_lens), N.fptr(attn), N.fptr(dattn),
+            N.fptr(dlogp), N.fptr(txt) if use_txt else None, N.fptr(dctx), N.fptr(dq), N.fptr(dk), N.fptr(dtxt), b, ca, t1, t2,
+            dt, ctx.temperature, N.stream()))
+        return dq, dk, None, None, dtxt, None
+
+
+class _PlainConvNorm(nn.Module):
+    """ConvNorm without partial padding (common.py:152-191): weight-normed Conv1d with 'same' padding.  The attention's
+    projections are three tiny convolutions per side; they stay library (cuDNN) calls."""
+
+    def __init__(self, cin, cout, kernel_size, w_init_gain="linear"):
+        super().__init__()
+        conv = nn.Conv1d(cin, cout, kernel_size, padding=(kernel_size - 1) // 2)
+        nn.init.xavier_uniform_(conv.weight, gain=nn.init.calculate_gain(w_init_gain))
+        self.conv = nn.utils.weight_norm(conv)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class ConvAttention(nn.Module):
+    """common.py:1188-1277: Gaussian-distance soft attention between mel frames (queries) and text tokens (keys)."""
+
+    def __init__(self, n_mel_channels=80, n_text_channels=512, n_att_channels=80, temperature=1.0):
+        super().__init__()
+        self.temperature = temperature
+        self.key_proj = nn.Sequential(_PlainConvNorm(n_text_channels, n_text_channels * 2, 3, "relu"), nn.ReLU(),
+                                      _PlainConvNorm(n_text_channels * 2, n_att_channels, 1))
+        self.query_proj = nn.Sequential(_PlainConvNorm(n_mel_channels, n_mel_channels * 2, 3, "relu"), nn.ReLU(),
+                                        _PlainConvNorm(n_mel_channels * 2, n_mel_channels, 1), nn.ReLU(),
+                                        _PlainConvNorm(n_mel_channels, n_att_channels, 1))
+
+    def _lens(self, keys, mask, key_lens):
+        if key_lens is not None:
+            return key_lens.to(device=keys.device, dtype=torch.int32).contiguous()
+        if mask is not None:       # mask: (B, T2, 1), True on padded tokens (tts_lightning_modules.py:451)
+            return (~mask.reshape(mask.shape[0], -1).bool()).sum(1).to(torch.int32)
+        return torch.full((keys.shape[0],), keys.shape[2], dtype=torch.int32, device=keys.device)
+
+    def forward(self, queries, keys, query_lens, mask=None, key_lens=None, attn_prior=None):
+        """Same arguments and outputs as the reference: (attn (B,1,T1,T2), attn_logprob (B,1,T1,T2))."""
+        keys_enc = self.key_proj(keys)
+        queries_enc = self.query_proj(queries)
+        attn, logp, _ = _SoftAttentionFunction.apply(queries_enc, keys_enc, attn_prior, self._lens(keys, mask, key_lens),
+                                                     None, 0.0005)
+        return attn, logp
+
+    def forward_with_context(self, queries, keys, txt_enc, mask=None, key_lens=None, attn_prior=None):
+        """Fused variant: also returns context = bmm(txt_enc, attn^T) (tts_lightning_modules.py:670) from the same kernel."""
+        keys_enc = self.key_proj(keys)
+        queries_enc = self.query_proj(queries)
+        return _SoftAttentionFunction.apply(queries_enc, keys_enc, attn_prior, self._lens(keys, mask, key_lens), txt_enc,
+                                            0.0005)

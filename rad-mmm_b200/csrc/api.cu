@@ -251,4 +251,12 @@ int radmmm_soft_attention(const float* q, const float* k, const float* prior, co
                           ST(stream));
 }
 
+int radmmm_soft_attention_backward(const float* q, const float* k, const float* prior, const int32_t* in_lens,
+                                   const float* attn, const float* dattn, const float* dlogprob, const float* txt_enc,
+                                   const float* dcontext, float* dq, float* dk, float* dtxt, int B, int Ca, int T1, int T2,
+                                   int Dt, float temperature, void* stream) {
+    return soft_attention_bwd(q, k, prior, in_lens, attn, dattn, dlogprob, txt_enc, dcontext, dq, dk, dtxt, B, Ca, T1, T2,
+                              Dt, temperature, ST(stream));
+}
+
 }  // extern "C"

@@ -101,7 +101,132 @@ __global__ void __launch_bounds__(ROWS * 32) soft_attention_kernel(
     }
 }
 
+// Backward of soft_attention_kernel.  One warp per query frame recomputes its logits from q/k (nothing but attn and the
+// optional prior-normalised log-probabilities' inputs are needed), forms d logit from d attn (+ the context matmul's
+// contribution txt_enc^T d context) and d attn_logprob, and accumulates dq (own frame, plain store) and dk (shared
+// across query frames: shared-memory accumulation per CTA, then one atomic per element).
+__global__ void __launch_bounds__(ROWS * 32) soft_attention_bwd_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ prior,
+    const int* __restrict__ in_lens, const float* __restrict__ attn, const float* __restrict__ dattn,
+    const float* __restrict__ dlogprob, const float* __restrict__ txt_enc, const float* __restrict__ dcontext,
+    float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dtxt, int Ca, int T1, int T2, int Dt, float temp) {
+    extern __shared__ float sm[];
+    float* ks = sm;                          // [Ca][T2]
+    float* dks = ks + (size_t)Ca * T2;       // [Ca][T2] accumulated over this CTA's query frames
+    float* qs = dks + (size_t)Ca * T2;       // [ROWS][Ca]
+    float* gs = qs + ROWS * Ca;              // [ROWS][T2]  d dist (per frame)
+    float* as = gs + ROWS * T2;              // [ROWS][T2]  attn rows (for dtxt)
+    const int b = blockIdx.y, t1_0 = blockIdx.x * ROWS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* kb = k + (long long)b * Ca * T2;
+    for (int i = tid; i < Ca * T2; i += ROWS * 32) { ks[i] = kb[i]; dks[i] = 0.0f; }
+    for (int i = tid; i < ROWS * Ca; i += ROWS * 32) {
+        const int r = i / Ca, c = i % Ca, t1 = t1_0 + r;
+        qs[i] = (t1 < T1) ? q[((long long)b * Ca + c) * T1 + t1] : 0.0f;
+    }
+    __syncthreads();
+    const int t1 = t1_0 + wid;
+    const int len = min(in_lens[b], T2);
+    float* grow = gs + (size_t)wid * T2;
+    float* arow = as + (size_t)wid * T2;
+    if (t1 < T1) {
+        const long long orow = ((long long)b * T1 + t1) * T2;
+        // d attn including the context matmul: dA[t2] = dattn[t2] + sum_d txt[d,t2] dctx[d,t1]
+        float dot = 0.0f;
+        for (int t2 = lane; t2 < T2; t2 += 32) {
+            float da = dattn ? dattn[orow + t2] : 0.0f;
+            if (txt_enc != nullptr && t2 < len) {
+                float acc = 0.0f;
+                for (int d = 0; d < Dt; ++d) acc = fmaf(txt_enc[((long long)b * Dt + d) * T2 + t2], dcontext[((long long)b * Dt + d) * T1 + t1], acc);
+                da += acc;
+            }
+            const float a = attn[orow + t2];
+            arow[t2] = a;
+            grow[t2] = da;
+            dot += (t2 < len) ? a * da : 0.0f;
+        }
+        dot = warp_sum(dot);
+        // g_lp = dlogprob + softmax backward (masked keys get no softmax gradient)
+        float gsum = 0.0f;
+        for (int t2 = lane; t2 < T2; t2 += 32) {
+            float g = (t2 < len) ? arow[t2] * (grow[t2] - dot) : 0.0f;
+            if (dlogprob) g += dlogprob[orow + t2];
+            grow[t2] = g;
+            gsum += g;
+        }
+        if (prior != nullptr) {
+            // log_softmax backward over ALL keys: g_logit = g_lp - softmax(logit) * sum(g_lp)
+            gsum = warp_sum(gsum);
+            float mx = -INFINITY;
+            for (int t2 = lane; t2 < T2; t2 += 32) {
+                float d = 0.0f;
+                for (int c = 0; c < Ca; ++c) { const float df = qs[wid * Ca + c] - ks[c * T2 + t2]; d = fmaf(df, df, d); }
+                const float lg = -temp * d;
+                arow[t2] = lg;                       // reuse as logits (attn no longer needed for this frame's dq/dk)
+                mx = fmaxf(mx, lg);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float se = 0.0f;
+            for (int t2 = lane; t2 < T2; t2 += 32) se += expf(arow[t2] - mx);
+            se = warp_sum(se);
+            for (int t2 = lane; t2 < T2; t2 += 32) grow[t2] -= expf(arow[t2] - mx) / se * gsum;
+            for (int t2 = lane; t2 < T2; t2 += 32) arow[t2] = attn[orow + t2];     // restore for dtxt
+        }
+        for (int t2 = lane; t2 < T2; t2 += 32) grow[t2] *= -temp;                   // d dist
+        __syncwarp();
+        // dq[c] = sum_t2 2 (q - k) ddist ; dk[c,t2] -= 2 (q - k) ddist
+        for (int c = 0; c < Ca; ++c) {
+            const float qc = qs[wid * Ca + c];
+            float acc = 0.0f;
+            for (int t2 = lane; t2 < T2; t2 += 32) {
+                const float v = 2.0f * (qc - ks[c * T2 + t2]) * grow[t2];
+                acc += v;
+                atomicAdd(&dks[c * T2 + t2], -v);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) dq[((long long)b * Ca + c) * T1 + t1] = acc;
+        }
+    } else {
+        for (int t2 = lane; t2 < T2; t2 += 32) arow[t2] = 0.0f;
+    }
+    __syncthreads();
+    float* dkb = dk + (long long)b * Ca * T2;
+    for (int i = tid; i < Ca * T2; i += ROWS * 32)
+        if (dks[i] != 0.0f) atomicAdd(dkb + i, dks[i]);
+    if (dtxt != nullptr) {
+        // dtxt[d,t2] += sum over this CTA's frames of dctx[d,t1] attn[t1,t2]
+        for (int i = tid; i < Dt * T2; i += ROWS * 32) {
+            const int d = i / T2, t2 = i % T2;
+            if (t2 >= len) continue;
+            float acc = 0.0f;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                if (t1_0 + r < T1) acc = fmaf(dcontext[((long long)b * Dt + d) * T1 + t1_0 + r], as[r * T2 + t2], acc);
+            atomicAdd(dtxt + ((long long)b * Dt + d) * T2 + t2, acc);
+        }
+    }
+}
+
 }  // namespace
+
+int soft_attention_bwd(const float* q, const float* k, const float* prior, const int* in_lens, const float* attn,
+                       const float* dattn, const float* dlogprob, const float* txt_enc, const float* dcontext, float* dq,
+                       float* dk, float* dtxt, int B, int Ca, int T1, int T2, int Dt, float temperature, cudaStream_t st) {
+    RADMMM_REQUIRE(B > 0 && Ca > 0 && T1 > 0 && T2 > 0, "soft_attention_bwd: bad sizes");
+    RADMMM_REQUIRE((txt_enc == nullptr) == (dcontext == nullptr), "soft_attention_bwd: txt_enc and dcontext go together");
+    const size_t smem = sizeof(float) * (2 * (size_t)Ca * T2 + (size_t)ROWS * Ca + 2 * (size_t)ROWS * T2);
+    RADMMM_REQUIRE(smem <= 220 * 1024, "soft_attention_bwd: T2=%d keys do not fit in shared memory", T2);
+    if (smem > 48 * 1024)
+        RADMMM_CUDA(cudaFuncSetAttribute(soft_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RADMMM_CUDA(cudaMemsetAsync(dk, 0, sizeof(float) * (size_t)B * Ca * T2, st));
+    if (dtxt) RADMMM_CUDA(cudaMemsetAsync(dtxt, 0, sizeof(float) * (size_t)B * Dt * T2, st));
+    dim3 grid(cdiv(T1, ROWS), B);
+    soft_attention_bwd_kernel<<<grid, ROWS * 32, smem, st>>>(q, k, prior, in_lens, attn, dattn, dlogprob, txt_enc, dcontext,
+                                                             dq, dk, dtxt, Ca, T1, T2, Dt, temperature);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
 
 int soft_attention(const float* q, const float* k, const float* prior, const int* in_lens, float* attn,
                    float* attn_logprob, const float* txt_enc, float* context, int B, int Ca, int T1, int T2, int Dt,

@@ -234,3 +234,70 @@ def test_context_lstm_vs_torch(precision, batch, lens):
     close(xg.grad.cpu().double() * mask.double(), xc.grad * mask.double(), tol * 5, what="lstm dx")
     for (n, p), (_, q) in zip(mine.named_parameters(), ref64.named_parameters()):
         close(p.grad, q.grad, tol * 10 * max(1.0, q.grad.abs().max().item()), what="lstm grad " + n)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_spline_flow_step_vs_reference(precision):
+    """FlowStep(use_spline=True): LUS 1x1 conv + FiLM parameter net + quadratic-spline kernels against the reference
+    fixture (train-mode batch statistics incl. the running-stat update, eval mode, inverse) and oracle gradients."""
+    import json
+    from oracle import spline as osp
+    from radmmm_b200 import decoders
+    from radmmm_b200.common import SequenceLength
+    gd = gold("spline_step.npz")
+    keys = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "spline_step_keys.json")))
+    sd = {}
+    for k, shape in keys:
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.tensor(0)
+        elif "running_var" in k or "lower_diag" in k:
+            sd[k] = torch.ones(shape)
+        elif k.endswith("invtbl_conv.p"):
+            sd[k] = torch.eye(8)[syn.hash_permutation("splstep.p", 8)]
+        else:
+            sd[k] = syn.hash_uniform("splstep." + k, tuple(shape), -0.3, 0.3)
+    sd["invtbl_conv.upper_diag"] = syn.hash_uniform("splstep.ud", (8,), 0.7, 1.3)
+    fs = decoders.FlowStep(8, 10, 2, mode="LUS", use_partial_padding=True, use_spline=True, use_bn=True)
+    assert [k for k, _ in keys] == list(fs.state_dict().keys())
+    fs.load_state_dict(sd)
+    fs.coupling_tfn.precision = precision
+    fs = fs.to(DEV).train()
+    lens = torch.tensor([21, 9])
+    z = syn.hash_uniform("splstep.z", (2, 8, 21), -3.5, 3.5)
+    ctx = syn.hash_uniform("splstep.ctx", (2, 10, 21), -1, 1)
+    m = of.length_mask(lens, 21)[:, None].double()
+    tol = 1e-4 if precision == "fp32" else 2e-3
+    zg = z.to(DEV).requires_grad_(True)
+    seq = SequenceLength(lens.to(DEV), 21)
+    zo, ld, ls = fs(zg, ctx.to(DEV), seq_lens=seq)
+    close(ld, gd["log_det"], 1e-6)
+    close(zo.cpu().double() * m, gd["z"].double() * m, tol, what="spline step z (train)")
+    close(ls.cpu().double() * m, gd["log_s"].double() * m, tol * 10, what="spline step log_s (train)")
+    close(fs.coupling_tfn.param_predictor.in_layers[0].bn.running_mean, gd["rm0"], 1e-5, what="running mean")
+    # gradients vs oracle autograd (fp64) on the same training forward
+    g1 = syn.hash_uniform("splstep.g1", (2, 8, 21)) * m.float()
+    g2 = syn.hash_uniform("splstep.g2", (2, 1, 21)) * m.float()
+    ((zo * g1.to(DEV)).sum() + (ls * g2.to(DEV)).sum()).backward()
+    sdd = {"flows.0." + k: (v.double().requires_grad_(True) if v.dtype == torch.float32 and v.numel() > 1 and
+                            not k.endswith(".p") and "running" not in k and "lower_diag" not in k else v.double() if v.is_floating_point() else v)
+           for k, v in sd.items()}
+    zc = z.double().requires_grad_(True)
+    cfg = of.DecoderConfig(n_conv_layers_per_step=2)
+    zm, _ = of.inv1x1_forward(sdd, "flows.0.invtbl_conv.", zc, "LUS")
+    zr, lr = osp.spline_coupling(sdd, "flows.0.coupling_tfn.", zm, ctx.double(), lens, cfg, training=True)
+    ((zr * g1.double()).sum() + (lr * g2.double()).sum()).backward()
+    gt = 2e-3 if precision == "fp32" else 2e-2
+    close(zg.grad, zc.grad, gt * max(1.0, zc.grad.abs().max().item()), what="spline step dz")
+    for name in ("coupling_tfn.param_predictor.end.weight", "coupling_tfn.param_predictor.in_layers.1.hidden_conv.conv.weight_v",
+                 "coupling_tfn.param_predictor.in_layers.0.cond_conv.conv.weight_g", "coupling_tfn.param_predictor.in_layers.0.bn.weight",
+                 "invtbl_conv.upper"):
+        ref = sdd["flows.0." + name].grad
+        mine = dict(fs.named_parameters())[name].grad
+        close(mine, ref, gt * max(1e-3, ref.abs().max().item()), what="grad " + name)
+    fs.eval()
+    with torch.no_grad():
+        zo2, _, ls2 = fs(z.to(DEV), ctx.to(DEV), seq_lens=seq)
+        close(zo2.cpu().double() * m, gd["z_eval"].double() * m, tol, what="spline step z (eval)")
+        close(ls2.cpu().double() * m, gd["log_s_eval"].double() * m, tol * 10, what="spline step log_s (eval)")
+        zi = fs(gd["z_eval"].to(DEV), ctx.to(DEV), inverse=True, seq_lens=seq)
+        close(zi.cpu().double() * m, gd["z_inv"].double() * m, 5e-3, what="spline step inverse")

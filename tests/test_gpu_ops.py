@@ -285,3 +285,46 @@ def test_soft_attention():
                                       None, B, 80, T1, T2, 0, 0.0005, N.stream()))
     close(attn, a_ref, 2e-6)
     close(logp, l_ref, 2e-5)
+
+
+def test_conv_attention_module_forward_backward():
+    """ConvAttention drop-in: state-dict compatible projections, fused attention kernel forward + backward (dq, dk through
+    the projections, and the fused context matmul) against oracle autograd."""
+    from radmmm_b200 import common
+    gd = gold("ops.npz")
+    att = common.ConvAttention(n_mel_channels=80, n_text_channels=24, n_att_channels=80)
+    sd = {}
+    for k, v in att.state_dict().items():
+        sd[k] = syn.hash_uniform("att." + k, tuple(v.shape), -0.2, 0.2)
+    att.load_state_dict(sd)
+    att = att.to(DEV)
+    q_in = syn.hash_uniform("att.q", (3, 80, 37), -1, 1)
+    k_in = syn.hash_uniform("att.k", (3, 24, 11), -1, 1)
+    in_lens = torch.tensor([11, 7, 3])
+    prior = syn.hash_uniform("att.prior", (3, 37, 11), 0.0, 1.0)
+    txt = syn.hash_uniform("att.txt", (3, 24, 11), -1, 1)
+    qg, kg, tg = q_in.to(DEV).requires_grad_(True), k_in.to(DEV).requires_grad_(True), txt.to(DEV).requires_grad_(True)
+    amask = ((torch.arange(11)[None] < in_lens[:, None])[..., None] == 0).to(DEV)
+    a, lp = att(qg, kg, LENS.to(DEV), amask, key_lens=in_lens.to(DEV), attn_prior=prior.to(DEV))
+    close(a, gd["att"], 2e-6, what="module attn vs reference")
+    close(lp, gd["att_logprob"], 2e-5, what="module logprob vs reference")
+    a2, lp2, ctx = att.forward_with_context(qg, kg, tg, key_lens=in_lens.to(DEV), attn_prior=prior.to(DEV))
+    close(ctx, gd["att_ctx"], 1e-5, what="fused context vs reference")
+    g1 = syn.hash_uniform("att.g1", (3, 1, 37, 11))
+    g2 = syn.hash_uniform("att.g2", (3, 1, 37, 11)) * 0.1
+    g3 = syn.hash_uniform("att.g3", (3, 24, 37))
+    ((a2 * g1.to(DEV)).sum() + (lp2 * g2.to(DEV)).sum() + (ctx * g3.to(DEV)).sum()).backward()
+    # oracle (fp64 autograd)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    qc, kc, tc = q_in.double().requires_grad_(True), k_in.double().requires_grad_(True), txt.double().requires_grad_(True)
+    qe, ke = ofe.attention_projections(sdd, "", qc, kc)
+    ar, lr = ofe.soft_attention(qe, ke, in_lens, prior.double())
+    cr = ofe.attend(tc, ar)
+    ((ar * g1.double()).sum() + (lr * g2.double()).sum() + (cr * g3.double()).sum()).backward()
+    close(qg.grad, qc.grad, 2e-5 * max(1.0, qc.grad.abs().max().item()), what="d queries")
+    close(kg.grad, kc.grad, 2e-5 * max(1.0, kc.grad.abs().max().item()), what="d keys")
+    close(tg.grad, tc.grad, 2e-5 * max(1.0, tc.grad.abs().max().item()), what="d txt_enc")
+    for n, p in att.named_parameters():
+        key = n.replace("weight_g", "weight_g").replace("weight_v", "weight_v")
+        ref = sdd[key].grad
+        close(p.grad, ref, 5e-5 * max(1e-3, ref.abs().max().item()), what="grad " + n)

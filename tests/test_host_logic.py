@@ -14,7 +14,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 SPECS = json.load(open(os.path.join(GOLD, "state_dict_keys.json")))
 
 
-@pytest.mark.parametrize("tag", ["radmmm", "radtts_accent"])
+@pytest.mark.parametrize("tag", ["radmmm", "radtts_accent", "radmmm_spline2"])
 def test_state_dict_matches_reference(tag):
     from radmmm_b200 import decoders
     spec = SPECS[tag]
