@@ -87,6 +87,10 @@ typedef struct radmmm_flow_desc {
     const void* ctx_rows;
     /* per-call activation workspace (radmmm_flow_workspace_bytes()); must outlive backward when training */
     void* workspace;
+    /* optional second cudaStream_t: radmmm_flow_backward forks the weight-gradient work (weight-grad GEMMs, weight-norm
+     * backward, bias sums) onto it so it overlaps the input-gradient chain, and joins it back before returning work to
+     * `stream`.  NULL = everything on `stream`. */
+    void* side_stream;
 } radmmm_flow_desc;
 
 size_t radmmm_flow_prepared_bytes(int mode, int C, int D, int H, int L);

@@ -36,6 +36,7 @@ class FlowDesc(C.Structure):
         ("prepared", _fp),
         ("ctx_rows", _fp),
         ("workspace", _fp),
+        ("side_stream", _fp),
     ]
 
 

@@ -103,6 +103,19 @@ def _as_btd(context: torch.Tensor) -> torch.Tensor:
 
 
 _scratch_cache = {}
+_side_streams = {}
+
+
+def _side_stream(device) -> int:
+    """One extra stream per device for the weight-gradient lane of radmmm_flow_backward (RADMMM_B200_SIDE_STREAM=0
+    disables the fork)."""
+    if os.environ.get("RADMMM_B200_SIDE_STREAM", "1") == "0":
+        return 0
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[device.index] = st
+    return st.cuda_stream
 
 # Optional gradient sink (radmmm_b200.ddp.BucketedGradReducer): maps a parameter's storage pointer to a fresh view of
 # its all-reduce bucket so FlowStepFunction.backward writes parameter gradients straight into bucket storage.
@@ -295,6 +308,7 @@ class FlowStepFunction(torch.autograd.Function):
         d.prepared = N.ptr(ctx.prepared_buf)
         d.ctx_rows = N.ptr(ctx.rows.rows)
         d.workspace = N.ptr(ctx.ws)
+        d.side_stream = _side_stream(z.device) or None
         W_T = W.t().contiguous() if ctx.has_W else None
         d.W, d.W_T, d.mean = (N.fptr(W) if ctx.has_W else None), N.fptr(W_T), (N.fptr(mean) if ctx.has_mean else None)
         dz_out = dz_out.contiguous() if dz_out is not None else torch.zeros_like(z)

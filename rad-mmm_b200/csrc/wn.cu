@@ -288,6 +288,13 @@ static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat&
     return launch_gemm(a, d.mode, st);
 }
 
+// events for the fork/join with the side stream (created once per host thread; timing disabled)
+static cudaEvent_t side_event(int i) {
+    static thread_local cudaEvent_t ev[16] = {};
+    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    return ev[i];
+}
+
 int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_mid, const float* params,
                   const float* dz_out, const float* dlog_s, float* dz_mid, float* dparams, float* dz_in,
                   float* dctx_rows, const radmmm_flow_grads* gr, void* scratch, cudaStream_t st) {
@@ -302,12 +309,28 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
     const int H = d.H, L = d.L;
     ActMat ctx; ctx.ptr = const_cast<void*>(f->ctx_rows); ctx.ld = d.Dp; ctx.plane_stride = (long long)d.R * d.Dp;
     GemmArgs a;
+    // Two lanes of work: `st` carries the input-gradient chain (the critical path), `sd` the weight-gradient work that
+    // only consumes what the chain produces.  Event k: "chain product k is ready"; event 8+k: "side is done with buffer k".
+    cudaStream_t sd = f->side_stream ? reinterpret_cast<cudaStream_t>(f->side_stream) : st;
+    const bool forked = sd != st;
+    auto signal = [&](cudaStream_t from, cudaStream_t to, int ev) -> int {
+        if (!forked) return RADMMM_OK;
+        RADMMM_CUDA(cudaEventRecord(side_event(ev), from));
+        RADMMM_CUDA(cudaStreamWaitEvent(to, side_event(ev), 0));
+        return RADMMM_OK;
+    };
 
     // 1. coupling tail
     RADMMM_TRY(coupling_bwd(dz_out, dlog_s, z_mid, params, f->lens, dz_mid, dparams, d.B, d.C, d.Tp, f->scaling_fn, st));
     RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, d.Cp, 1, st));
-    // 2. end conv: bias, weight, input gradients
-    RADMMM_TRY(colsum(d.mode, s.DP, g, d.C, 1, 0, gr->end_b, st));
+    // 2. end conv: input gradient on the chain ...
+    init_args(a, d, f->lens, EPI_DOUT, H);
+    add_seg(a, s.DP, p.WendT, d.Cp, 0);
+    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.S[i]; a.epi.dq[i] = s.DQ[i]; }
+    RADMMM_TRY(launch_gemm(a, d.mode, st));
+    RADMMM_TRY(signal(st, sd, 0));            // DP and every DQ_i are ready
+    //    ... bias / weight gradients on the side
+    RADMMM_TRY(colsum(d.mode, s.DP, g, d.C, 1, 0, gr->end_b, sd));
     {   // dW_end = dP^T (sum_i s_i): one weight-grad GEMM accumulating over the L stored s_i
         GemmArgs wa;
         init_args(wa, d, f->lens, EPI_WGRAD, H);
@@ -315,23 +338,21 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         for (int i = 0; i < L; ++i) { GemmSeg& sg = wa.seg[wa.n_seg++]; sg.a = s.DP; sg.w = w.S[i]; sg.K = d.R; sg.shift = 0; }
         wa.epi.M = d.C; wa.epi.f32_out = gr->end_w; wa.epi.f32_ld = H; wa.epi.f32_tap_stride = 0;
         wa.split_k = 0; wa.epi.atomic = 1;
-        RADMMM_CUDA(cudaMemsetAsync(gr->end_w, 0, sizeof(float) * (size_t)d.C * H, st));
-        RADMMM_TRY(launch_gemm(wa, d.mode, st));
+        RADMMM_CUDA(cudaMemsetAsync(gr->end_w, 0, sizeof(float) * (size_t)d.C * H, sd));
+        RADMMM_TRY(launch_gemm(wa, d.mode, sd));
     }
-    init_args(a, d, f->lens, EPI_DOUT, H);
-    add_seg(a, s.DP, p.WendT, d.Cp, 0);
-    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.S[i]; a.epi.dq[i] = s.DQ[i]; }
-    RADMMM_TRY(launch_gemm(a, d.mode, st));
     // 3. layers, last to first
     for (int i = L - 1; i >= 0; --i) {
         const int dil = 1 << i;
         const int cur = i & 1, nxt = (i + 1) & 1;
-        // res-skip conv i
-        RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], st));
-        RADMMM_TRY(wgrad(d, f->lens, s.DQ[i], w.Hs[i + 1], H, H, 1, 1, s.dW, H, 0, st));
+        // side: res-skip conv i (needs DQ_i, available since event 0)
+        RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], sd));
+        RADMMM_TRY(wgrad(d, f->lens, s.DQ[i], w.Hs[i + 1], H, H, 1, 1, s.dW, H, 0, sd));
         RADMMM_TRY(wn_bwd(s.dW, H, 0, H, nullptr, 0, 0, f->rs_v[i], f->rs_g[i], p.norm_rs + (size_t)i * H, H, H, 1,
-                          gr->rs_v[i], gr->rs_g[i], st));
-        // dh_{i+1} = Wrs_i^T dq_i + sum_taps Win_{i+1,j}^T dacc_{i+1}[r - (j-2) d_{i+1}]  -> dacc_i
+                          gr->rs_v[i], gr->rs_g[i], sd));
+        // chain: dh_{i+1} = Wrs_i^T dq_i + sum_taps Win_{i+1,j}^T dacc_{i+1}[r - (j-2) d_{i+1}]  -> dacc_i
+        // DACC[cur] was last read by the side stream for layer i+2: wait until it is done with it
+        if (forked && i + 2 <= L - 1) RADMMM_CUDA(cudaStreamWaitEvent(st, side_event(8 + cur), 0));
         init_args(a, d, f->lens, EPI_DH, H);
         add_seg(a, s.DQ[i], sub_mode(p.WrsT, (long long)i * p.HH, d.es), H, 0);
         if (i < L - 1)
@@ -341,26 +362,30 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         a.epi.dilation = dil;
         a.epi.out0 = s.DACC[cur];
         RADMMM_TRY(launch_gemm(a, d.mode, st));
-        // dilated conv i: bias (un-ratio'd), weights
-        RADMMM_TRY(colsum(d.mode, s.DACC[cur], g, H, dil, 1, gr->in_b[i], st));
-        RADMMM_TRY(wgrad(d, f->lens, s.DACC[cur], w.Hs[i], H, H, 5, dil, s.dW, H, p.HH, st));
+        RADMMM_TRY(signal(st, sd, 1 + cur));  // dacc_i ready
+        // side: dilated conv i: bias (un-ratio'd), weights
+        RADMMM_TRY(colsum(d.mode, s.DACC[cur], g, H, dil, 1, gr->in_b[i], sd));
+        RADMMM_TRY(wgrad(d, f->lens, s.DACC[cur], w.Hs[i], H, H, 5, dil, s.dW, H, p.HH, sd));
         RADMMM_TRY(wn_bwd(s.dW, H, p.HH, H, nullptr, 0, 0, f->in_v[i], f->in_g[i], p.norm_in + (size_t)i * H, H, H, 5,
-                          gr->in_v[i], gr->in_g[i], st));
+                          gr->in_v[i], gr->in_g[i], sd));
+        if (forked) RADMMM_CUDA(cudaEventRecord(side_event(8 + cur), sd));   // side is done reading DACC[cur]
     }
-    // 4. dh0 (masked) from layer 0's dilated conv; reuse DACC[1] for it
+    // 4. dh0 (masked) from layer 0's dilated conv; it reuses DACC[1] (last read by the side stream for layer 1 / 3)
+    if (forked && L >= 2) RADMMM_CUDA(cudaStreamWaitEvent(st, side_event(8 + 1), 0));
     init_args(a, d, f->lens, EPI_DH0, H);
     for (int j = 0; j < 5; ++j) add_seg(a, s.DACC[0], sub_mode(p.WinT, (long long)j * p.HH, d.es), H, -(j - 2));
     a.epi.out0 = s.DACC[1];
     RADMMM_TRY(launch_gemm(a, d.mode, st));
     const ActMat& DH0 = s.DACC[1];
-    // 5. start conv
-    RADMMM_TRY(colsum(d.mode, DH0, g, H, 1, 0, gr->start_b, st));
+    RADMMM_TRY(signal(st, sd, 3));            // dh0 ready
+    // 5. start conv: weight / bias gradients on the side, input gradients on the chain
+    RADMMM_TRY(colsum(d.mode, DH0, g, H, 1, 0, gr->start_b, sd));
     float* dWz = s.dW;
     float* dWc = s.dW + (size_t)H * d.Kz;
-    RADMMM_TRY(wgrad(d, f->lens, DH0, w.Z0, H, d.Kz, 1, 1, dWz, d.Kz, 0, st));
-    RADMMM_TRY(wgrad(d, f->lens, DH0, ctx, H, d.Dp, 1, 1, dWc, d.Dp, 0, st));
+    RADMMM_TRY(wgrad(d, f->lens, DH0, w.Z0, H, d.Kz, 1, 1, dWz, d.Kz, 0, sd));
+    RADMMM_TRY(wgrad(d, f->lens, DH0, ctx, H, d.Dp, 1, 1, dWc, d.Dp, 0, sd));
     RADMMM_TRY(wn_bwd(dWz, d.Kz, 0, d.Ch, dWc, d.Dp, 0, f->start_v, f->start_g, p.norm_start, H, d.Ch + d.D, 1,
-                      gr->start_v, gr->start_g, st));
+                      gr->start_v, gr->start_g, sd));
     init_args(a, d, f->lens, EPI_DZ0, d.Ch);
     add_seg(a, DH0, p.WzT, H, 0);
     a.epi.cf_out = dz_mid; a.epi.cf_C = d.C; a.epi.cf_c0 = 0; a.epi.accumulate = 1;
@@ -378,6 +403,7 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
     } else {
         RADMMM_REQUIRE(dz_in == dz_mid, "flow_backward: without W_T, dz_in must alias dz_mid");
     }
+    RADMMM_TRY(signal(sd, st, 4));            // join: everything the caller sees is ordered on `st`
     return RADMMM_OK;
 }
 
