@@ -449,10 +449,16 @@ class _InvertibleBase(nn.Module):
     def _weight(self) -> torch.Tensor:
         raise NotImplementedError
 
+    def _compute_inverse(self) -> torch.Tensor:
+        raise NotImplementedError
+
     def _inverse_weight(self) -> torch.Tensor:
+        """W^-1 for the inference pass (common.py:532-537, 599-604), cached when ``cache_inverse`` is set.  Built from
+        triangular solves of the LU factors (cuBLAS trsm) rather than a dense inverse: no cuSOLVER on the path."""
         if self.cache_inverse and getattr(self, "W_inverse", None) is not None:
             return self.W_inverse
-        w_inv = torch.linalg.inv(self._weight().detach().float())
+        with torch.no_grad():
+            w_inv = self._compute_inverse().float().contiguous()
         if self.cache_inverse:
             self.W_inverse = w_inv
         return w_inv
@@ -481,6 +487,16 @@ class Invertible1x1ConvLUS(_InvertibleBase):
         U = torch.triu(self.upper, 1) + torch.diag(self.upper_diag)
         Lm = torch.tril(self.lower, -1) + torch.diag(self.lower_diag)
         return torch.mm(self.p, torch.mm(Lm, U))
+
+    def _compute_inverse(self):
+        # W = P L U  ->  W^-1 = U^-1 L^-1 P^T
+        c = self.upper.shape[0]
+        eye = torch.eye(c, device=self.upper.device, dtype=torch.float64)
+        U = (torch.triu(self.upper, 1) + torch.diag(self.upper_diag)).double()
+        Lm = (torch.tril(self.lower, -1) + torch.diag(self.lower_diag)).double()
+        u_inv = torch.linalg.solve_triangular(U, eye, upper=True)
+        l_inv = torch.linalg.solve_triangular(Lm, eye, upper=False)
+        return u_inv @ l_inv @ self.p.double().t()
 
     def forward(self, z, inverse=False, lens=None):
         b, c, t = z.shape
@@ -516,7 +532,8 @@ class DataInitializedInvertible1x1Conv(_InvertibleBase):
             cen = (data - mean[None, :, None]) * mask
             covar = torch.einsum("bct,bdt->cd", cen, cen) / n
             self.covar = covar
-            wm = torch.linalg.cholesky(torch.linalg.inv(covar), upper=True).contiguous()
+            # one-off 160x160 factorisation: done on the host in fp64 (keeps cuSOLVER off the GPU path)
+            wm = torch.linalg.cholesky(torch.linalg.inv(covar.double().cpu()), upper=True).float().to(data.device).contiguous()
             mean = mean[:, None].contiguous()
             if dist.is_available() and dist.is_initialized():
                 dist.broadcast(wm, 0)
@@ -538,6 +555,11 @@ class DataInitializedInvertible1x1Conv(_InvertibleBase):
 
     def _weight(self):
         return torch.triu(self.upper, 1) + torch.diag(self.upper_diag)
+
+    def _compute_inverse(self):
+        c = self.upper.shape[0]
+        eye = torch.eye(c, device=self.upper.device, dtype=torch.float64)
+        return torch.linalg.solve_triangular(self._weight().double(), eye, upper=True)
 
     def forward(self, z, inverse=False, lens=None):
         b, c, t = z.shape
@@ -566,7 +588,8 @@ class Invertible1x1Conv(nn.Module):
         ln = _lens_of(None, z.shape[0], z.shape[2], z.device)
         if inverse:
             if not (self.cache_inverse and getattr(self, "W_inverse", None) is not None):
-                self.W_inverse = torch.linalg.inv(W.detach().float())
+                # dense W: invert once on the host in fp64 (a 160x160 matrix), no cuSOLVER on the GPU path
+                self.W_inverse = torch.linalg.inv(W.detach().double().cpu()).float().to(W.device)
             w_inv = self.W_inverse
             if not self.cache_inverse:
                 self.W_inverse = None

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-PT="python -m pytest -q -p no:cacheprovider --timeout=300 -m gpu"
+PT="python -m pytest -q -p no:cacheprovider --timeout=600 -m gpu"
 run() { name=$1; shift; echo "=== $name"; timeout 900 "$@" > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -n 8 gpurun_out/$name.log; }
 run lstm      $PT tests/test_gpu_decoder.py -k "context_lstm"
 run ops       $PT tests/test_gpu_ops.py

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-PT="python -m pytest -q -p no:cacheprovider --timeout=300 -m gpu"
+PT="python -m pytest -q -p no:cacheprovider --timeout=600 -m gpu"
 run() { name=$1; shift; echo "=== $name"; timeout 900 "$@" > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -n 6 gpurun_out/$name.log; }
 run dec       $PT tests/test_gpu_decoder.py -k "fixture or small"
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench5_bf16.json 2> gpurun_out/bench5_bf16.err; echo "bf16 exit $?"; python - <<'PY'
