@@ -14,13 +14,10 @@
 // The weight-grad GEMM contracts over rows: dY [R][M] and X [R][N] are read as MN-major UMMA operands straight from the
 // row matrices (64-channel x 64-row boxes, 128B swizzle), so the tap shift is an outer (row) TMA coordinate and no
 // transposed copies exist; split-K partial tiles are reduced with fp32 atomics.
-// Cluster variant (CL = 4, a 2x2 group of tiles): the two CTAs that share a row tile each load half of the A box and
-// multicast it to both, the two CTAs that share a column tile do the same for B, so every operand byte crosses the
-// L2 -> SM fabric once per CTA pair instead of once per CTA (the k=5 conv at B=8, T=800 moves 400 MB per launch without
-// it and is L2-bandwidth bound at ~730 TFLOP/s).  Stage release is a multicast tcgen05.commit to the three CTAs that
-// write into this CTA's stage.
+// CTA-pair variant (CL = 2, tcgen05.mma.cta_group::2, UMMA 256 x BN x 16): used whenever the row-tile count is even.
 // Roofline: tensor pipe (dense bf16, MEASURED_PEAKS.json); BF16X3 has one third of it.
 #include <cuda.h>
+#include <stdlib.h>
 #include "gemm.cuh"
 
 namespace radmmm {
@@ -83,14 +80,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+// cta_group::2 form: executed by both CTAs of a pair; the transaction bytes update the LEADER's barrier (peer bit of the
+// shared::cluster barrier address cleared, as CUTLASS' SM100_TMA_2SM_LOAD does)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+template <int CL>
+__device__ __forceinline__ void tma_load(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    if constexpr (CL == 2) tma_load_2d_2sm(smem_dst, map, bar, c0, c1);
+    else tma_load_2d(smem_dst, map, bar, c0, c1);
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -115,15 +124,30 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CL>
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if constexpr (CL == 2) {     // arrive on the barrier at this offset in BOTH CTAs of the pair
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
 }
+template <int CL>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    if constexpr (CL == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -161,16 +185,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn, bool mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(int bn, bool mn_major, int cl) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
-           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((BM * cl) >> 4) << 24);      // M = 128 per CTA, 256 for a CTA pair
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, int CL>
 struct Cfg {
     static constexpr int planes = (MODE == MODE_BF16X3) ? 2 : 1;
-    static constexpr int a_bytes = BM * BK * 2;
-    static constexpr int b_bytes = BN * BK * 2;
+    static constexpr int a_bytes = BM * BK * 2;                 // this CTA's 128 rows (row GEMM) / 128 channels (weight-grad)
+    static constexpr int b_rows = BN / CL;                      // cta_group::2: each CTA of the pair holds half of B's N extent
+    static constexpr int b_bytes = b_rows * BK * 2;
     static constexpr int stage_bytes = planes * (a_bytes + b_bytes);
     static constexpr int stages = (200 * 1024) / stage_bytes > 8 ? 8 : (200 * 1024) / stage_bytes;
     static constexpr int tmem_cols = 2 * BN;      // 256 or 512: powers of two
@@ -178,23 +203,25 @@ struct Cfg {
     static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * stage_tile_bytes;
 };
 
+// CL == 1: one CTA per 128 x BN tile, tcgen05.mma.cta_group::1.
+// CL == 2: a CTA pair (cluster of 2) per 256 x BN tile, tcgen05.mma.cta_group::2 issued by the leader (rank 0): each
+//          CTA stages its own 128 rows of A and HALF of B, the pair's tensor cores read both halves, each CTA keeps its
+//          128 accumulator rows in its own TMEM.  Per-CTA shared-memory traffic per MMA drops from 48 KB to 32 KB
+//          (BN = 256), which buys 6 pipeline stages instead of 4 -- the 1-CTA kernel was TMA-latency bound with the
+//          tensor pipe 57 % active (profiles/).
 template <int MODE, int KIND, int BN, bool WGRAD, int CL>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
-    using C = Cfg<MODE, BN>;
-    static_assert(CL == 1 || CL == 4, "cluster size");
-    // 2x2 cluster geometry: rank = cm + 2*cn; cm selects the row tile of the pair, cn the column tile
-    const uint32_t crank = (CL == 4) ? cluster_rank() : 0u;
-    const int cm = crank & 1, cn = crank >> 1;
-    const uint16_t mask_a = (uint16_t)((1u << crank) | (1u << (crank ^ 2)));     // CTAs sharing my row tile (same cm)
-    const uint16_t mask_b = (uint16_t)((1u << crank) | (1u << (crank ^ 1)));     // CTAs sharing my column tile (same cn)
-    const uint16_t mask_rel = (uint16_t)(mask_a | mask_b);                        // CTAs that write into my stages
+    using C = Cfg<MODE, BN, CL>;
+    static_assert(CL == 1 || CL == 2, "cluster size");
+    const uint32_t crank = (CL == 2) ? cluster_rank() : 0u;
+    const bool leader = crank == 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
-    uint64_t* full = bars;                       // [stages]
+    uint64_t* full = bars;                       // [stages]  (CL == 2: only the leader's are waited on)
     uint64_t* empty = bars + C::stages;          // [stages]
     uint64_t* tfull = bars + 2 * C::stages;      // [2]
-    uint64_t* tempty = bars + 2 * C::stages + 2; // [2]
+    uint64_t* tempty = bars + 2 * C::stages + 2; // [2]       (CL == 2: only the leader's are waited on)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::stages + 4);
     __nv_bfloat16* stage_tiles = reinterpret_cast<__nv_bfloat16*>(smem + C::stages * C::stage_bytes + 256);
 
@@ -205,42 +232,45 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         for (int i = 0; i < P.n_b_maps; ++i) { prefetch_tmap(&P.b_hi[i]); if (C::planes == 2) prefetch_tmap(&P.b_lo[i]); }
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < C::stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL == 4 ? 3 : 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * kEpiWarps); }
+        for (int i = 0; i < C::stages; ++i) { mbar_init(&full[i], CL); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CL * 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CL == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (CL == 4) cluster_sync_all();          // peers' barriers are initialised before any remote arrive / multicast
+    if (CL == 2) cluster_sync_all();          // the peer's barriers exist before any remote arrive / 2-CTA TMA / MMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Tile walk.  CL == 1: CTA b takes tiles b, b + grid, ...  CL == 4: cluster c takes 2x2 super-tiles c, c + #clusters, ...
-    // and CTA (cm, cn) of the cluster works on tile (2*sm + cm, 2*sn + cn); `tile` below always is the CTA's own linear
-    // tile index in the (m_tiles x n_tiles [x taps x split]) space, `walk` the scheduler position.
+    // Tile walk.  A "walk" position is one 128 x BN tile (CL == 1) or one 256 x BN pair tile (CL == 2, CTA `crank` takes
+    // row tile 2*pm + crank).  Weight-grad: the (tap, split-K range) pair is the slowest index.
     const int tiles_mn = P.m_tiles * P.n_tiles;
-    const int n_tiles_total = WGRAD ? tiles_mn * P.taps * P.split_k : tiles_mn;
-    const int walk_begin = (CL == 4) ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
-    const int walk_step = (CL == 4) ? (int)(gridDim.x >> 2) : (int)gridDim.x;
-    const int walk_end = (CL == 4) ? n_tiles_total / 4 : n_tiles_total;
-    auto tile_of = [&](int walk) -> int {
-        if (CL == 1) return walk;
-        const int sn_tiles = P.n_tiles >> 1, smn = (P.m_tiles >> 1) * sn_tiles;
-        const int outer = walk / smn, inner = walk % smn;          // outer = (tap, split) for weight-grad
-        const int sm = inner / sn_tiles, sn = inner % sn_tiles;
-        return outer * tiles_mn + (2 * sm + cm) * P.n_tiles + (2 * sn + cn);
+    const int walk_mn = tiles_mn / CL;
+    const int walk_end = WGRAD ? walk_mn * P.taps * P.split_k : walk_mn;
+    const int walk_begin = (int)blockIdx.x / CL, walk_step = (int)gridDim.x / CL;
+    auto decode = [&](int walk, int& m_blk, int& n_blk, int& tap, int& split) {
+        const int mn = walk % walk_mn, ts = walk / walk_mn;
+        tap = WGRAD ? ts / P.split_k : 0;
+        split = WGRAD ? ts % P.split_k : 0;
+        m_blk = (mn / P.n_tiles) * CL + (int)crank;
+        n_blk = mn % P.n_tiles;
     };
-
     // weight-grad split-K range (in 64-row K blocks)
     auto k_range = [&](int split, int& kb0, int& kb1) {
         const int per = (P.k_blocks_total + P.split_k - 1) / P.split_k;
         kb0 = min(P.k_blocks_total, split * per);
         kb1 = min(P.k_blocks_total, kb0 + per);
     };
+    const bool all_segs = !WGRAD || P.acc_segs;     // segments accumulate into one tile (row GEMM / accumulating weight-grad)
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA producer
@@ -248,11 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             for (int walk = walk_begin; walk < walk_end; walk += walk_step) {
-                const int tile = tile_of(walk);
-                int mn = tile, tap = 0, split = 0;
-                if (WGRAD) { mn = tile % tiles_mn; const int ts = tile / tiles_mn; tap = ts / P.split_k; split = ts % P.split_k; }
-                const int m_blk = mn / P.n_tiles, n_blk = mn % P.n_tiles;
-                const int seg_begin = (WGRAD && !P.acc_segs) ? tap : 0, seg_end = (WGRAD && !P.acc_segs) ? tap + 1 : P.n_seg;
+                int m_blk, n_blk, tap, split;
+                decode(walk, m_blk, n_blk, tap, split);
+                const int seg_begin = all_segs ? 0 : tap, seg_end = all_segs ? P.n_seg : tap + 1;
                 for (int s = seg_begin; s < seg_end; ++s) {
                     const TcSeg sg = P.seg[s];
                     int kb0 = 0, kb1 = sg.k_blocks;
@@ -260,55 +288,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* st = smem + stage * C::stage_bytes;
-                        mbar_expect_tx(&full[stage], C::stage_bytes);
                         uint8_t* sa_hi = st;
-                        uint8_t* sb_hi = st + C::planes * C::a_bytes;
                         uint8_t* sa_lo = st + C::a_bytes;
-                        uint8_t* sb_lo = st + 2 * C::a_bytes + C::b_bytes;
-                        if (!WGRAD && CL == 4) {
-                            // my half of each box (A: 64 of the 128 rows, B: BN/2 rows), multicast to the sharing pair
-                            const int a_c0 = kb * BK, a_c1 = m_blk * BM + cn * (BM / 2) + sg.a_row_shift;
-                            const int b_c0 = kb * BK, b_c1 = n_blk * BN + cm * (BN / 2) + sg.b_row_off;
-                            const int a_off = cn * (BM / 2) * 128, b_off = cm * (BN / 2) * 128;
-                            tma_load_2d_mc(sa_hi + a_off, &P.a_hi[sg.a_map], &full[stage], a_c0, a_c1, mask_a);
-                            tma_load_2d_mc(sb_hi + b_off, &P.b_hi[sg.b_map], &full[stage], b_c0, b_c1, mask_b);
-                            if (C::planes == 2) {
-                                tma_load_2d_mc(sa_lo + a_off, &P.a_lo[sg.a_map], &full[stage], a_c0, a_c1, mask_a);
-                                tma_load_2d_mc(sb_lo + b_off, &P.b_lo[sg.b_map], &full[stage], b_c0, b_c1, mask_b);
-                            }
-                        } else if (!WGRAD) {
+                        uint8_t* sb_hi = st + C::planes * C::a_bytes;
+                        uint8_t* sb_lo = sb_hi + C::b_bytes;
+                        uint64_t* fb = &full[stage];
+                        if (CL == 1) mbar_expect_tx(fb, C::stage_bytes);
+                        if (!WGRAD) {
                             const int a_c0 = kb * BK, a_c1 = m_blk * BM + sg.a_row_shift;
-                            const int b_c0 = kb * BK, b_c1 = n_blk * BN + sg.b_row_off;
-                            tma_load_2d(sa_hi, &P.a_hi[sg.a_map], &full[stage], a_c0, a_c1);
-                            tma_load_2d(sb_hi, &P.b_hi[sg.b_map], &full[stage], b_c0, b_c1);
+                            const int b_c0 = kb * BK, b_c1 = n_blk * BN + (int)crank * C::b_rows + sg.b_row_off;
+                            tma_load<CL>(sa_hi, &P.a_hi[sg.a_map], fb, a_c0, a_c1);
+                            tma_load<CL>(sb_hi, &P.b_hi[sg.b_map], fb, b_c0, b_c1);
                             if (C::planes == 2) {
-                                tma_load_2d(sa_lo, &P.a_lo[sg.a_map], &full[stage], a_c0, a_c1);
-                                tma_load_2d(sb_lo, &P.b_lo[sg.b_map], &full[stage], b_c0, b_c1);
-                            }
-                        } else if (CL == 4) {
-                            // weight-grad: 64-channel x 64-row boxes; I load box cn of A and boxes [cm*BN/128, ...) of B
-                            const int ra = kb * BK, rb = kb * BK + sg.b_row_off;
-                            tma_load_2d_mc(sa_hi + cn * (BK * 128), &P.a_hi[0], &full[stage], m_blk * BM + cn * 64, ra, mask_a);
-                            if (C::planes == 2) tma_load_2d_mc(sa_lo + cn * (BK * 128), &P.a_lo[0], &full[stage], m_blk * BM + cn * 64, ra, mask_a);
-#pragma unroll
-                            for (int j = 0; j < BN / 128; ++j) {
-                                const int i = cm * (BN / 128) + j;
-                                tma_load_2d_mc(sb_hi + i * (BK * 128), &P.b_hi[sg.b_map], &full[stage], n_blk * BN + i * 64, rb, mask_b);
-                                if (C::planes == 2) tma_load_2d_mc(sb_lo + i * (BK * 128), &P.b_lo[sg.b_map], &full[stage], n_blk * BN + i * 64, rb, mask_b);
+                                tma_load<CL>(sa_lo, &P.a_lo[sg.a_map], fb, a_c0, a_c1);
+                                tma_load<CL>(sb_lo, &P.b_lo[sg.b_map], fb, b_c0, b_c1);
                             }
                         } else {
                             // 64-channel x 64-row boxes; inner coordinate = channel, outer = row (tap shift on X)
                             const int ra = kb * BK, rb = kb * BK + sg.b_row_off;
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i) {
-                                tma_load_2d(sa_hi + i * (BK * 128), &P.a_hi[0], &full[stage], m_blk * BM + i * 64, ra);
-                                if (C::planes == 2) tma_load_2d(sa_lo + i * (BK * 128), &P.a_lo[0], &full[stage], m_blk * BM + i * 64, ra);
+                                tma_load<CL>(sa_hi + i * (BK * 128), &P.a_hi[0], fb, m_blk * BM + i * 64, ra);
+                                if (C::planes == 2) tma_load<CL>(sa_lo + i * (BK * 128), &P.a_lo[0], fb, m_blk * BM + i * 64, ra);
                             }
 #pragma unroll
-                            for (int i = 0; i < BN / 64; ++i) {
-                                tma_load_2d(sb_hi + i * (BK * 128), &P.b_hi[sg.b_map], &full[stage], n_blk * BN + i * 64, rb);
-                                if (C::planes == 2) tma_load_2d(sb_lo + i * (BK * 128), &P.b_lo[sg.b_map], &full[stage], n_blk * BN + i * 64, rb);
+                            for (int i = 0; i < C::b_rows / 64; ++i) {
+                                const int col = n_blk * BN + (int)crank * C::b_rows + i * 64;
+                                tma_load<CL>(sb_hi + i * (BK * 128), &P.b_hi[sg.b_map], fb, col, rb);
+                                if (C::planes == 2) tma_load<CL>(sb_lo + i * (BK * 128), &P.b_lo[sg.b_map], fb, col, rb);
                             }
+                        }
+                        if (CL == 2) {
+                            // both CTAs' bytes land on the LEADER's barrier: the leader posts the expected total, the
+                            // peer contributes its arrival remotely
+                            if (leader) mbar_expect_tx(fb, 2 * C::stage_bytes);
+                            else mbar_arrive_remote(fb, 0);
                         }
                         if (++stage == C::stages) { stage = 0; phase ^= 1; }
                     }
@@ -316,62 +330,63 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc(BN, WGRAD);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int walk = walk_begin; walk < walk_end; walk += walk_step, ++it) {
-            const int tile = tile_of(walk);
-            int total_kb = 0;
-            if (!WGRAD) {
-                for (int s = 0; s < P.n_seg; ++s) total_kb += P.seg[s].k_blocks;
-            } else {
-                const int split = (tile / tiles_mn) % P.split_k;
-                int kb0, kb1;
-                k_range(split, kb0, kb1);
-                total_kb = (kb1 - kb0) * (P.acc_segs ? P.n_seg : 1);
-            }
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            mbar_wait(&tempty[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BN;
-            for (int kb = 0; kb < total_kb; ++kb) {
-                mbar_wait(&full[stage], phase);
+        // ------------------------------------------------------------------------------------------ MMA issuer (leader only)
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(BN, WGRAD, CL);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int walk = walk_begin; walk < walk_end; walk += walk_step, ++it) {
+                int m_blk, n_blk, tap, split;
+                decode(walk, m_blk, n_blk, tap, split);
+                int total_kb = 0;
+                if (!WGRAD) {
+                    for (int s = 0; s < P.n_seg; ++s) total_kb += P.seg[s].k_blocks;
+                } else {
+                    int kb0, kb1;
+                    k_range(split, kb0, kb1);
+                    total_kb = (kb1 - kb0) * (P.acc_segs ? P.n_seg : 1);
+                }
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(smem + stage * C::stage_bytes);
-                    // K-major: one UMMA_K step = 32 B inside the 128 B swizzle row; MN-major: 16 K-rows = 2048 B
-                    constexpr uint32_t kstep = WGRAD ? (UMMA_K * 128) : (UMMA_K * 2);
-                    const uint64_t da_hi = WGRAD ? make_smem_desc_mn(st) : make_smem_desc(st);
-                    const uint64_t db_hi = WGRAD ? make_smem_desc_mn(st + C::planes * C::a_bytes)
-                                                 : make_smem_desc(st + C::planes * C::a_bytes);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * kstep) >> 4);
-                        umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    }
-                    if (C::planes == 2) {
-                        const uint64_t da_lo = WGRAD ? make_smem_desc_mn(st + C::a_bytes) : make_smem_desc(st + C::a_bytes);
-                        const uint64_t db_lo = WGRAD ? make_smem_desc_mn(st + 2 * C::a_bytes + C::b_bytes)
-                                                     : make_smem_desc(st + 2 * C::a_bytes + C::b_bytes);
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t st = smem_u32(smem + stage * C::stage_bytes);
+                        const uint32_t a_hi = st, a_lo = st + C::a_bytes;
+                        const uint32_t b_hi = st + C::planes * C::a_bytes, b_lo = b_hi + C::b_bytes;
+                        // K-major: one UMMA_K step = 32 B inside the 128 B swizzle row; MN-major: 16 K-rows = 2048 B
+                        constexpr uint32_t kstep = WGRAD ? (UMMA_K * 128) : (UMMA_K * 2);
+                        const uint64_t da_hi = WGRAD ? make_smem_desc_mn(a_hi) : make_smem_desc(a_hi);
+                        const uint64_t db_hi = WGRAD ? make_smem_desc_mn(b_hi) : make_smem_desc(b_hi);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * kstep) >> 4);
-                            umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
-                            umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                            umma_bf16<CL>(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         }
+                        if (C::planes == 2) {
+                            const uint64_t da_lo = WGRAD ? make_smem_desc_mn(a_lo) : make_smem_desc(a_lo);
+                            const uint64_t db_lo = WGRAD ? make_smem_desc_mn(b_lo) : make_smem_desc(b_lo);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                const uint64_t koff = (uint64_t)((k * kstep) >> 4);
+                                umma_bf16<CL>(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                                umma_bf16<CL>(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                            }
+                        }
+                        tc_commit<CL>(&empty[stage]);                       // smem slot(s) reusable once these MMAs retire
+                        if (kb == total_kb - 1) tc_commit<CL>(&tfull[as]);  // accumulator complete (both CTAs' epilogues)
                     }
-                    if (CL == 4) tc_commit_mc(&empty[stage], mask_rel);   // release the slot to every CTA that writes into it
-                    else tc_commit(&empty[stage]);                  // smem slot reusable once these MMAs retire
-                    if (kb == total_kb - 1) tc_commit(&tfull[as]);  // accumulator complete
+                    __syncwarp();
+                    if (++stage == C::stages) { stage = 0; phase ^= 1; }
                 }
+                if (total_kb == 0 && elect_one()) tc_commit<CL>(&tfull[as]);
                 __syncwarp();
-                if (++stage == C::stages) { stage = 0; phase ^= 1; }
             }
-            if (total_kb == 0 && elect_one()) tc_commit(&tfull[as]);
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------------------------------ epilogue
@@ -381,10 +396,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const Stager stager{stage_tiles + (warp - 4) * (32 * kStageLd), lane};
         int it = 0;
         for (int walk = walk_begin; walk < walk_end; walk += walk_step, ++it) {
-            const int tile = tile_of(walk);
-            int mn = tile, tap = 0, split = 0;
-            if (WGRAD) { mn = tile % tiles_mn; const int ts = tile / tiles_mn; tap = ts / P.split_k; split = ts % P.split_k; }
-            const int m_blk = mn / P.n_tiles, n_blk = mn % P.n_tiles;
+            int m_blk, n_blk, tap, split;
+            decode(walk, m_blk, n_blk, tap, split);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tfull[as], aphase);
@@ -405,16 +418,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[as]);
+            if (CL == 2 && !leader) mbar_arrive_remote(&tempty[as], 0);     // the leader's MMA warp owns the wait
+            else mbar_arrive(&tempty[as]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (CL == 4) cluster_sync_all();          // no CTA may exit while a peer can still arrive on its barriers
+    if (CL == 2) cluster_sync_all();          // no CTA may exit while its peer can still arrive on its barriers / read its smem
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::tmem_cols) : "memory");
+        if (CL == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::tmem_cols) : "memory");
     }
 }
 
@@ -465,7 +480,7 @@ static int sm_count() {
 
 template <int MODE, int KIND, int BN, bool WGRAD, int CL>
 static int launch_inst(const TcParams& P, int n_tiles_total, cudaStream_t st) {
-    using C = Cfg<MODE, BN>;
+    using C = Cfg<MODE, BN, CL>;
     auto kern = gemm_tc_kernel<MODE, KIND, BN, WGRAD, CL>;
     static bool configured = false;
     static int max_clusters = 0;
@@ -526,6 +541,13 @@ static int launch_kind(const TcParams& P, int n_tiles_total, bool wgrad, cudaStr
 
 struct MapKey { const void* ptr; long long ld, plane; };
 
+// RADMMM_B200_TC_PAIR=0 forces the 1-CTA kernel (debugging / A-B measurements)
+static bool pair_mode_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RADMMM_B200_TC_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 }  // namespace
 
 int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
@@ -559,8 +581,8 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     if (!args.wgrad) {
         P.m_tiles = args.R / BM;
         n_tiles_total = P.m_tiles * P.n_tiles;
-        use_cl = (P.m_tiles % 2 == 0) && (P.n_tiles % 2 == 0);
-        const int a_box = use_cl ? BM / 2 : BM, b_box = use_cl ? BN / 2 : BN;
+        use_cl = (P.m_tiles % 2 == 0) && pair_mode_enabled();
+        const int a_box = BM, b_box = use_cl ? BN / 2 : BN;
         // B maps: segments whose weight matrices sit in one allocation (same ld / plane stride, row-aligned offsets)
         // share a map anchored at the lowest pointer; the segment carries its row offset.
         for (int s = 0; s < args.n_seg; ++s) {
@@ -631,7 +653,7 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         }
         P.split_k = split;
         n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
-        use_cl = (P.m_tiles % 2 == 0) && (P.n_tiles % 2 == 0);
+        use_cl = (P.m_tiles % 2 == 0) && pair_mode_enabled();
         RADMMM_REQUIRE(split == 1 || args.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
         // inner extents stop at the logical widths (rounded to the 64-channel box) so that operands which are column
         // slices of wider matrices never read past their rows
@@ -658,9 +680,9 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
 
     const bool wg = args.wgrad != 0;
     if (use_cl) {
-        if (x3) return launch_kind<MODE_BF16X3, 128, 4>(P, n_tiles_total, wg, stream);
-        if (BN == 256) return launch_kind<MODE_BF16, 256, 4>(P, n_tiles_total, wg, stream);
-        return launch_kind<MODE_BF16, 128, 4>(P, n_tiles_total, wg, stream);
+        if (x3) return launch_kind<MODE_BF16X3, 128, 2>(P, n_tiles_total, wg, stream);
+        if (BN == 256) return launch_kind<MODE_BF16, 256, 2>(P, n_tiles_total, wg, stream);
+        return launch_kind<MODE_BF16, 128, 2>(P, n_tiles_total, wg, stream);
     }
     if (x3) return launch_kind<MODE_BF16X3, 128, 1>(P, n_tiles_total, wg, stream);
     if (BN == 256) return launch_kind<MODE_BF16, 256, 1>(P, n_tiles_total, wg, stream);
