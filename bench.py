@@ -244,6 +244,27 @@ def run_ours(args):
     e2e_step()
     ms_e2e = timed(e2e_step, max(3, args.steps // 2))
 
+    # ---- inference (BASELINE metric "infer frames/s"): RADMMMFlow.infer on the same shapes (text tokens ~ T/6,
+    #      durations summing to each length), sigma = 0.8
+    dec.eval()
+    n_tok = max(4, frames // 6)
+    lens_dev = resident["out_lens"]
+    dur = torch.zeros(batch, n_tok, dtype=torch.long, device=dev)
+    base = lens_dev // n_tok
+    dur += base[:, None]
+    dur[:, 0] += lens_dev - base * n_tok
+    txt_enc = syn.hash_uniform("bench.txt", (batch, 520, n_tok)).to(dev)
+
+    def infer_step():
+        with torch.no_grad():
+            return dec.infer(resident["spk_vecs"], txt_enc, 0.8, dur=dur, f0=resident["f0"],
+                             energy_avg=resident["energy_avg"], out_lens=lens_dev)["mel"]
+
+    for _ in range(3):
+        infer_step()
+    ms_infer = timed(infer_step, max(5, args.steps))
+    dec.train()
+
     # ---- per-kernel roofline of the dominant kernel (dilated k=5 conv forward, tcgen05): events around every launch
     lib = N.lib()
     lib.radmmm_profile_enable(1)
@@ -294,6 +315,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4},
+        "infer": {"value": world * valid_frames / (ms_infer * 1e-3), "unit": UNIT, "ms_per_call": ms_infer,
+                  "note": "RADMMMFlow.infer (length regulation + context LSTM + 8 inverse flow steps), sigma 0.8",
+                  "tensor_roofline_frac": (world * valid_frames / (ms_infer * 1e-3)) * FWD_MFLOP_PER_FRAME * 1e6 / 1e12 / world / pk["bf16_sustained"]},
         "gpu_launches": int(sum(cnt)) * args.steps,
         "roofline": roof,
         "step_tensor_roofline": {"achieved_tflops": step_tflops, "peak_tflops": pk["bf16_sustained"],

@@ -232,6 +232,17 @@ class WN(nn.Module):
             self._prepared[d.mode] = hit
         return hit[1]
 
+    def prepare(self, precision: str) -> None:
+        """Weight-norm + re-layout for ``precision`` if any raw parameter changed since the last call (enqueued on the
+        current stream).  RADMMMFlow.forward runs this for every flow on the side stream while the context LSTM runs."""
+        d = N.FlowDesc()
+        d.mode, d.B, d.C, d.Tp = N.MODES[precision], 1, 2 * self.n_in_channels, 1
+        d.D, d.H, d.L = self.n_context_dim, self.n_channels, self.n_layers
+        params = self.raw_params()
+        with torch.no_grad():
+            self.fill_desc(d, params)
+            self.prepared(d, params)
+
     def forward(self, forward_input, seq_lens=None):
         """(z0 (B,Cin,T), context (B,D,T)) -> (B, 2*Cin, T).  Inference-only when called on its own; training goes
         through AffineTransformationLayer / FlowStep (one fused autograd node)."""

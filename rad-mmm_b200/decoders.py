@@ -137,14 +137,34 @@ class RADMMMFlow(RADMMM):
         for fs in self.flows:
             fs.enable_inverse_cache()
 
+    def _prepare_weights_async(self, device):
+        """Weight preparation of all flows depends only on the parameters, so it is forked onto the side stream and
+        overlaps the (latency-bound) context LSTM; returns the event the flow steps must wait for."""
+        side_handle = common._side_stream(device)
+        if not side_handle:
+            return None
+        side = common._side_streams[device.index]
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for fs in self.flows:
+                tfn = fs.coupling_tfn
+                if hasattr(tfn, "affine_param_predictor"):
+                    tfn.affine_param_predictor.prepare(tfn.precision)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
+
     def forward(self, mel, spk_vecs, context, out_lens, f0=None, energy_avg=None, accent_vecs=None):
         lengths = out_lens.lengths if hasattr(out_lens, "lengths") else out_lens
+        prep_done = self._prepare_weights_async(mel.device) if mel.is_cuda else None
         context_w_spkvec = self.preprocess_context(context, spk_vecs, lengths, f0, energy_avg, accent_vecs=accent_vecs)
         if self.n_group_size > 1:
             mel = squeeze_time(mel, self.n_group_size)
         lens_g = torch.div(lengths, self.n_group_size, rounding_mode="floor")
         seq = _Lens(lens_g)
         z_out, log_s_list, log_det_W_list = [], [], []
+        if prep_done is not None:
+            torch.cuda.current_stream(mel.device).wait_event(prep_done)
         for i, flow_step in enumerate(self.flows):
             if i in self.exit_steps:
                 z_out.append(mel[:, :self.n_early_size])
