@@ -40,11 +40,12 @@ struct LstmParams {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Per-direction arrive/spin barrier.  The CTA's stores are ordered before thread 0's release-reduction by the bar.sync
+// (cumulativity), so no per-thread MEMBAR is needed; consumers read the exchanged data after the acquire + bar.sync.
 __device__ __forceinline__ void dir_barrier(unsigned int* counter, unsigned int target) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         long long spins = 0;
         while (true) {
             unsigned int v;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
     extern __shared__ float sm[];
     const int H = p.H, Bp = p.Bp, H4 = 4 * p.H;
     float* Wb = sm;                                          // [U][4H]   Wb[w][rho] = Whh[rho][u0 + w]
-    float* dgs = sm + (size_t)U * H4;                        // [BT][4H]
+    float* dgs = sm + (size_t)U * H4;                        // [4H][BT]  (sequence fastest: two LDS.128 per gate row)
     const int dir = blockIdx.x / p.G, slice = blockIdx.x % p.G, u0 = slice * U;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const float* Whh = p.whh[dir];
@@ -190,7 +191,29 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dh_rec[i] = 0.0f; dc_next[i] = 0.0f; }
     const int unit = u0 + w;
-    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H4;        // [2 parity][Bp][4H]
+    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H4;        // [2 parity][4H][Bp]
+
+    // saved values of (unit, sequence lane&7) for one step; prefetched one step ahead when the batch is a single tile
+    struct Saved { float gi, gf, gg, go, c, c_prev, dout; };
+    auto load_saved = [&](int s, int bb, Saved& v) -> bool {
+        int len = 0;
+        if (bb < p.B) len = min(p.lens[bb], p.Tp);
+        const bool active = bb < p.B && s >= 0 && s < len;
+        if (active) {
+            const int t = dir ? len - 1 - s : s;
+            const long long r = (long long)bb * p.pitch + t;
+            const float* gp = p.gates + r * 8 * H + (size_t)dir * 4 * H + unit;
+            v.gi = gp[0]; v.gf = gp[H]; v.gg = gp[2 * H]; v.go = gp[3 * H];
+            v.c = p.cstate[r * 2 * H + (size_t)dir * H + unit];
+            const long long rp = dir ? r + 1 : r - 1;
+            v.c_prev = (s > 0) ? p.cstate[rp * 2 * H + (size_t)dir * H + unit] : 0.0f;
+            v.dout = p.dout[((long long)bb * p.Tp + t) * 2 * H + (size_t)dir * H + unit];
+        }
+        return active;
+    };
+    Saved pre = {};
+    bool pre_active = false;
+    if (n_tiles == 1 && lane < 8) pre_active = load_saved(tmax - 1, lane & 7, pre);
 
     for (int s = tmax - 1; s >= 0; --s) {
         // phase 1: gate gradients of this CTA's units
@@ -200,17 +223,14 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
             if (lane < 8 && bb < Bp) {
                 int len = 0;
                 if (bb < p.B) len = min(p.lens[bb], p.Tp);
-                const bool active = bb < p.B && s < len;
+                Saved v = pre;
+                const bool active = (n_tiles == 1) ? pre_active : load_saved(s, bb, v);
                 float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
                 if (active) {
                     const int t = dir ? len - 1 - s : s;
                     const long long r = (long long)bb * p.pitch + t;
-                    const float* gp = p.gates + r * 8 * H + (size_t)dir * 4 * H + unit;
-                    const float gi = gp[0], gf = gp[H], gg = gp[2 * H], go = gp[3 * H];
-                    const float c = p.cstate[r * 2 * H + (size_t)dir * H + unit];
-                    const long long rp = dir ? r + 1 : r - 1;
-                    const float c_prev = (s > 0) ? p.cstate[rp * 2 * H + (size_t)dir * H + unit] : 0.0f;
-                    const float dh = p.dout[((long long)bb * p.Tp + t) * 2 * H + (size_t)dir * H + unit] + dh_rec[bt];
+                    const float gi = v.gi, gf = v.gf, gg = v.gg, go = v.go, c = v.c, c_prev = v.c_prev;
+                    const float dh = v.dout + dh_rec[bt];
                     const float tc = tanhf(c);
                     const float dc = dh * go * (1.0f - tc * tc) + dc_next[bt];
                     d_o = dh * tc * go * (1.0f - go);
@@ -223,26 +243,32 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
                 } else {
                     dc_next[bt] = 0.0f;
                 }
-                float* x = xbuf + ((size_t)(s & 1) * Bp + bb) * H4 + unit;
-                x[0] = d_i; x[H] = d_f; x[2 * H] = d_g; x[3 * H] = d_o;
+                float* x = xbuf + ((size_t)(s & 1) * H4 + unit) * Bp + bb;          // lanes = consecutive sequences: 32 B segments
+                x[0] = d_i; x[(size_t)H * Bp] = d_f; x[(size_t)2 * H * Bp] = d_g; x[(size_t)3 * H * Bp] = d_o;
             }
         }
         if (s == 0) break;
+        if (n_tiles == 1 && lane < 8) pre_active = load_saved(s - 1, lane & 7, pre);     // in flight across the barrier
         dir_barrier(p.counters + dir, (unsigned int)p.G * (tmax - s));
         // phase 2: dh_rec[b][unit] = sum_rho Whh[rho][unit] * dG[b][rho]
 #pragma unroll 1
         for (int bt = 0; bt < n_tiles; ++bt) {
-            const float4* src = reinterpret_cast<const float4*>(xbuf + ((size_t)(s & 1) * Bp + (size_t)bt * BT) * H4);
+            const float* src = xbuf + (size_t)(s & 1) * H4 * Bp + (size_t)bt * BT;
             __syncthreads();
-            for (int i = tid; i < BT * H4 / 4; i += NT) reinterpret_cast<float4*>(dgs)[i] = __ldcg(src + i);
+            for (int i = tid; i < H4 * 2; i += NT)            // (rho, half): 4 sequences = one float4
+                reinterpret_cast<float4*>(dgs)[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(i >> 1) * Bp + (i & 1) * 4));
             __syncthreads();
             float acc[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
             for (int rho = lane; rho < H4; rho += 32) {
                 const float wv = Wb[w * H4 + rho];
-#pragma unroll
-                for (int b = 0; b < BT; ++b) acc[b] = fmaf(wv, dgs[b * H4 + rho], acc[b]);
+                const float4 g0 = *reinterpret_cast<const float4*>(dgs + rho * BT);
+                const float4 g1 = *reinterpret_cast<const float4*>(dgs + rho * BT + 4);
+                acc[0] = fmaf(wv, g0.x, acc[0]); acc[1] = fmaf(wv, g0.y, acc[1]);
+                acc[2] = fmaf(wv, g0.z, acc[2]); acc[3] = fmaf(wv, g0.w, acc[3]);
+                acc[4] = fmaf(wv, g1.x, acc[4]); acc[5] = fmaf(wv, g1.y, acc[5]);
+                acc[6] = fmaf(wv, g1.z, acc[6]); acc[7] = fmaf(wv, g1.w, acc[7]);
             }
             const float v = reduce8(acc, lane);              // lane l holds sequence l & 7
             dh_rec[bt] = v;
