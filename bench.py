@@ -197,6 +197,9 @@ def run_ours(args):
     resident = {k: v.to(dev) for k, v in host.items()}
 
     def train_step(bt):
+        # no optimizer in the timed loop: mark the parameters as changed so that every step re-runs the weight norm +
+        # re-layout of all 219 M parameters, as it must after a real optimizer step (nothing is served from a cache)
+        dec.invalidate_weight_cache()
         for p in dec.parameters():
             p.grad = None
         out = dec(bt["mel"], bt["spk_vecs"], bt["context"], SequenceLength(bt["out_lens"], frames), f0=bt["f0"],
@@ -212,12 +215,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    host_ms = {}
+
+    def timed(fn, steps, tag=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        if tag:
+            host_ms[tag] = (time.perf_counter() - t0) * 1e3 / steps      # host enqueue time per step (diagnostic)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / steps
@@ -227,22 +235,58 @@ def run_ours(args):
             ms = float(t)
         return ms
 
-    # ---- value: inputs resident in HBM
-    for _ in range(args.warmup):
-        train_step(resident)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms = timed(lambda: train_step(resident), args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- e2e: host buffers in, loss out, through the public module API
-    def e2e_step():
+    # ---- eager module path (what a Lightning loop calls): kept as a secondary number -- at this shape the host needs
+    #      about as long to enqueue the ~1000 launches of a step as the GPU needs to run them
+    def e2e_eager_step():
         bt = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         return float(train_step(bt).detach().cpu())
 
+    for _ in range(args.warmup):
+        train_step(resident)
+    eager_steps = max(3, args.steps // 2)
+    ms_eager = timed(lambda: train_step(resident), eager_steps, "train_eager")
+    e2e_eager_step()
+    ms_e2e_eager = timed(e2e_eager_step, max(3, args.steps // 4))
+
+    # ---- headline path: the same step captured once into a CUDA graph (radmmm_b200.graphs.GraphedTrainStep) and
+    #      replayed; inputs are copied into the graph's static buffers every step
+    gstep, graph_error = None, None
+    if not args.eager:
+        try:
+            from radmmm_b200.graphs import GraphedTrainStep
+            gstep = GraphedTrainStep(dec, resident, after_backward=(reducer.finish if reducer is not None else None))
+        except Exception as exc:                                   # report, then fall back to the eager numbers
+            graph_error = f"{type(exc).__name__}: {exc}"[:300]
+            gstep = None
+    graph_ok = torch.tensor([1 if gstep is not None else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(graph_ok, op=dist.ReduceOp.MIN)
+    if int(graph_ok) == 0:
+        gstep = None
+    run_step = (lambda: gstep(resident)) if gstep is not None else (lambda: train_step(resident))
+
+    # ---- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        run_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = N.lib().radmmm_launch_count()
+    ms = timed(run_step, args.steps, 'train')
+    launches = N.lib().radmmm_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers in, loss out, through the public API (GraphedTrainStep.__call__ / the module)
+    def e2e_step():
+        if gstep is not None:
+            return float(gstep(host).cpu())
+        return e2e_eager_step()
+
     e2e_step()
     ms_e2e = timed(e2e_step, max(3, args.steps // 2))
+    if gstep is not None:
+        for p in dec.parameters():        # leave graph mode: the remaining (eager) sections own their gradients again
+            p.grad = None
 
     # ---- inference (BASELINE metric "infer frames/s"): RADMMMFlow.infer on the same shapes (text tokens ~ T/6,
     #      durations summing to each length), sigma = 0.8
@@ -267,6 +311,9 @@ def run_ours(args):
 
     # ---- per-kernel roofline of the dominant kernel (dilated k=5 conv forward, tcgen05): events around every launch
     lib = N.lib()
+    l0 = lib.radmmm_launch_count()
+    train_step(resident)
+    launches_per_eager_step = lib.radmmm_launch_count() - l0
     lib.radmmm_profile_enable(1)
     train_step(resident)
     n_tags = 32
@@ -318,7 +365,15 @@ def run_ours(args):
         "infer": {"value": world * valid_frames / (ms_infer * 1e-3), "unit": UNIT, "ms_per_call": ms_infer,
                   "note": "RADMMMFlow.infer (length regulation + context LSTM + 8 inverse flow steps), sigma 0.8",
                   "tensor_roofline_frac": (world * valid_frames / (ms_infer * 1e-3)) * FWD_MFLOP_PER_FRAME * 1e6 / 1e12 / world / pk["bf16_sustained"]},
-        "gpu_launches": int(sum(cnt)) * args.steps,
+        "gpu_launches": int(launches) if gstep is None else int(launches_per_eager_step) * args.steps,
+        "graph": {"captured": gstep is not None, "error": graph_error,
+                  "note": "one whole train step (weight prep, LSTM, 8 flows, NLL, backward) replayed as a CUDA graph; "
+                          "gpu_launches counts the kernels inside the graph x steps"},
+        "eager": {"ms_per_step": ms_eager, "e2e_ms_per_step": ms_e2e_eager,
+                  "value": world * valid_frames / (ms_eager * 1e-3), "e2e_value": world * valid_frames / (ms_e2e_eager * 1e-3),
+                  "host_enqueue_ms_per_step": host_ms.get("train_eager"),
+                  "note": "RADMMMFlow.forward + flow_nll + backward called eagerly (the Lightning-loop path)"},
+        "host_enqueue_ms_per_step": host_ms.get("train"),
         "roofline": roof,
         "step_tensor_roofline": {"achieved_tflops": step_tflops, "peak_tflops": pk["bf16_sustained"],
                                  "frac": step_tflops / pk["bf16_sustained"],
@@ -344,6 +399,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--ref-frames", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="skip the CUDA-graph capture; time the eager module path only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

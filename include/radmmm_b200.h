@@ -46,6 +46,9 @@ const char* radmmm_last_error(void);
  * weight-grad GEMM), the launch count, summed device milliseconds and summed executed FLOPs.  Not thread-safe. */
 void radmmm_profile_enable(int on);
 int radmmm_profile_collect(int max_tags, int* counts, double* ms, double* flops);
+/* Number of kernels this library has launched in the process so far (every launch site counts itself; memsets and
+ * library calls are not included).  bench.py reports the difference over its timed region as "gpu_launches". */
+long long radmmm_launch_count(void);
 /* sizeof(radmmm_flow_desc) / sizeof(radmmm_flow_grads) as compiled -- lets a binding verify its struct layout */
 size_t radmmm_sizeof_flow_desc(void);
 size_t radmmm_sizeof_flow_grads(void);

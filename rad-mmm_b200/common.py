@@ -50,6 +50,9 @@ def _lens_of(seq_lens, batch: int, tp: int, device) -> torch.Tensor:
     """int32 device lengths from a SequenceLength (ours or the reference's), a tensor, or None (= full length)."""
     if seq_lens is None:
         return torch.full((batch,), tp, dtype=torch.int32, device=device)
+    cached = getattr(seq_lens, "lens_i32", None)          # decoders._Lens: converted once per step, so every flow step
+    if cached is not None and cached.device == device:    # sees the SAME tensor (context-rows cache key, no re-casts)
+        return cached
     lengths = seq_lens.lengths if hasattr(seq_lens, "lengths") else seq_lens
     return lengths.to(device=device, dtype=torch.int32).contiguous()
 
@@ -77,6 +80,9 @@ class _ContextRows:
         lib = N.lib()
         b, tp, d = ctx_btd.shape
         self.key = (ctx_btd.data_ptr(), ctx_btd._version, tuple(ctx_btd.shape), mode, lens.data_ptr(), lens._version)
+        # the key is only meaningful while the source tensors are alive (a freed block can come back at the same address
+        # with version 0): the cache entry keeps them
+        self.src = (ctx_btd.detach(), lens)        # detached: keeps the storage, not the autograd graph
         self.rows = torch.empty(lib.radmmm_context_rows_bytes(mode, b, tp, d), dtype=torch.uint8, device=ctx_btd.device)
         N.check(lib.radmmm_context_rows(mode, N.fptr(ctx_btd), N.ptr(lens), b, tp, d, N.ptr(self.rows), N.stream()))
 
@@ -232,6 +238,10 @@ class WN(nn.Module):
             self._prepared[d.mode] = hit
         return hit[1]
 
+    def invalidate_prepared(self) -> None:
+        """Forget the prepared weights (as after an optimizer step that bypassed the tensors' version counters)."""
+        self._prepared = {m: (None, buf) for m, (_, buf) in self._prepared.items()}
+
     def prepare(self, precision: str) -> None:
         """Weight-norm + re-layout for ``precision`` if any raw parameter changed since the last call (enqueued on the
         current stream).  RADMMMFlow.forward runs this for every flow on the side stream while the context LSTM runs."""
@@ -292,6 +302,7 @@ class FlowStepFunction(torch.autograd.Function):
         ws = torch.empty(lib.radmmm_flow_workspace_bytes(mode, int(training), batch, tp, chans, d.D, d.H, d.L),
                          dtype=torch.uint8, device=z.device)
         d.workspace = N.ptr(ws)
+        d.side_stream = _side_stream(z.device) or None
         Wc = W.contiguous() if W is not None else None
         d.W, d.mean = N.fptr(Wc), N.fptr(mean)
         z_mid = torch.empty_like(z) if W is not None else z
@@ -379,6 +390,7 @@ def _flow_apply(wn: WN, W, W_inv, mean, z, context, seq_lens, scaling_fn: str, p
             ws = torch.empty(lib.radmmm_flow_workspace_bytes(mode, 0, batch, tp, chans, d.D, d.H, d.L),
                              dtype=torch.uint8, device=z.device)
             d.workspace = N.ptr(ws)
+            d.side_stream = _side_stream(z.device) or None
             if W_inv is None:
                 W_inv = torch.eye(chans, device=z.device)
             W_inv = W_inv.contiguous()

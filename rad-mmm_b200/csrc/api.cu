@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+static long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
+
 // ---- optional per-launch profiler (bench.py): CUDA events around every contraction launch, on the launching stream.
 // Off by default; when off the launch path does not touch it.
 struct ProfSlot { cudaEvent_t e0, e1; int tag; double flops; };
@@ -81,6 +84,7 @@ using namespace radmmm;
 extern "C" {
 
 int radmmm_abi_version(void) { return RADMMM_ABI_VERSION; }
+long long radmmm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 void radmmm_profile_enable(int on) { g_prof_on = on != 0; if (on) g_prof_n = 0; }
 int radmmm_profile_collect(int max_tags, int* counts, double* ms, double* flops) {

@@ -13,6 +13,7 @@ namespace radmmm {
 // ---------------------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 const char* last_error();
+void count_launch();          // bumps the process-wide kernel-launch counter (radmmm_launch_count)
 
 #define RADMMM_OK 0
 #define RADMMM_ERR_ARG -1
@@ -35,6 +36,7 @@ const char* last_error();
 
 #define RADMMM_LAUNCH_CHECK()                                                                             \
     do {                                                                                                  \
+        ::radmmm::count_launch();                                                                         \
         cudaError_t _e = cudaGetLastError();                                                              \
         if (_e != cudaSuccess) {                                                                          \
             ::radmmm::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

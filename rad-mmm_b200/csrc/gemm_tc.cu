@@ -517,6 +517,7 @@ static int launch_inst(const TcParams& P, int n_tiles_total, cudaStream_t st) {
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     RADMMM_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    count_launch();
     return RADMMM_OK;
 }
 

@@ -40,6 +40,28 @@ struct LstmParams {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// L2 -> shared copy of n4 float4 with up to BATCH loads per thread in flight (the exchange buffers were just written by
+// the other CTAs, so every load is an L2 round trip: issuing them back to back instead of load/store/load/store cuts the
+// reload from ~n4/NT round trips to ~n4/(NT*BATCH); measured 35 % of the forward step before).  `src_index(i)` maps
+// the destination float4 index to the source float4 index.
+template <int BATCH, typename F>
+__device__ __forceinline__ void copy_f4_batched(float4* __restrict__ dst, const float4* __restrict__ src, int n4, int tid,
+                                                F src_index) {
+    for (int base = 0; base < n4; base += BATCH * 256) {
+        float4 t[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int i = base + j * 256 + tid;
+            if (i < n4) t[j] = __ldcg(src + src_index(i));
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int i = base + j * 256 + tid;
+            if (i < n4) dst[i] = t[j];
+        }
+    }
+}
+
 // Per-direction arrive/spin barrier.  The CTA's stores are ordered before thread 0's release-reduction by the bar.sync
 // (cumulativity), so no per-thread MEMBAR is needed; consumers read the exchanged data after the acquire + bar.sync.
 __device__ __forceinline__ void dir_barrier(unsigned int* counter, unsigned int target) {
@@ -92,7 +114,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
     extern __shared__ float sm[];
     const int H = p.H, Bp = p.Bp;
     float4* Wt = reinterpret_cast<float4*>(sm);             // [U][H] float4 = the 4 gates of (unit w, input k)
-    float* hs = sm + (size_t)U * H * 4;                     // [Bp][H]
+    float4* hs4 = reinterpret_cast<float4*>(sm + (size_t)U * H * 4);     // [Bp/4][H] float4 = 4 sequences of input k
     const int dir = blockIdx.x / p.G, slice = blockIdx.x % p.G, u0 = slice * U;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const float* Whh = p.whh[dir];
@@ -101,7 +123,8 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
         Wt[i] = make_float4(Whh[(size_t)(0 * H + u0 + uu) * H + k], Whh[(size_t)(1 * H + u0 + uu) * H + k],
                             Whh[(size_t)(2 * H + u0 + uu) * H + k], Whh[(size_t)(3 * H + u0 + uu) * H + k]);
     }
-    for (int i = tid; i < Bp * H; i += NT) hs[i] = 0.0f;
+    const int n4 = Bp / 4 * H;
+    for (int i = tid; i < n4; i += NT) hs4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     int tmax = 0;
     for (int b = 0; b < p.B; ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
     __syncthreads();
@@ -111,7 +134,16 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) c_state[i] = 0.0f;
     const int unit = u0 + w;
-    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H;        // [2 parity][Bp][H]
+    float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H;        // [2 parity][Bp/4][H][4]  (same layout as hs4)
+    struct Kept { float gi, gf, gg, go, c, h; long long r, o; bool valid; };
+    Kept keep = {};
+    auto store_kept = [&](const Kept& k) {
+        if (!k.valid) return;
+        float* gp = p.gates + k.r * 8 * H + (size_t)dir * 4 * H + unit;
+        gp[0] = k.gi; gp[H] = k.gf; gp[2 * H] = k.gg; gp[3 * H] = k.go;
+        p.cstate[k.r * 2 * H + (size_t)dir * H + unit] = k.c;
+        p.out[k.o * 2 * H + (size_t)dir * H + unit] = k.h;
+    };
 
     for (int s = 0; s < tmax; ++s) {
 #pragma unroll 1
@@ -130,16 +162,19 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
             float acc[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
-            const float* hb = hs + (size_t)bt * BT * H;
+            const float4* ha = hs4 + (size_t)(2 * bt) * H;      // sequences bt*8 .. +3
+            const float4* hb = ha + H;                           // sequences bt*8+4 .. +7
+#pragma unroll 2
             for (int k = lane; k < H; k += 32) {
                 const float4 w4 = Wt[w * H + k];
+                const float4 h0 = ha[k], h1 = hb[k];
+                const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
                 for (int b = 0; b < BT; ++b) {
-                    const float hv = hb[b * H + k];
-                    acc[0 * 8 + b] = fmaf(w4.x, hv, acc[0 * 8 + b]);
-                    acc[1 * 8 + b] = fmaf(w4.y, hv, acc[1 * 8 + b]);
-                    acc[2 * 8 + b] = fmaf(w4.z, hv, acc[2 * 8 + b]);
-                    acc[3 * 8 + b] = fmaf(w4.w, hv, acc[3 * 8 + b]);
+                    acc[0 * 8 + b] = fmaf(w4.x, hv[b], acc[0 * 8 + b]);
+                    acc[1 * 8 + b] = fmaf(w4.y, hv[b], acc[1 * 8 + b]);
+                    acc[2 * 8 + b] = fmaf(w4.z, hv[b], acc[2 * 8 + b]);
+                    acc[3 * 8 + b] = fmaf(w4.w, hv[b], acc[3 * 8 + b]);
                 }
             }
             const float mine = reduce32(acc, lane);         // lane v: gate v/8, sequence v%8
@@ -155,18 +190,25 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
                     const float c = gf * c_state[bt] + gi * gg;
                     h = go * tanhf(c);
                     c_state[bt] = c;
-                    float* gp = p.gates + r * 8 * H + (size_t)dir * 4 * H + unit;
-                    gp[0] = gi; gp[H] = gf; gp[2 * H] = gg; gp[3 * H] = go;
-                    p.cstate[r * 2 * H + (size_t)dir * H + unit] = c;
-                    p.out[((long long)bb * p.Tp + t) * 2 * H + (size_t)dir * H + unit] = h;
+                    // publish h; the copies kept for the backward pass (6 stores to HBM-homed lines) are deferred past the
+                    // barrier so that the release fence only has this one store to wait for
+                    xbuf[(((size_t)(s & 1) * (Bp / 4) + (bb >> 2)) * H + unit) * 4 + (bb & 3)] = h;
+                    if (bt == n_tiles - 1) {
+                        keep = Kept{gi, gf, gg, go, c, h, r, ((long long)bb * p.Tp + t), true};
+                    } else {
+                        store_kept(Kept{gi, gf, gg, go, c, h, r, ((long long)bb * p.Tp + t), true});
+                    }
+                } else {
+                    xbuf[(((size_t)(s & 1) * (Bp / 4) + (bb >> 2)) * H + unit) * 4 + (bb & 3)] = h;
                 }
-                xbuf[((size_t)(s & 1) * Bp + bb) * H + unit] = h;
             }
         }
-        if (s + 1 == tmax) break;
+        if (s + 1 == tmax) { store_kept(keep); break; }
         dir_barrier(p.counters + dir, (unsigned int)p.G * (s + 1));
         const float4* src = reinterpret_cast<const float4*>(xbuf + (size_t)(s & 1) * Bp * H);
-        for (int i = tid; i < Bp * H / 4; i += NT) reinterpret_cast<float4*>(hs)[i] = __ldcg(src + i);
+        copy_f4_batched<5>(hs4, src, n4, tid, [](int i) { return i; });
+        store_kept(keep);
+        keep.valid = false;
         __syncthreads();
     }
 }
@@ -174,13 +216,14 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
 __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
     extern __shared__ float sm[];
     const int H = p.H, Bp = p.Bp, H4 = 4 * p.H;
-    float* Wb = sm;                                          // [U][4H]   Wb[w][rho] = Whh[rho][u0 + w]
-    float* dgs = sm + (size_t)U * H4;                        // [4H][BT]  (sequence fastest: two LDS.128 per gate row)
+    float* Wb = sm;                                          // [4H][U]   Wb[rho][uu] = Whh[rho][u0 + uu]
+    float* dgs = sm + (size_t)U * H4;                        // [4H][BT]  gate gradients of one sequence tile
+    float* red = dgs + (size_t)BT * H4;                      // [8 warps][U * BT] cross-warp partial sums
     const int dir = blockIdx.x / p.G, slice = blockIdx.x % p.G, u0 = slice * U;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const float* Whh = p.whh[dir];
     for (int i = tid; i < U * H4; i += NT) {
-        const int uu = i / H4, rho = i % H4;
+        const int rho = i / U, uu = i % U;
         Wb[i] = Whh[(size_t)rho * H + u0 + uu];
     }
     int tmax = 0;
@@ -192,6 +235,8 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
     for (int i = 0; i < 8; ++i) { dh_rec[i] = 0.0f; dc_next[i] = 0.0f; }
     const int unit = u0 + w;
     float* xbuf = p.xchg + (size_t)dir * 2 * Bp * H4;        // [2 parity][4H][Bp]
+    // phase-2 thread tile: 2 units x 4 sequences, every 4th gate row
+    const int ug = lane >> 3, bg = (lane >> 2) & 1, rq = lane & 3;
 
     // saved values of (unit, sequence lane&7) for one step; prefetched one step ahead when the batch is a single tile
     struct Saved { float gi, gf, gg, go, c, c_prev, dout; };
@@ -211,6 +256,14 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
         }
         return active;
     };
+    // the copy of the gate gradients kept for the weight-gradient contractions is stored after the barrier (see forward)
+    struct KeptG { float d_i, d_f, d_g, d_o; long long r; bool valid; };
+    KeptG keep = {};
+    auto store_kept = [&](const KeptG& k) {
+        if (!k.valid) return;
+        float* dg = p.dgates + k.r * 8 * H + (size_t)dir * 4 * H + unit;
+        dg[0] = k.d_i; dg[H] = k.d_f; dg[2 * H] = k.d_g; dg[3 * H] = k.d_o;
+    };
     Saved pre = {};
     bool pre_active = false;
     if (n_tiles == 1 && lane < 8) pre_active = load_saved(tmax - 1, lane & 7, pre);
@@ -226,9 +279,10 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
                 Saved v = pre;
                 const bool active = (n_tiles == 1) ? pre_active : load_saved(s, bb, v);
                 float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
+                long long r = 0;
                 if (active) {
                     const int t = dir ? len - 1 - s : s;
-                    const long long r = (long long)bb * p.pitch + t;
+                    r = (long long)bb * p.pitch + t;
                     const float gi = v.gi, gf = v.gf, gg = v.gg, go = v.go, c = v.c, c_prev = v.c_prev;
                     const float dh = v.dout + dh_rec[bt];
                     const float tc = tanhf(c);
@@ -238,40 +292,63 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
                     d_g = dc * gi * (1.0f - gg * gg);
                     d_f = dc * c_prev * gf * (1.0f - gf);
                     dc_next[bt] = dc * gf;
-                    float* dg = p.dgates + r * 8 * H + (size_t)dir * 4 * H + unit;
-                    dg[0] = d_i; dg[H] = d_f; dg[2 * H] = d_g; dg[3 * H] = d_o;
                 } else {
                     dc_next[bt] = 0.0f;
                 }
+                // publish first (the other CTAs wait for it), then the copy kept for the weight-gradient contractions
                 float* x = xbuf + ((size_t)(s & 1) * H4 + unit) * Bp + bb;          // lanes = consecutive sequences: 32 B segments
                 x[0] = d_i; x[(size_t)H * Bp] = d_f; x[(size_t)2 * H * Bp] = d_g; x[(size_t)3 * H * Bp] = d_o;
+                if (active) {
+                    if (bt == n_tiles - 1) keep = KeptG{d_i, d_f, d_g, d_o, r, true};
+                    else store_kept(KeptG{d_i, d_f, d_g, d_o, r, true});
+                }
             }
         }
-        if (s == 0) break;
+        if (s == 0) { store_kept(keep); break; }
         if (n_tiles == 1 && lane < 8) pre_active = load_saved(s - 1, lane & 7, pre);     // in flight across the barrier
         dir_barrier(p.counters + dir, (unsigned int)p.G * (tmax - s));
-        // phase 2: dh_rec[b][unit] = sum_rho Whh[rho][unit] * dG[b][rho]
+        store_kept(keep);
+        keep.valid = false;
+        // phase 2: dh_rec[b][unit] = sum_rho Whh[rho][unit] * dG[b][rho].  Warp w takes the gate rows rho = 4*(w + 8*i) + rq;
+        // a lane accumulates 2 units x 4 sequences (one LDS.64 of weights + one LDS.128 of gate gradients per 8 FMAs, both
+        // conflict-free), the 4 rq lanes are summed with two shuffles and the 8 warps through shared memory.
 #pragma unroll 1
         for (int bt = 0; bt < n_tiles; ++bt) {
-            const float* src = xbuf + (size_t)(s & 1) * H4 * Bp + (size_t)bt * BT;
+            const float4* src = reinterpret_cast<const float4*>(xbuf + (size_t)(s & 1) * H4 * Bp + (size_t)bt * BT);
             __syncthreads();
-            for (int i = tid; i < H4 * 2; i += NT)            // (rho, half): 4 sequences = one float4
-                reinterpret_cast<float4*>(dgs)[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(i >> 1) * Bp + (i & 1) * 4));
+            const int q = Bp / 4;
+            copy_f4_batched<6>(reinterpret_cast<float4*>(dgs), src, H4 * 2, tid,
+                               [q](int i) { return (i >> 1) * q + (i & 1); });      // (rho, half): 4 sequences = one float4
             __syncthreads();
-            float acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-            for (int rho = lane; rho < H4; rho += 32) {
-                const float wv = Wb[w * H4 + rho];
-                const float4 g0 = *reinterpret_cast<const float4*>(dgs + rho * BT);
-                const float4 g1 = *reinterpret_cast<const float4*>(dgs + rho * BT + 4);
-                acc[0] = fmaf(wv, g0.x, acc[0]); acc[1] = fmaf(wv, g0.y, acc[1]);
-                acc[2] = fmaf(wv, g0.z, acc[2]); acc[3] = fmaf(wv, g0.w, acc[3]);
-                acc[4] = fmaf(wv, g1.x, acc[4]); acc[5] = fmaf(wv, g1.y, acc[5]);
-                acc[6] = fmaf(wv, g1.z, acc[6]); acc[7] = fmaf(wv, g1.w, acc[7]);
+            float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 6
+            for (int rho = 4 * w + rq; rho < H4; rho += 32) {
+                const float2 wv = *reinterpret_cast<const float2*>(Wb + rho * U + 2 * ug);
+                const float4 g = *reinterpret_cast<const float4*>(dgs + rho * BT + 4 * bg);
+                a0[0] = fmaf(wv.x, g.x, a0[0]); a0[1] = fmaf(wv.x, g.y, a0[1]);
+                a0[2] = fmaf(wv.x, g.z, a0[2]); a0[3] = fmaf(wv.x, g.w, a0[3]);
+                a1[0] = fmaf(wv.y, g.x, a1[0]); a1[1] = fmaf(wv.y, g.y, a1[1]);
+                a1[2] = fmaf(wv.y, g.z, a1[2]); a1[3] = fmaf(wv.y, g.w, a1[3]);
             }
-            const float v = reduce8(acc, lane);              // lane l holds sequence l & 7
-            dh_rec[bt] = v;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], 1);
+                a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], 1);
+                a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], 2);
+                a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], 2);
+            }
+            if (rq == 0) {
+                float* o = red + w * (U * BT) + (2 * ug) * BT + 4 * bg;
+                *reinterpret_cast<float4*>(o) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+                *reinterpret_cast<float4*>(o + BT) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+            }
+            __syncthreads();
+            if (lane < 8) {
+                float v = 0.0f;
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww) v += red[ww * (U * BT) + w * BT + lane];
+                dh_rec[bt] = v;
+            }
         }
     }
 }
@@ -305,10 +382,15 @@ int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, con
     p.xproj = xproj; p.whh[0] = whh_f; p.whh[1] = whh_r; p.out = out; p.gates = gates; p.cstate = cstate;
     const size_t smem = sizeof(float) * ((size_t)U * H * 4 + (size_t)p.Bp * H);
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d, B=%d)", smem, H, B);
-    RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set_fwd = 0;
+    if (smem > smem_set_fwd) {
+        RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set_fwd = smem;
+    }
     RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
     void* args[] = {&p};
     RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
+    count_launch();
     return RADMMM_OK;
 }
 
@@ -319,12 +401,17 @@ int lstm_backward(const float* dout, const float* gates, const float* cstate, co
     RADMMM_TRY(lstm_common(p, lens, B, Tp, H, workspace));
     p.dout = dout; p.gates = const_cast<float*>(gates); p.cstate = const_cast<float*>(cstate);
     p.whh[0] = whh_f; p.whh[1] = whh_r; p.dgates = dgates;
-    const size_t smem = sizeof(float) * ((size_t)U * 4 * H + (size_t)BT * 4 * H);
+    const size_t smem = sizeof(float) * ((size_t)U * 4 * H + (size_t)BT * 4 * H + 8 * U * BT);
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d)", smem, H);
-    RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set_bwd = 0;
+    if (smem > smem_set_bwd) {
+        RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set_bwd = smem;
+    }
     RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
     void* args[] = {&p};
     RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
+    count_launch();
     return RADMMM_OK;
 }
 

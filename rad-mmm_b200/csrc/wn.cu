@@ -193,11 +193,22 @@ static void add_seg(GemmArgs& a, const ActMat& act, const ActMat& w, int K, int 
     s.a = act; s.w = w; s.K = K; s.shift = shift;
 }
 
-// WN forward on rows: fills ws (H*, SIG*, OUT*) and writes params (B, C, Tp)
+// events for the fork/join with the side stream (created once per host thread; timing disabled)
+static cudaEvent_t side_event(int i) {
+    static thread_local cudaEvent_t ev[32] = {};
+    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    return ev[i];
+}
+
+// WN forward on rows: fills ws (H*, S*) and writes params (B, C, Tp).
+// The dilated convs form the dependent chain h_0 -> h_1 -> ... on `st`; res-skip conv i only feeds the `end` GEMM, so it
+// runs on the side stream (when the descriptor carries one) and fills the SMs the chain's 104-tile launches leave idle.
 static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepared& p, const Workspace& w,
                            const float* z_mid, float* params, cudaStream_t st) {
     const RowGeom g = geom_of(d, f->lens);
     ActMat ctx; ctx.ptr = const_cast<void*>(f->ctx_rows); ctx.ld = d.Dp; ctx.plane_stride = (long long)d.R * d.Dp;
+    cudaStream_t sd = f->side_stream ? reinterpret_cast<cudaStream_t>(f->side_stream) : st;
+    const bool forked = sd != st;
     // z0 = z_mid[:, :Ch] -> rows
     RADMMM_TRY(rows_from_cf(d.mode, z_mid, (long long)d.C * d.Tp, d.Ch, g, w.Z0, d.Kz, 1, st));
     GemmArgs a;
@@ -210,6 +221,8 @@ static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepa
     RADMMM_TRY(launch_gemm(a, d.mode, st));
     for (int i = 0; i < d.L; ++i) {
         const int dil = 1 << i;
+        // inference re-uses two h buffers: h_{i+1} overwrites h_{i-1}, which res-skip conv i-2 may still be reading
+        if (forked && !f->training && i >= 2) RADMMM_CUDA(cudaStreamWaitEvent(st, side_event(20 + ((i - 2) & 1)), 0));
         init_args(a, d, f->lens, EPI_IN, d.H);
         for (int j = 0; j < 5; ++j)
             add_seg(a, w.Hs[i], sub_mode(p.Win, ((long long)i * 5 + j) * p.HH, d.es), d.H, (j - 2) * dil);
@@ -217,12 +230,21 @@ static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepa
         a.epi.dilation = dil;
         a.epi.out0 = w.Hs[i + 1];
         RADMMM_TRY(launch_gemm(a, d.mode, st));
+        if (forked) {
+            RADMMM_CUDA(cudaEventRecord(side_event(16 + (i & 1)), st));          // h_{i+1} ready
+            RADMMM_CUDA(cudaStreamWaitEvent(sd, side_event(16 + (i & 1)), 0));
+        }
         init_args(a, d, f->lens, EPI_RS, d.H);
         add_seg(a, w.Hs[i + 1], sub_mode(p.Wrs, (long long)i * p.HH, d.es), d.H, 0);
         a.epi.bias = f->rs_b[i];
         a.epi.padq = p.padq + (size_t)i * d.H;
         a.epi.out0 = w.S[i];
-        RADMMM_TRY(launch_gemm(a, d.mode, st));
+        RADMMM_TRY(launch_gemm(a, d.mode, sd));
+        if (forked && !f->training) RADMMM_CUDA(cudaEventRecord(side_event(20 + (i & 1)), sd));   // done reading h_{i+1}
+    }
+    if (forked) {                                                                 // join: every s_i is ready
+        RADMMM_CUDA(cudaEventRecord(side_event(18), sd));
+        RADMMM_CUDA(cudaStreamWaitEvent(st, side_event(18), 0));
     }
     // end(sum_i s_i) = sum_i end(s_i): one GEMM whose K runs over the L stored s_i
     init_args(a, d, f->lens, EPI_END, d.C);
@@ -282,17 +304,15 @@ static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat&
     // every launcher picks its own split-K; partial tiles are reduced with fp32 atomics into a zeroed output
     a.split_k = 0;
     a.epi.atomic = 1;
-    if (zero_out)
-        for (int j = 0; j < taps; ++j)
-            RADMMM_CUDA(cudaMemset2DAsync(out + j * tap_stride, sizeof(float) * ld, 0, sizeof(float) * N, M, st));
+    if (zero_out) {
+        if (ld == N && (taps == 1 || tap_stride == (long long)M * ld)) {       // one contiguous block
+            RADMMM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)taps * M * ld, st));
+        } else {
+            for (int j = 0; j < taps; ++j)
+                RADMMM_CUDA(cudaMemset2DAsync(out + j * tap_stride, sizeof(float) * ld, 0, sizeof(float) * N, M, st));
+        }
+    }
     return launch_gemm(a, d.mode, st);
-}
-
-// events for the fork/join with the side stream (created once per host thread; timing disabled)
-static cudaEvent_t side_event(int i) {
-    static thread_local cudaEvent_t ev[16] = {};
-    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
-    return ev[i];
 }
 
 int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_mid, const float* params,

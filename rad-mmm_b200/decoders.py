@@ -69,9 +69,11 @@ class FlowStep(nn.Module):
         if hasattr(conv, "maybe_initialize"):
             conv.maybe_initialize(z, seq_lens if seq_lens is not None else
                                   torch.full((z.shape[0],), z.shape[2], device=z.device))
-        z_out, log_s, _ = _flow_apply(tfn.affine_param_predictor, conv._weight(), None, mean, z, context, seq_lens,
+        pre, self._pre_W = getattr(self, "_pre_W", None), None     # assembled on the side stream by RADMMMFlow.forward
+        W, log_det_W = pre if pre is not None else (conv._weight(), conv.log_det())
+        z_out, log_s, _ = _flow_apply(tfn.affine_param_predictor, W, None, mean, z, context, seq_lens,
                                       tfn.scaling_fn, tfn.precision)
-        return z_out, conv.log_det(), log_s
+        return z_out, log_det_W, log_s
 
 
 class RADMMMFlow(RADMMM):
@@ -137,6 +139,17 @@ class RADMMMFlow(RADMMM):
         for fs in self.flows:
             fs.enable_inverse_cache()
 
+    def invalidate_weight_cache(self):
+        """Treat every parameter as changed: the next forward re-runs weight norm + re-layout for all flows and the
+        LSTM input weights, exactly as it does after an optimizer step (which bumps the tensors' version counters).
+        bench.py calls this every step because its timed loop has no optimizer."""
+        from . import lstm as _lstm
+        for fs in self.flows:
+            tfn = fs.coupling_tfn
+            if hasattr(tfn, "affine_param_predictor"):
+                tfn.affine_param_predictor.invalidate_prepared()
+        _lstm._wcache.clear()
+
     def _prepare_weights_async(self, device):
         """Weight preparation of all flows depends only on the parameters, so it is forked onto the side stream and
         overlaps the (latency-bound) context LSTM; returns the event the flow steps must wait for."""
@@ -150,6 +163,12 @@ class RADMMMFlow(RADMMM):
                 tfn = fs.coupling_tfn
                 if hasattr(tfn, "affine_param_predictor"):
                     tfn.affine_param_predictor.prepare(tfn.precision)
+                # the 1x1-conv matrix W = P (L + I) (U + diag) and log|det W| depend on the parameters only: assemble
+                # them here too (a dozen tiny kernels per flow, forward and backward) instead of on the flow chain
+                conv = fs.invtbl_conv
+                ready = (not hasattr(conv, "maybe_initialize")) or getattr(conv, "_init_seen", False) or not self.training
+                if not fs.use_spline and ready:
+                    fs._pre_W = (conv._weight(), conv.log_det())
             ev = torch.cuda.Event()
             ev.record(side)
         return ev
@@ -213,3 +232,4 @@ class _Lens:
 
     def __init__(self, lengths):
         self.lengths = lengths.long()
+        self.lens_i32 = lengths.to(torch.int32).contiguous()

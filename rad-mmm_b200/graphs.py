@@ -1,0 +1,80 @@
+"""CUDA-graph capture of the decoder train step.
+
+The eager module path (radmmm_b200.decoders.RADMMMFlow called from a Lightning loop) issues ~1000 kernel launches per
+step through Python / ctypes / autograd, and at B=8 x T=800 the host needs about as long to enqueue them as the B200
+needs to run them.  ``GraphedTrainStep`` captures ONE whole step -- weight preparation, context LSTM, the 8 flow steps,
+the flow NLL and the complete backward pass, including the side-stream forks -- into a CUDA graph with static input
+buffers; every later step is ``copy inputs -> replay``.  Sequence lengths are device data, so one graph serves every
+batch that is padded to the captured (batch, frames) shape.
+
+Gradients land in the parameters' ``.grad`` tensors, which are allocated during capture and re-written by every replay
+(do not set them to None between steps; zeroing is unnecessary because a replay overwrites them).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import loss as L
+from .common import SequenceLength
+
+_INPUT_KEYS = ("mel", "spk_vecs", "context", "out_lens", "f0", "energy_avg", "accent_vecs")
+
+
+class GraphedTrainStep:
+    """decoder forward + flow NLL + backward as one replayable CUDA graph.
+
+    ``example`` is a dict with the keys of ``radmmm_b200.synthetic.synthetic_batch`` (mel (B,80,T), spk_vecs (B,16),
+    context (B,n_text,T), out_lens (B), f0 (B,T), energy_avg (B,T), accent_vecs (B,n_acc)); only shapes and dtypes matter.
+    ``after_backward`` (optional) is called inside the captured region after ``loss.backward()`` (e.g. the gradient
+    all-reduce of ``radmmm_b200.ddp.BucketedGradReducer.finish``).
+    """
+
+    def __init__(self, decoder, example: Dict[str, torch.Tensor], sigma: float = 1.0, warmup: int = 3,
+                 after_backward: Optional[Callable[[], None]] = None):
+        dev = next(decoder.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.decoder, self.sigma, self.after_backward = decoder, sigma, after_backward
+        self.static = {k: example[k].detach().to(dev).clone() for k in _INPUT_KEYS if example.get(k) is not None}
+        self.frames = int(self.static["mel"].shape[2])
+        self.group = decoder.n_group_size
+        # warm-up on a side stream (allocator pools, lazily created events / attributes, data-dependent init)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        for p in decoder.parameters():
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self) -> torch.Tensor:
+        st, dec = self.static, self.decoder
+        dec.invalidate_weight_cache()          # parameters change between replays: re-run weight norm / re-layout
+        out = dec(st["mel"], st["spk_vecs"], st["context"], SequenceLength(st["out_lens"], self.frames),
+                  f0=st.get("f0"), energy_avg=st.get("energy_avg"), accent_vecs=st.get("accent_vecs"))
+        lens_g = torch.div(st["out_lens"], self.group, rounding_mode="floor")
+        loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g, self.sigma)
+        loss.backward()
+        if self.after_backward is not None:
+            self.after_backward()
+        return loss.detach()
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Copy ``batch`` (host or device tensors of the captured shapes) into the static buffers and replay.  Returns the
+        static loss tensor (device; valid until the next call)."""
+        for k, dst in self.static.items():
+            src = batch[k]
+            if src.shape != dst.shape:
+                raise RuntimeError(f"GraphedTrainStep: '{k}' has shape {tuple(src.shape)}, the graph was captured for "
+                                   f"{tuple(dst.shape)} (pad the batch to the captured shape)")
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss
