@@ -123,6 +123,22 @@ def _side_stream(device) -> int:
         _side_streams[device.index] = st
     return st.cuda_stream
 
+_prep_streams = {}
+
+
+def _prep_stream(device):
+    """Stream for the per-step weight preparation (weight norm + re-layout + 1x1-conv matrix assembly).  Separate from the
+    side stream so that flow i's res-skip GEMMs never queue behind the preparation of flows i+1 ..; None when the
+    side-stream fork is disabled."""
+    if os.environ.get("RADMMM_B200_SIDE_STREAM", "1") == "0":
+        return None
+    st = _prep_streams.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _prep_streams[device.index] = st
+    return st
+
+
 # Optional gradient sink (radmmm_b200.ddp.BucketedGradReducer): maps a parameter's storage pointer to a fresh view of
 # its all-reduce bucket so FlowStepFunction.backward writes parameter gradients straight into bucket storage.
 _grad_sink = None

@@ -178,50 +178,48 @@ int coupling_bwd(const float* dz_out, const float* dlog_s, const float* z, const
 
 // =========================================================================================================
 // Invertible 1x1 convolution (common.py:540-548, 605-617):  out[b,co,t] = sum_ci W[co,ci]*(in[b,ci,t]-pre[ci]) + post[co]
-// One CTA per (32-frame tile, batch): W^T (padded rows) and the x tile are resident in shared memory; a thread owns
-// 4 consecutive frames x up to 8 output channels (co = ty + 32 i): per input channel 1 LDS.128 + <=8 LDS for <=32 FMAs.
-// fp32 FFMA; HBM-bound: 2*C*4 bytes per grouped frame (W, 100 KB, is re-read from L2 by every CTA).
+// A small fp32 GEMM per utterance (M = Cout <= 256, N = T', K = Cin): one CTA per 32 (co) x 64 (t) output tile, K in
+// chunks of 32 through shared memory (W tile stored k-major so a thread reads its 2 output channels side by side, x tile
+// as is); a thread owns 2 channels x 4 consecutive frames.  Every global access is a full 128-byte row segment.
+// HBM-bound: 2*C*4 bytes per grouped frame; W (100 KB) comes from L2.
 // =========================================================================================================
-constexpr int INV_TT = 32;
+constexpr int INV_TC = 32, INV_TN = 64, INV_TK = 32;
 __global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
                                                      const float* __restrict__ W, const float* __restrict__ pre,
                                                      const float* __restrict__ post, float* __restrict__ out,
                                                      long long out_bs, int Cin, int Cout, int Tp) {
-    extern __shared__ float sm[];
-    const int ldw = Cout + 1;
-    float* xs = sm;                          // [Cin][INV_TT]
-    float* wt = sm + (size_t)Cin * INV_TT;   // [Cin][Cout + 1]  (transposed W)
-    const int t0 = blockIdx.x * INV_TT, b = blockIdx.y;
-    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;     // 8 x 32
-    for (int i = tid; i < Cin * INV_TT; i += 256) {
-        const int c = i / INV_TT, t = t0 + (i % INV_TT);
-        xs[i] = (t < Tp) ? in[(long long)b * in_bs + (long long)c * Tp + t] - (pre ? pre[c] : 0.0f) : 0.0f;
-    }
-    for (int i = tid; i < Cout * Cin; i += 256) {
-        const int co = i / Cin, ci = i % Cin;
-        wt[ci * ldw + co] = W[i];
-    }
-    __syncthreads();
-    constexpr int MAXO = 8;                  // Cout <= 256
-    float acc[MAXO][4];
-#pragma unroll
-    for (int i = 0; i < MAXO; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
-    for (int k = 0; k < Cin; ++k) {
-        const float4 x4 = *reinterpret_cast<const float4*>(xs + k * INV_TT + 4 * tx);
-        const float* wr = wt + k * ldw + ty;
-#pragma unroll
-        for (int i = 0; i < MAXO; ++i) {
-            if (ty + 32 * i < Cout) {
-                const float w = wr[32 * i];
-                acc[i][0] = fmaf(w, x4.x, acc[i][0]); acc[i][1] = fmaf(w, x4.y, acc[i][1]);
-                acc[i][2] = fmaf(w, x4.z, acc[i][2]); acc[i][3] = fmaf(w, x4.w, acc[i][3]);
-            }
+    __shared__ float ws[INV_TK][INV_TC + 2];      // [k][co]  (+2: float2 reads stay 8-byte aligned, conflict-light)
+    __shared__ __align__(16) float xs[INV_TK][INV_TN];          // [k][t]
+    const int t0 = blockIdx.x * INV_TN, co0 = blockIdx.y * INV_TC, b = blockIdx.z;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // 16 (t quads) x 16 (co pairs)
+    const float* inb = in + (long long)b * in_bs;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int k0 = 0; k0 < Cin; k0 += INV_TK) {
+        for (int i = tid; i < INV_TC * INV_TK; i += 256) {          // W tile: rows co, 32 consecutive ci each
+            const int c = i >> 5, k = i & 31;
+            ws[k][c] = (co0 + c < Cout && k0 + k < Cin) ? W[(long long)(co0 + c) * Cin + k0 + k] : 0.0f;
         }
+        for (int i = tid; i < INV_TK * INV_TN; i += 256) {          // x tile: rows ci, 64 consecutive frames each
+            const int k = i >> 6, t = i & 63;
+            const int ci = k0 + k;
+            xs[k][t] = (ci < Cin && t0 + t < Tp) ? inb[(long long)ci * Tp + t0 + t] - (pre ? pre[ci] : 0.0f) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < INV_TK; ++k) {
+            const float2 w2 = *reinterpret_cast<const float2*>(&ws[k][2 * ty]);
+            const float4 x4 = *reinterpret_cast<const float4*>(&xs[k][4 * tx]);
+            acc[0][0] = fmaf(w2.x, x4.x, acc[0][0]); acc[0][1] = fmaf(w2.x, x4.y, acc[0][1]);
+            acc[0][2] = fmaf(w2.x, x4.z, acc[0][2]); acc[0][3] = fmaf(w2.x, x4.w, acc[0][3]);
+            acc[1][0] = fmaf(w2.y, x4.x, acc[1][0]); acc[1][1] = fmaf(w2.y, x4.y, acc[1][1]);
+            acc[1][2] = fmaf(w2.y, x4.z, acc[1][2]); acc[1][3] = fmaf(w2.y, x4.w, acc[1][3]);
+        }
+        __syncthreads();
     }
     const int t = t0 + 4 * tx;
 #pragma unroll
-    for (int i = 0; i < MAXO; ++i) {
-        const int co = ty + 32 * i;
+    for (int i = 0; i < 2; ++i) {
+        const int co = co0 + 2 * ty + i;
         if (co < Cout) {
             const float pb = post ? post[co] : 0.0f;
             float* o = out + (long long)b * out_bs + (long long)co * Tp + t;
@@ -238,55 +236,70 @@ __global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ i
 
 int inv1x1(const float* in, long long in_bs, const float* W, const float* pre, const float* post, float* out,
            long long out_bs, int B, int Cin, int Cout, int Tp, cudaStream_t st) {
-    RADMMM_REQUIRE(Cout <= 256 && Cin <= 256, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
-    size_t smem = ((size_t)Cin * INV_TT + (size_t)Cin * (Cout + 1)) * sizeof(float);
-    RADMMM_REQUIRE(smem <= 220 * 1024, "inv1x1: shared memory %zu B too large", smem);
-    if (smem > 48 * 1024) RADMMM_CUDA(cudaFuncSetAttribute(inv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(Tp, INV_TT), B);
-    inv1x1_kernel<<<grid, 256, smem, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
+    RADMMM_REQUIRE(Cout >= 1 && Cin >= 1, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
+    dim3 grid(cdiv(Tp, INV_TN), cdiv(Cout, INV_TC), B);
+    inv1x1_kernel<<<grid, 256, 0, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }
 
-// dW[co][ci] += sum over valid (b,t) of dz[b,co,t] * (x[b,ci,t] - pre[ci]).  32x32 output tile per CTA, split over
-// (batch, time chunks) with atomics into a zeroed fp32 buffer.
+// dW[co][ci] += sum over valid (b,t) of dz[b,co,t] * (x[b,ci,t] - pre[ci]).  One CTA per 64 x 64 output tile and
+// (utterance, time chunk); a thread owns 4 x 4 outputs (two LDS.128 per 16 FMAs); partial tiles are reduced with fp32
+// atomics into the zeroed output.
+constexpr int WG_T = 32;
 __global__ void __launch_bounds__(256) inv1x1_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ x,
                                                            const float* __restrict__ pre, const int* __restrict__ lens,
                                                            float* __restrict__ dW, int C, int Tp, int t_chunk) {
-    __shared__ float a[32][33], bx[32][33];
-    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
-    const int b = blockIdx.z / cdiv(Tp, t_chunk), tc = blockIdx.z % cdiv(Tp, t_chunk);
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    __shared__ __align__(16) float a[WG_T][64 + 4], bx[WG_T][64 + 4];        // [t][channel]
+    const int co0 = blockIdx.x * 64, ci0 = blockIdx.y * 64;
+    const int n_tc = cdiv(Tp, t_chunk);
+    const int b = blockIdx.z / n_tc, tc = blockIdx.z % n_tc;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // 16 (ci quads) x 16 (co quads)
     const int len = min(lens[b], Tp);
     const int t_begin = tc * t_chunk, t_end = min(len, t_begin + t_chunk);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t0 = t_begin; t0 < t_end; t0 += 32) {
-        for (int i = ty; i < 32; i += 8) {
-            const int t = t0 + tx;
+    if (t_begin >= t_end) return;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int t0 = t_begin; t0 < t_end; t0 += WG_T) {
+        for (int i = tid; i < 64 * WG_T; i += 256) {               // rows = channels, 32 consecutive frames each
+            const int c = i >> 5, tt = i & 31;
+            const int t = t0 + tt;
             const bool ok = t < t_end;
-            a[i][tx] = (ok && co0 + i < C) ? dz[((long long)b * C + co0 + i) * Tp + t] : 0.0f;
-            bx[i][tx] = (ok && ci0 + i < C) ? x[((long long)b * C + ci0 + i) * Tp + t] - (pre ? pre[ci0 + i] : 0.0f) : 0.0f;
+            a[tt][c] = (ok && co0 + c < C) ? dz[((long long)b * C + co0 + c) * Tp + t] : 0.0f;
+            bx[tt][c] = (ok && ci0 + c < C) ? x[((long long)b * C + ci0 + c) * Tp + t] - (pre ? pre[ci0 + c] : 0.0f) : 0.0f;
         }
         __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < WG_T; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&a[k][4 * ty]);
+            const float4 bv = *reinterpret_cast<const float4*>(&bx[k][4 * tx]);
+            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = fmaf(a[ty + 8 * j][k], bx[tx][k], acc[j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
         __syncthreads();
     }
-    if (t_begin < t_end)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + 4 * ty + i;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int co = co0 + ty + 8 * j, ci = ci0 + tx;
-            if (co < C && ci < C) atomicAdd(dW + (long long)co * C + ci, acc[j]);
+            const int ci = ci0 + 4 * tx + j;
+            if (co < C && ci < C) atomicAdd(dW + (long long)co * C + ci, acc[i][j]);
         }
+    }
 }
 
 int inv1x1_wgrad(const float* dz, const float* x, const float* pre, const int* lens, float* dW, int B, int C, int Tp,
                  cudaStream_t st) {
-    const int t_chunk = 256;
+    const int t_chunk = 224;
     RADMMM_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * C * C, st));
-    dim3 grid(cdiv(C, 32), cdiv(C, 32), B * cdiv(Tp, t_chunk));
+    dim3 grid(cdiv(C, 64), cdiv(C, 64), B * cdiv(Tp, t_chunk));
     inv1x1_wgrad_kernel<<<grid, 256, 0, st>>>(dz, x, pre, lens, dW, C, Tp, t_chunk);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
@@ -463,10 +476,67 @@ __global__ void wn_bwd_kernel(const float* __restrict__ src0, long long ld0, lon
     for (int i = threadIdx.x; i < per_co; i += blockDim.x) o[i] = sc * (dw_at(i / ksize, i % ksize) - vp[i] * coef);
 }
 
+// Same computation with the output channel's v row and its dW entries staged in shared memory: every global access is
+// coalesced (dW is read tap plane by tap plane, v and dv as contiguous rows) and each byte moves exactly once
+// (algorithmic traffic 3 x 4 bytes per weight; the generic kernel above gathers dW across the tap planes twice).
+__global__ void __launch_bounds__(256) wn_bwd_staged_kernel(const float* __restrict__ src0, long long ld0, long long tap0,
+                                                            int n_ci0, const float* __restrict__ src1, long long ld1,
+                                                            long long tap1, const float* __restrict__ v,
+                                                            const float* __restrict__ g, const float* __restrict__ norm,
+                                                            int ci_total, int ksize, float* __restrict__ dv,
+                                                            float* __restrict__ dg) {
+    extern __shared__ float wsm[];
+    const int co = blockIdx.x;
+    const int per_co = ci_total * ksize;
+    float* sv = wsm;                 // [ci][k]  (the layout of v)
+    float* sd = wsm + per_co;        // [ci][k]
+    const float* vp = v + (long long)co * per_co;
+    for (int i = threadIdx.x; i < per_co; i += 256) sv[i] = vp[i];
+    for (int k = 0; k < ksize; ++k) {
+        const float* p0 = src0 + k * tap0 + (long long)co * ld0;
+        const float* p1 = src1 ? src1 + k * tap1 + (long long)co * ld1 : nullptr;
+        for (int ci = threadIdx.x; ci < ci_total; ci += 256)
+            sd[ci * ksize + k] = ci < n_ci0 ? p0[ci] : p1[ci - n_ci0];
+    }
+    __syncthreads();
+    double dot = 0.0;
+    {
+        float part = 0.0f;               // <= 8 products per fp32 partial, then fp64
+        int n = 0;
+        for (int i = threadIdx.x; i < per_co; i += 256) {
+            part = fmaf(sd[i], sv[i], part);
+            if (++n == 8) { dot += (double)part; part = 0.0f; n = 0; }
+        }
+        dot += (double)part;
+    }
+    __shared__ double red[8];
+    __shared__ float sdot;
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0;
+        for (int i = 0; i < 8; ++i) a += red[i];
+        sdot = (float)a;
+    }
+    __syncthreads();
+    const float nrm = norm[co], gg = g[co];
+    const float d = sdot;
+    if (threadIdx.x == 0) dg[co] = d / nrm;
+    const float sc = gg / nrm, coef = d / (nrm * nrm);
+    float* o = dv + (long long)co * per_co;
+    for (int i = threadIdx.x; i < per_co; i += 256) o[i] = sc * (sd[i] - sv[i] * coef);
+}
+
 int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const float* src1, long long ld1,
            long long tap1, const float* v, const float* g, const float* norm, int n_co, int ci_total, int ksize,
            float* dv, float* dg, cudaStream_t st) {
-    wn_bwd_kernel<<<n_co, 256, 0, st>>>(src0, ld0, tap0, n_ci0, src1, ld1, tap1, v, g, norm, ci_total, ksize, dv, dg);
+    const size_t smem = sizeof(float) * 2 * (size_t)ci_total * ksize;
+    if (smem <= 48 * 1024) {
+        wn_bwd_staged_kernel<<<n_co, 256, smem, st>>>(src0, ld0, tap0, n_ci0, src1, ld1, tap1, v, g, norm, ci_total, ksize, dv, dg);
+    } else {
+        wn_bwd_kernel<<<n_co, 256, 0, st>>>(src0, ld0, tap0, n_ci0, src1, ld1, tap1, v, g, norm, ci_total, ksize, dv, dg);
+    }
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }

@@ -66,8 +66,23 @@ struct GemmArgs {
     int wgrad;      // 0 row GEMM; 1 weight-grad GEMM, one output tile set per segment (= conv tap);
                     // 2 weight-grad GEMM, all segments (same dY, different X) accumulate into ONE output
     int split_k;    // weight-grad only
+    int zero_output;  // weight-grad: the launcher zeroes `f32_out` itself if (and only if) its split-K reduces with atomics,
+                      // and stores plainly otherwise (epi.atomic is then decided by the launcher)
     EpiParams epi;
 };
+
+// zero the [taps][M][ld] fp32 weight-gradient output of `a` (columns [0, N))
+inline int zero_wgrad_output(const GemmArgs& a, cudaStream_t st) {
+    const int taps = a.wgrad == 2 ? 1 : a.n_seg;
+    const long long ld = a.epi.f32_ld, ts = a.epi.f32_tap_stride;
+    if (ld == a.epi.N && (taps == 1 || ts == (long long)a.epi.M * ld)) {       // one contiguous block
+        RADMMM_CUDA(cudaMemsetAsync(a.epi.f32_out, 0, sizeof(float) * (size_t)taps * a.epi.M * ld, st));
+    } else {
+        for (int j = 0; j < taps; ++j)
+            RADMMM_CUDA(cudaMemset2DAsync(a.epi.f32_out + j * ts, sizeof(float) * ld, 0, sizeof(float) * a.epi.N, a.epi.M, st));
+    }
+    return RADMMM_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Epilogue for one row r and NV consecutive columns n0..n0+NV-1 (n0 % NV == 0, NV in {4, 8, 16, 32}).
@@ -115,8 +130,13 @@ __device__ __forceinline__ void staged_store32(const Stager& st, const ActMat& m
     }
 }
 
+// Saved-activation tile of one epilogue warp, 32 rows x 32 columns: coalesced global loads into registers (`raw`, issued
+// early so that their latency overlaps the main loop / other loads), later turned into this thread's row via the stage.
 template <int MODE>
-__device__ __forceinline__ void staged_load32(const Stager& st, const ActMat& m, int r, int n0, float* v) {
+struct RawTile { uint4 q[(MODE == MODE_BF16X3 ? 2 : 1) * 4]; };
+
+template <int MODE>
+__device__ __forceinline__ void staged_fetch32(const Stager& st, const ActMat& m, int r, int n0, RawTile<MODE>& raw) {
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.ptr);
     const int row_base = r - st.lane;
 #pragma unroll
@@ -124,8 +144,20 @@ __device__ __forceinline__ void staged_load32(const Stager& st, const ActMat& m,
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int rr = i * 8 + (st.lane >> 2), seg = st.lane & 3;
-            const uint4 val = *reinterpret_cast<const uint4*>(base + (long long)plane * m.plane_stride + (long long)(row_base + rr) * m.ld + n0 + seg * 8);
-            *reinterpret_cast<uint4*>(st.buf + rr * kStageLd + seg * 8) = val;
+            raw.q[plane * 4 + i] = *reinterpret_cast<const uint4*>(base + (long long)plane * m.plane_stride +
+                                                                    (long long)(row_base + rr) * m.ld + n0 + seg * 8);
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void staged_unpack32(const Stager& st, const RawTile<MODE>& raw, float* v) {
+#pragma unroll
+    for (int plane = 0; plane < (MODE == MODE_BF16X3 ? 2 : 1); ++plane) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (st.lane >> 2), seg = st.lane & 3;
+            *reinterpret_cast<uint4*>(st.buf + rr * kStageLd + seg * 8) = raw.q[plane * 4 + i];
         }
         __syncwarp();
         const uint4* mine = reinterpret_cast<const uint4*>(st.buf + st.lane * kStageLd);
@@ -139,6 +171,36 @@ __device__ __forceinline__ void staged_load32(const Stager& st, const ActMat& m,
                 if (plane == 0) { v[8 * j + 2 * k] = f.x; v[8 * j + 2 * k + 1] = f.y; }
                 else { v[8 * j + 2 * k] += f.x; v[8 * j + 2 * k + 1] += f.y; }
             }
+        }
+        __syncwarp();
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void staged_load32(const Stager& st, const ActMat& m, int r, int n0, float* v) {
+    RawTile<MODE> raw;
+    staged_fetch32<MODE>(st, m, r, n0, raw);
+    staged_unpack32<MODE>(st, raw, v);
+}
+
+// fp32 rows [R][ld]: this thread holds 32 consecutive floats of row r.  Through the stage (80-byte rows = 16 floats + pad)
+// in two halves, so that a warp instruction writes 8 rows x 64 contiguous bytes instead of 32 rows x 4 bytes.
+__device__ __forceinline__ void staged_store32_f32(const Stager& st, float* out, long long ld, int r, int n0, const float* v) {
+    float* sbuf = reinterpret_cast<float*>(st.buf);
+    constexpr int kLdF = kStageLd / 2;                      // 20 floats per staged row
+    const int row_base = r - st.lane;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float4* mine = reinterpret_cast<float4*>(sbuf + st.lane * kLdF);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            mine[j] = make_float4(v[half * 16 + 4 * j], v[half * 16 + 4 * j + 1], v[half * 16 + 4 * j + 2], v[half * 16 + 4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (st.lane >> 2), seg = st.lane & 3;
+            const float4 val = *reinterpret_cast<const float4*>(sbuf + rr * kLdF + seg * 4);
+            *reinterpret_cast<float4*>(out + (long long)(row_base + rr) * ld + n0 + half * 16 + seg * 4) = val;
         }
         __syncwarp();
     }
@@ -254,19 +316,45 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
         for (int i = 0; i < NV; ++i) out[i] = softplus_f<FAST>(valid ? acc[i] + s[i] : s[i]);
         store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_END || KIND == EPI_DZ0) {
-        if (b < p.geom.B && t < p.geom.Tp) {
+        if (b < p.geom.B && t < p.geom.Tp && n0 < p.N) {
+            float* dst0 = p.cf_out + ((long long)(b * p.cf_C + p.cf_c0 + n0)) * p.geom.Tp + t;
+            const long long cs = p.geom.Tp;                 // channel stride; lanes = consecutive t: coalesced
+            if (p.accumulate) {                              // all loads first (they are independent L2 round trips)
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                int n = n0 + i;
-                if (n < p.N) {
-                    float v = acc[i] + (KIND == EPI_END ? __ldg(p.bias + n) : 0.0f);
-                    float* dst = p.cf_out + ((long long)(b * p.cf_C + p.cf_c0 + n)) * p.geom.Tp + t;
-                    if (p.accumulate) v += *dst;
-                    *dst = v;
-                }
+                for (int i = 0; i < NV; ++i) out[i] = (n0 + i < p.N) ? dst0[i * cs] : 0.0f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) out[i] = 0.0f;
             }
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (n0 + i < p.N) dst0[i * cs] = out[i] + acc[i] + (KIND == EPI_END ? __ldg(p.bias + n0 + i) : 0.0f);
         }
     } else if constexpr (KIND == EPI_DOUT) {
+        if constexpr (MODE != MODE_F32 && NV == 32) {
+            if (st.buf != nullptr) {
+                // tensor-core path: the epilogue is pure memory traffic (L tiles in, L tiles out); issue the loads of a
+                // group of layers back to back so that their latencies overlap instead of adding up
+                constexpr int G = (MODE == MODE_BF16X3) ? 2 : 4;
+                for (int l0 = 0; l0 < p.n_layers; l0 += G) {
+                    RawTile<MODE> raw[G];
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+                        if (l0 + j < p.n_layers) staged_fetch32<MODE>(st, p.sig[l0 + j], r, n0, raw[j]);
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        if (l0 + j < p.n_layers) {
+                            float sv[NV];
+                            staged_unpack32<MODE>(st, raw[j], sv);
+#pragma unroll
+                            for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<FAST>(sv[i]) : 0.0f;
+                            store_row_vec<MODE, NV>(st, p.dq[l0 + j], r, n0, out);
+                        }
+                    }
+                }
+                return;
+            }
+        }
         for (int l = 0; l < p.n_layers; ++l) {
             float sv[NV];
             load_row_vec<MODE, NV>(st, p.sig[l], r, n0, sv);          // s_l = softplus(q_l); d softplus = 1 - exp(-s)
@@ -286,6 +374,14 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
         for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] : 0.0f;
         store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_DCTX || KIND == EPI_F32) {
+        if constexpr (NV == 32) {
+            if (st.buf != nullptr && !p.accumulate && n0 + NV <= p.N && (p.f32_ld & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) out[i] = acc[i] + ((KIND == EPI_F32 && p.bias) ? __ldg(p.bias + n0 + i) : 0.0f);
+                staged_store32_f32(st, p.f32_out, p.f32_ld, r, n0, out);
+                return;
+            }
+        }
         float* o = p.f32_out + (long long)r * p.f32_ld + n0;
 #pragma unroll
         for (int i = 0; i < NV; ++i)
@@ -294,6 +390,20 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
                 o[i] = p.accumulate ? o[i] + v : v;
             }
     }
+}
+
+// EPI_DH with the saved activation h already in registers (the tcgen05 kernel fetches it while the main loop runs)
+template <int MODE>
+__device__ __forceinline__ void epi_dh_with_h(const EpiParams& p, const Stager& st, int r, int n0, const float* acc,
+                                              const float* hv) {
+    int b, t, len;
+    row_decode(p.geom, r, b, t, len);
+    const bool valid = t < len;
+    const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
+    float out[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<true>(hv[i]) * ratio : 0.0f;
+    store_row_vec<MODE, 32>(st, p.out0, r, n0, out);
 }
 
 // weight-grad tile element (m, n0..n0+NV) of tap `tap`

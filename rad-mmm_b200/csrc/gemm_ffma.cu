@@ -149,6 +149,7 @@ int launch_gemm_ffma(const GemmArgs& args, cudaStream_t stream) {
             a2.split_k = split < 1 ? 1 : split;
         }
         RADMMM_REQUIRE(a2.split_k == 1 || a2.epi.atomic, "gemm_ffma: split-K needs the atomic epilogue");
+        if (args.zero_output) RADMMM_TRY(zero_wgrad_output(args, stream));
         dim3 grid(cdiv(args.epi.M, BM), cdiv(args.epi.N, BN), (args.wgrad == 2 ? 1 : args.n_seg) * a2.split_k);
         gemm_ffma_kernel<EPI_WGRAD, true><<<grid, NT, 0, stream>>>(a2);
         RADMMM_LAUNCH_CHECK();

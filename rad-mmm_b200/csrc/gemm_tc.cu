@@ -43,6 +43,7 @@ struct TcParams {
     int n_seg, n_a_maps, n_b_maps;
     int m_tiles, n_tiles, taps, split_k, k_blocks_total;   // weight-grad: k_blocks_total = R/64
     int acc_segs;                                          // weight-grad: all segments accumulate into one output
+    int debug;                                             // probe bits (tools/gemm_probe.py): 1 no epilogue, 2 no MMA, 4 no TMA
     EpiParams epi;
 };
 
@@ -293,6 +294,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         uint8_t* sb_hi = st + C::planes * C::a_bytes;
                         uint8_t* sb_lo = sb_hi + C::b_bytes;
                         uint64_t* fb = &full[stage];
+                        if (P.debug & 4) {                        // probe: no loads, just hand the slot over
+                            if (CL == 2 && !leader) mbar_arrive_remote(fb, 0);
+                            else mbar_arrive(fb);
+                            if (++stage == C::stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         if (CL == 1) mbar_expect_tx(fb, C::stage_bytes);
                         if (!WGRAD) {
                             const int a_c0 = kb * BK, a_c1 = m_blk * BM + sg.a_row_shift;
@@ -355,7 +362,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    if (elect_one()) {
+                    if (P.debug & 2) {                            // probe: no MMAs, release the slot at once
+                        if (elect_one()) {
+                            mbar_arrive(&empty[stage]);
+                            if (CL == 2) mbar_arrive_remote(&empty[stage], 1);
+                            if (kb == total_kb - 1) tc_commit<CL>(&tfull[as]);
+                        }
+                    } else if (elect_one()) {
                         const uint32_t st = smem_u32(smem + stage * C::stage_bytes);
                         const uint32_t a_hi = st, a_lo = st + C::a_bytes;
                         const uint32_t b_hi = st + C::planes * C::a_bytes, b_lo = b_hi + C::b_bytes;
@@ -400,13 +413,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             decode(walk, m_blk, n_blk, tap, split);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
+            const int row = m_blk * BM + q * 32 + lane;
+            if constexpr (!WGRAD && KIND == EPI_DH) {
+                // the saved activations this warp needs are fetched BEFORE waiting for the accumulator, two 32-column
+                // chunks ahead, so their latency hides behind the main loop (one tile per CTA: nothing else overlaps it)
+                constexpr int NCH = kColsPerWarp / 32;
+                RawTile<MODE> raw[2];
+                const int nb = n_blk * BN + half * kColsPerWarp;
+                staged_fetch32<MODE>(stager, P.epi.h, row, nb, raw[0]);
+                if (NCH > 1) staged_fetch32<MODE>(stager, P.epi.h, row, nb + 32, raw[1]);
+                mbar_wait(&tfull[as], aphase);
+                tc_fence_after();
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    if (P.debug & 1) break;
+                    float v[32], hv[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + half * kColsPerWarp + ci * 32), v);
+                    staged_unpack32<MODE>(stager, raw[ci & 1], hv);
+                    if (ci + 2 < NCH) staged_fetch32<MODE>(stager, P.epi.h, row, nb + (ci + 2) * 32, raw[ci & 1]);
+                    epi_dh_with_h<MODE>(P.epi, stager, row, nb + ci * 32, v, hv);
+                }
+                tc_fence_before();
+                if (CL == 2 && !leader) mbar_arrive_remote(&tempty[as], 0);
+                else mbar_arrive(&tempty[as]);
+                continue;
+            }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const int row = m_blk * BM + q * 32 + lane;
             bool has_acc = true;
             if (WGRAD) { int kb0, kb1; k_range(split, kb0, kb1); has_acc = kb1 > kb0; }
 #pragma unroll 1
             for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
+                if (P.debug & 1) break;                           // probe: no epilogue
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), v);
                 const int n0 = n_blk * BN + c;
@@ -544,9 +582,12 @@ struct MapKey { const void* ptr; long long ld, plane; };
 
 // RADMMM_B200_TC_PAIR=0 forces the 1-CTA kernel (debugging / A-B measurements)
 static bool pair_mode_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("RADMMM_B200_TC_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
+    const char* e = getenv("RADMMM_B200_TC_PAIR");
+    return !(e && e[0] == '0');
+}
+static int probe_bits() {
+    const char* e = getenv("RADMMM_B200_TC_PROBE");
+    return e ? atoi(e) : 0;
 }
 
 }  // namespace
@@ -560,11 +601,22 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     memset(&P, 0, sizeof(P));
     P.epi = args.epi;
     P.n_seg = args.n_seg;
+    P.debug = probe_bits();
 
     // output tiling
     const int N = args.epi.N;
     const int n_pad = (int)round_up(N, 128);
-    const int BN = (!x3 && n_pad % 256 == 0) ? 256 : 128;
+    int BN = (!x3 && n_pad % 256 == 0) ? 256 : 128;
+    if (args.wgrad && BN == 256 && args.split_k < 1) {
+        // weight-grad tiling: if 128-wide tiles alone fill the machine ~1.5 times over (the 5-tap dilated conv: 160 pair
+        // tiles for 74 pair slots) take them and skip split-K -- plain stores, no zero-fill, no fp32 atomics; 256-wide
+        // tiles leave 80 pair tiles = two rounds for 6 pairs
+        const int taps = args.wgrad == 2 ? 1 : args.n_seg;
+        const long long slots = sm_count();
+        const long long t256 = (long long)cdiv(args.epi.M, BM) * (n_pad / 256) * taps;
+        const long long t128 = (long long)cdiv(args.epi.M, BM) * (n_pad / 128) * taps;
+        if (2 * t256 < 3 * slots && 2 * t128 >= 3 * slots) BN = 128;
+    }
     P.n_tiles = n_pad / BN;
     int n_tiles_total;
 
@@ -641,6 +693,7 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // split K (= rows) so that the persistent grid sees >= ~4 tiles per SM while every tile keeps >= 8 K blocks
         const int tiles0 = P.m_tiles * P.n_tiles * P.taps;
         int split = args.split_k;
+        if (split < 1 && 2 * (long long)tiles0 >= 3 * sm_count()) split = 1;      // enough tiles already
         if (split < 1) {
             split = cdiv(2 * sm_count(), tiles0);
             const int max_split = P.k_blocks_total / 8 > 1 ? P.k_blocks_total / 8 : 1;
@@ -655,7 +708,11 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         P.split_k = split;
         n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
         use_cl = (P.m_tiles % 2 == 0) && pair_mode_enabled();
-        RADMMM_REQUIRE(split == 1 || args.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
+        if (args.zero_output) {                 // the launcher owns the reduction strategy
+            P.epi.atomic = split > 1;
+            if (split > 1) RADMMM_TRY(zero_wgrad_output(args, stream));
+        }
+        RADMMM_REQUIRE(split == 1 || P.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
         // inner extents stop at the logical widths (rounded to the 64-channel box) so that operands which are column
         // slices of wider matrices never read past their rows
         const long long a_in = round_up(M, 64) < g0.a.ld ? round_up(M, 64) : g0.a.ld;

@@ -1,6 +1,7 @@
 // One flow step (invertible 1x1 conv + WN + affine coupling): weight preparation, forward, inverse, backward.
 // Host-side orchestration only -- every launch goes to the caller's stream, nothing allocates or synchronises.
 #include "../../include/radmmm_b200.h"
+#include <stdlib.h>
 #include "gemm.cuh"
 #include "ops.cuh"
 
@@ -113,22 +114,23 @@ static size_t layout_workspace(const Dims& d, int training, void* base, Workspac
 struct Scratch {
     ActMat DP;
     ActMat DQ[RADMMM_MAX_LAYERS];
-    ActMat DACC[2];
-    float* dW;     // [5][H][H] fp32 (also holds dWz [H][Kz] + dWc [H][Dp])
+    ActMat DACC[RADMMM_MAX_LAYERS + 1];    // one per layer + dh0: the chain never waits for the weight-gradient lanes
+    float* dW_in[RADMMM_MAX_LAYERS];       // [5][H][H] fp32 per dilated conv
+    float* dW_rs[RADMMM_MAX_LAYERS];       // [H][H] fp32 per res-skip conv
+    float* dW_start;                       // dWz [H][Kz] + dWc [H][Dp]
 };
 
 static size_t layout_scratch(const Dims& d, void* base, Scratch* s) {
     Bump b{(char*)base, 0};
     Scratch q;
     q.DP = take_act(b, d, d.R, d.Cp);
+    for (int i = 0; i < d.L; ++i) q.DQ[i] = take_act(b, d, d.R, d.H);
+    for (int i = 0; i <= d.L; ++i) q.DACC[i] = take_act(b, d, d.R, d.H);
     for (int i = 0; i < d.L; ++i) {
-        q.DQ[i] = take_act(b, d, d.R, d.H);
+        q.dW_in[i] = (float*)b.take(sizeof(float) * (size_t)5 * d.H * d.H);
+        q.dW_rs[i] = (float*)b.take(sizeof(float) * (size_t)d.H * d.H);
     }
-    for (int i = 0; i < 2; ++i) {
-        q.DACC[i] = take_act(b, d, d.R, d.H);
-    }
-    size_t n1 = (size_t)5 * d.H * d.H, n2 = (size_t)d.H * (d.Kz + d.Dp);
-    q.dW = (float*)b.take(sizeof(float) * (n1 > n2 ? n1 : n2));
+    q.dW_start = (float*)b.take(sizeof(float) * (size_t)d.H * (d.Kz + d.Dp));
     if (s) *s = q;
     return (size_t)round_up((long long)b.off, 1024);
 }
@@ -193,6 +195,30 @@ static void add_seg(GemmArgs& a, const ActMat& act, const ActMat& w, int K, int 
     s.a = act; s.w = w; s.K = K; s.shift = shift;
 }
 
+// Auxiliary streams for the weight-gradient lanes of flow_backward (created once per host thread).  Each lane runs
+// complete, mutually independent chains (bias column sum -> weight-grad GEMM -> weight-norm backward) with private
+// scratch, so the only serial chain left is the input-gradient GEMMs on the caller's stream.
+constexpr int kLanes = 4;
+static cudaStream_t lane_stream(int i) {
+    static thread_local cudaStream_t st[kLanes] = {};
+    if (!st[i]) cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    return st[i];
+}
+static cudaStream_t chain_stream() {
+    static thread_local cudaStream_t st = nullptr;
+    if (!st) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest);
+    }
+    return st;
+}
+static cudaEvent_t lane_event(int i) {
+    static thread_local cudaEvent_t ev[64] = {};
+    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    return ev[i];
+}
+
 // events for the fork/join with the side stream (created once per host thread; timing disabled)
 static cudaEvent_t side_event(int i) {
     static thread_local cudaEvent_t ev[32] = {};
@@ -204,11 +230,17 @@ static cudaEvent_t side_event(int i) {
 // The dilated convs form the dependent chain h_0 -> h_1 -> ... on `st`; res-skip conv i only feeds the `end` GEMM, so it
 // runs on the side stream (when the descriptor carries one) and fills the SMs the chain's 104-tile launches leave idle.
 static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepared& p, const Workspace& w,
-                           const float* z_mid, float* params, cudaStream_t st) {
+                           const float* z_mid, float* params, cudaStream_t caller) {
     const RowGeom g = geom_of(d, f->lens);
     ActMat ctx; ctx.ptr = const_cast<void*>(f->ctx_rows); ctx.ld = d.Dp; ctx.plane_stride = (long long)d.R * d.Dp;
-    cudaStream_t sd = f->side_stream ? reinterpret_cast<cudaStream_t>(f->side_stream) : st;
-    const bool forked = sd != st;
+    cudaStream_t sd = f->side_stream ? reinterpret_cast<cudaStream_t>(f->side_stream) : caller;
+    const bool forked = sd != caller;
+    cudaStream_t st = caller;                 // the chain's stream: high priority when forked (see flow_backward)
+    if (forked) {
+        st = chain_stream();
+        RADMMM_CUDA(cudaEventRecord(side_event(22), caller));
+        RADMMM_CUDA(cudaStreamWaitEvent(st, side_event(22), 0));
+    }
     // z0 = z_mid[:, :Ch] -> rows
     RADMMM_TRY(rows_from_cf(d.mode, z_mid, (long long)d.C * d.Tp, d.Ch, g, w.Z0, d.Kz, 1, st));
     GemmArgs a;
@@ -252,6 +284,10 @@ static int wn_forward_rows(const radmmm_flow_desc* f, const Dims& d, const Prepa
     a.epi.bias = f->end_b;
     a.epi.cf_out = params; a.epi.cf_C = d.C; a.epi.cf_c0 = 0;
     RADMMM_TRY(launch_gemm(a, d.mode, st));
+    if (forked) {                                                                 // hand the result back to the caller
+        RADMMM_CUDA(cudaEventRecord(side_event(23), st));
+        RADMMM_CUDA(cudaStreamWaitEvent(caller, side_event(23), 0));
+    }
     return RADMMM_OK;
 }
 
@@ -301,17 +337,10 @@ static int wgrad(const Dims& d, const int* lens, const ActMat& dY, const ActMat&
     }
     a.epi.M = M;
     a.epi.f32_out = out; a.epi.f32_ld = ld; a.epi.f32_tap_stride = tap_stride;
-    // every launcher picks its own split-K; partial tiles are reduced with fp32 atomics into a zeroed output
+    // every launcher picks its own tiling / split-K and zeroes the output itself when it reduces with atomics
     a.split_k = 0;
     a.epi.atomic = 1;
-    if (zero_out) {
-        if (ld == N && (taps == 1 || tap_stride == (long long)M * ld)) {       // one contiguous block
-            RADMMM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)taps * M * ld, st));
-        } else {
-            for (int j = 0; j < taps; ++j)
-                RADMMM_CUDA(cudaMemset2DAsync(out + j * tap_stride, sizeof(float) * ld, 0, sizeof(float) * N, M, st));
-        }
-    }
+    a.zero_output = zero_out ? 1 : 0;
     return launch_gemm(a, d.mode, st);
 }
 
@@ -329,29 +358,44 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
     const int H = d.H, L = d.L;
     ActMat ctx; ctx.ptr = const_cast<void*>(f->ctx_rows); ctx.ld = d.Dp; ctx.plane_stride = (long long)d.R * d.Dp;
     GemmArgs a;
-    // Two lanes of work: `st` carries the input-gradient chain (the critical path), `sd` the weight-gradient work that
-    // only consumes what the chain produces.  Event k: "chain product k is ready"; event 8+k: "side is done with buffer k".
-    cudaStream_t sd = f->side_stream ? reinterpret_cast<cudaStream_t>(f->side_stream) : st;
-    const bool forked = sd != st;
-    auto signal = [&](cudaStream_t from, cudaStream_t to, int ev) -> int {
+    // `st` carries the input-gradient chain (the critical path).  With a side stream in the descriptor the weight-gradient
+    // work is spread over kLanes auxiliary streams; every chain waits for the chain product it consumes (event) and all
+    // lanes are joined back into `st` before returning.  Without one, everything runs on `st`.
+    static const bool lanes_on = []() { const char* e = getenv("RADMMM_B200_LANES"); return !(e && e[0] == '0'); }();
+    const bool forked = f->side_stream != nullptr && lanes_on;
+    int n_ev = 0;
+    // the chain itself runs on a high-priority stream: its CTAs win the SMs whenever a lane kernel and a chain kernel
+    // are both waiting for them
+    cudaStream_t mc = st;
+    if (forked) {
+        mc = chain_stream();
+        cudaEvent_t e = lane_event(n_ev++);
+        RADMMM_CUDA(cudaEventRecord(e, st));
+        RADMMM_CUDA(cudaStreamWaitEvent(mc, e, 0));
+    }
+    auto lane = [&](int i) -> cudaStream_t { return forked ? lane_stream(i % kLanes) : st; };
+    auto ready = [&](cudaStream_t to) -> int {       // `to` waits for everything enqueued on the chain so far
         if (!forked) return RADMMM_OK;
-        RADMMM_CUDA(cudaEventRecord(side_event(ev), from));
-        RADMMM_CUDA(cudaStreamWaitEvent(to, side_event(ev), 0));
+        cudaEvent_t e = lane_event(n_ev++);
+        RADMMM_CUDA(cudaEventRecord(e, mc));
+        RADMMM_CUDA(cudaStreamWaitEvent(to, e, 0));
         return RADMMM_OK;
     };
 
     // 1. coupling tail
-    RADMMM_TRY(coupling_bwd(dz_out, dlog_s, z_mid, params, f->lens, dz_mid, dparams, d.B, d.C, d.Tp, f->scaling_fn, st));
-    RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, d.Cp, 1, st));
+    RADMMM_TRY(coupling_bwd(dz_out, dlog_s, z_mid, params, f->lens, dz_mid, dparams, d.B, d.C, d.Tp, f->scaling_fn, mc));
+    RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, d.Cp, 1, mc));
     // 2. end conv: input gradient on the chain ...
     init_args(a, d, f->lens, EPI_DOUT, H);
     add_seg(a, s.DP, p.WendT, d.Cp, 0);
     for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.S[i]; a.epi.dq[i] = s.DQ[i]; }
-    RADMMM_TRY(launch_gemm(a, d.mode, st));
-    RADMMM_TRY(signal(st, sd, 0));            // DP and every DQ_i are ready
-    //    ... bias / weight gradients on the side
-    RADMMM_TRY(colsum(d.mode, s.DP, g, d.C, 1, 0, gr->end_b, sd));
-    {   // dW_end = dP^T (sum_i s_i): one weight-grad GEMM accumulating over the L stored s_i
+    RADMMM_TRY(launch_gemm(a, d.mode, mc));
+    //    ... DP and every DQ_i are ready: the end conv and all L res-skip convs can take their weight gradients now
+    for (int l = 0; l < (forked ? kLanes : 0); ++l) RADMMM_TRY(ready(lane_stream(l)));
+    {
+        cudaStream_t sd = lane(3);
+        RADMMM_TRY(colsum(d.mode, s.DP, g, d.C, 1, 0, gr->end_b, sd));
+        // dW_end = dP^T (sum_i s_i): one weight-grad GEMM accumulating over the L stored s_i
         GemmArgs wa;
         init_args(wa, d, f->lens, EPI_WGRAD, H);
         wa.wgrad = 2;
@@ -361,69 +405,79 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         RADMMM_CUDA(cudaMemsetAsync(gr->end_w, 0, sizeof(float) * (size_t)d.C * H, sd));
         RADMMM_TRY(launch_gemm(wa, d.mode, sd));
     }
+    for (int i = L - 1; i >= 0; --i) {       // res-skip conv i (needs DQ_i only): lanes 0 and 1
+        cudaStream_t sd = lane(i & 1);
+        RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], sd));
+        RADMMM_TRY(wgrad(d, f->lens, s.DQ[i], w.Hs[i + 1], H, H, 1, 1, s.dW_rs[i], H, 0, sd));
+        RADMMM_TRY(wn_bwd(s.dW_rs[i], H, 0, H, nullptr, 0, 0, f->rs_v[i], f->rs_g[i], p.norm_rs + (size_t)i * H, H, H, 1,
+                          gr->rs_v[i], gr->rs_g[i], sd));
+    }
     // 3. layers, last to first
     for (int i = L - 1; i >= 0; --i) {
         const int dil = 1 << i;
-        const int cur = i & 1, nxt = (i + 1) & 1;
-        // side: res-skip conv i (needs DQ_i, available since event 0)
-        RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], sd));
-        RADMMM_TRY(wgrad(d, f->lens, s.DQ[i], w.Hs[i + 1], H, H, 1, 1, s.dW, H, 0, sd));
-        RADMMM_TRY(wn_bwd(s.dW, H, 0, H, nullptr, 0, 0, f->rs_v[i], f->rs_g[i], p.norm_rs + (size_t)i * H, H, H, 1,
-                          gr->rs_v[i], gr->rs_g[i], sd));
         // chain: dh_{i+1} = Wrs_i^T dq_i + sum_taps Win_{i+1,j}^T dacc_{i+1}[r - (j-2) d_{i+1}]  -> dacc_i
-        // DACC[cur] was last read by the side stream for layer i+2: wait until it is done with it
-        if (forked && i + 2 <= L - 1) RADMMM_CUDA(cudaStreamWaitEvent(st, side_event(8 + cur), 0));
         init_args(a, d, f->lens, EPI_DH, H);
         add_seg(a, s.DQ[i], sub_mode(p.WrsT, (long long)i * p.HH, d.es), H, 0);
         if (i < L - 1)
             for (int j = 0; j < 5; ++j)
-                add_seg(a, s.DACC[nxt], sub_mode(p.WinT, ((long long)(i + 1) * 5 + j) * p.HH, d.es), H, -(j - 2) * (dil * 2));
+                add_seg(a, s.DACC[i + 1], sub_mode(p.WinT, ((long long)(i + 1) * 5 + j) * p.HH, d.es), H, -(j - 2) * (dil * 2));
         a.epi.h = w.Hs[i + 1];
         a.epi.dilation = dil;
-        a.epi.out0 = s.DACC[cur];
-        RADMMM_TRY(launch_gemm(a, d.mode, st));
-        RADMMM_TRY(signal(st, sd, 1 + cur));  // dacc_i ready
-        // side: dilated conv i: bias (un-ratio'd), weights
-        RADMMM_TRY(colsum(d.mode, s.DACC[cur], g, H, dil, 1, gr->in_b[i], sd));
-        RADMMM_TRY(wgrad(d, f->lens, s.DACC[cur], w.Hs[i], H, H, 5, dil, s.dW, H, p.HH, sd));
-        RADMMM_TRY(wn_bwd(s.dW, H, p.HH, H, nullptr, 0, 0, f->in_v[i], f->in_g[i], p.norm_in + (size_t)i * H, H, H, 5,
+        a.epi.out0 = s.DACC[i];
+        RADMMM_TRY(launch_gemm(a, d.mode, mc));
+        // dilated conv i: bias (un-ratio'd) and weights on lanes 2 and 3
+        cudaStream_t sd = lane(2 + (i & 1));
+        RADMMM_TRY(ready(sd));                // dacc_i ready
+        RADMMM_TRY(colsum(d.mode, s.DACC[i], g, H, dil, 1, gr->in_b[i], sd));
+        RADMMM_TRY(wgrad(d, f->lens, s.DACC[i], w.Hs[i], H, H, 5, dil, s.dW_in[i], H, p.HH, sd));
+        RADMMM_TRY(wn_bwd(s.dW_in[i], H, p.HH, H, nullptr, 0, 0, f->in_v[i], f->in_g[i], p.norm_in + (size_t)i * H, H, H, 5,
                           gr->in_v[i], gr->in_g[i], sd));
-        if (forked) RADMMM_CUDA(cudaEventRecord(side_event(8 + cur), sd));   // side is done reading DACC[cur]
     }
-    // 4. dh0 (masked) from layer 0's dilated conv; it reuses DACC[1] (last read by the side stream for layer 1 / 3)
-    if (forked && L >= 2) RADMMM_CUDA(cudaStreamWaitEvent(st, side_event(8 + 1), 0));
+    // 4. dh0 (masked) from layer 0's dilated conv
     init_args(a, d, f->lens, EPI_DH0, H);
     for (int j = 0; j < 5; ++j) add_seg(a, s.DACC[0], sub_mode(p.WinT, (long long)j * p.HH, d.es), H, -(j - 2));
-    a.epi.out0 = s.DACC[1];
-    RADMMM_TRY(launch_gemm(a, d.mode, st));
-    const ActMat& DH0 = s.DACC[1];
-    RADMMM_TRY(signal(st, sd, 3));            // dh0 ready
-    // 5. start conv: weight / bias gradients on the side, input gradients on the chain
-    RADMMM_TRY(colsum(d.mode, DH0, g, H, 1, 0, gr->start_b, sd));
-    float* dWz = s.dW;
-    float* dWc = s.dW + (size_t)H * d.Kz;
-    RADMMM_TRY(wgrad(d, f->lens, DH0, w.Z0, H, d.Kz, 1, 1, dWz, d.Kz, 0, sd));
-    RADMMM_TRY(wgrad(d, f->lens, DH0, ctx, H, d.Dp, 1, 1, dWc, d.Dp, 0, sd));
-    RADMMM_TRY(wn_bwd(dWz, d.Kz, 0, d.Ch, dWc, d.Dp, 0, f->start_v, f->start_g, p.norm_start, H, d.Ch + d.D, 1,
-                      gr->start_v, gr->start_g, sd));
+    a.epi.out0 = s.DACC[L];
+    RADMMM_TRY(launch_gemm(a, d.mode, mc));
+    const ActMat& DH0 = s.DACC[L];
+    // 5. start conv: weight / bias gradients on lane 0, input gradients on the chain
+    {
+        cudaStream_t sd = lane(0);
+        RADMMM_TRY(ready(sd));                // dh0 ready
+        RADMMM_TRY(colsum(d.mode, DH0, g, H, 1, 0, gr->start_b, sd));
+        float* dWz = s.dW_start;
+        float* dWc = s.dW_start + (size_t)H * d.Kz;
+        RADMMM_TRY(wgrad(d, f->lens, DH0, w.Z0, H, d.Kz, 1, 1, dWz, d.Kz, 0, sd));
+        RADMMM_TRY(wgrad(d, f->lens, DH0, ctx, H, d.Dp, 1, 1, dWc, d.Dp, 0, sd));
+        RADMMM_TRY(wn_bwd(dWz, d.Kz, 0, d.Ch, dWc, d.Dp, 0, f->start_v, f->start_g, p.norm_start, H, d.Ch + d.D, 1,
+                          gr->start_v, gr->start_g, sd));
+    }
     init_args(a, d, f->lens, EPI_DZ0, d.Ch);
     add_seg(a, DH0, p.WzT, H, 0);
     a.epi.cf_out = dz_mid; a.epi.cf_C = d.C; a.epi.cf_c0 = 0; a.epi.accumulate = 1;
-    RADMMM_TRY(launch_gemm(a, d.mode, st));
+    RADMMM_TRY(launch_gemm(a, d.mode, mc));
     init_args(a, d, f->lens, EPI_DCTX, d.Dp);
     add_seg(a, DH0, p.WcT, H, 0);
     a.epi.f32_out = dctx_rows; a.epi.f32_ld = d.Dp;
-    RADMMM_TRY(launch_gemm(a, d.mode, st));
+    RADMMM_TRY(launch_gemm(a, d.mode, mc));
     // 6. invertible 1x1 conv: dz_in = W^T dz_mid, dW = sum dz_mid (z_in - mean)^T over valid frames
     const long long bs = (long long)d.C * d.Tp;
     if (f->W_T) {
         RADMMM_REQUIRE(gr->W != nullptr, "flow_backward: dW output missing");
-        RADMMM_TRY(inv1x1(dz_mid, bs, f->W_T, nullptr, nullptr, dz_in, bs, d.B, d.C, d.C, d.Tp, st));
-        RADMMM_TRY(inv1x1_wgrad(dz_mid, z_in, f->mean, f->lens, gr->W, d.B, d.C, d.Tp, st));
+        cudaStream_t sd = lane(1);
+        RADMMM_TRY(ready(sd));                // dz_mid complete: dW of the 1x1 conv goes to a lane
+        RADMMM_TRY(inv1x1_wgrad(dz_mid, z_in, f->mean, f->lens, gr->W, d.B, d.C, d.Tp, sd));
+        RADMMM_TRY(inv1x1(dz_mid, bs, f->W_T, nullptr, nullptr, dz_in, bs, d.B, d.C, d.C, d.Tp, mc));
     } else {
         RADMMM_REQUIRE(dz_in == dz_mid, "flow_backward: without W_T, dz_in must alias dz_mid");
     }
-    RADMMM_TRY(signal(sd, st, 4));            // join: everything the caller sees is ordered on `st`
+    // join: everything the caller sees is ordered on `st` (the scratch buffers are shared by all flow steps)
+    if (forked) {
+        for (int l = 0; l <= kLanes; ++l) {
+            cudaEvent_t e = lane_event(n_ev++);
+            RADMMM_CUDA(cudaEventRecord(e, l < kLanes ? lane_stream(l) : mc));
+            RADMMM_CUDA(cudaStreamWaitEvent(st, e, 0));
+        }
+    }
     return RADMMM_OK;
 }
 

@@ -10,6 +10,7 @@ C ABI (see common.FlowStepFunction); ``precision`` selects the contraction path:
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -151,14 +152,16 @@ class RADMMMFlow(RADMMM):
         _lstm._wcache.clear()
 
     def _prepare_weights_async(self, device):
-        """Weight preparation of all flows depends only on the parameters, so it is forked onto the side stream and
-        overlaps the (latency-bound) context LSTM; returns the event the flow steps must wait for."""
-        side_handle = common._side_stream(device)
-        if not side_handle:
+        """Weight preparation of all flows depends only on the parameters, so it is forked onto its own stream and
+        overlaps the (latency-bound) context LSTM; returns one event per flow step (flow i waits for its own event only,
+        so the flow chain starts while later flows are still being prepared)."""
+        prep = common._prep_stream(device)
+        if prep is None:
             return None
-        side = common._side_streams[device.index]
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
+        main_stream = torch.cuda.current_stream(device)
+        prep.wait_stream(main_stream)
+        events = []
+        with torch.cuda.stream(prep):
             for fs in self.flows:
                 tfn = fs.coupling_tfn
                 if hasattr(tfn, "affine_param_predictor"):
@@ -167,11 +170,17 @@ class RADMMMFlow(RADMMM):
                 # them here too (a dozen tiny kernels per flow, forward and backward) instead of on the flow chain
                 conv = fs.invtbl_conv
                 ready = (not hasattr(conv, "maybe_initialize")) or getattr(conv, "_init_seen", False) or not self.training
-                if not fs.use_spline and ready:
-                    fs._pre_W = (conv._weight(), conv.log_det())
-            ev = torch.cuda.Event()
-            ev.record(side)
-        return ev
+                if not fs.use_spline and ready and os.environ.get("RADMMM_B200_PRE_W", "1") != "0":
+                    W, log_det = conv._weight(), conv.log_det()
+                    # allocated on the preparation stream, consumed by kernels on the main stream: tell the caching
+                    # allocator, or the blocks can be handed out again (to this stream) while those kernels are pending
+                    W.record_stream(main_stream)
+                    log_det.record_stream(main_stream)
+                    fs._pre_W = (W, log_det)
+                ev = torch.cuda.Event()
+                ev.record(prep)
+                events.append(ev)
+        return events
 
     def forward(self, mel, spk_vecs, context, out_lens, f0=None, energy_avg=None, accent_vecs=None):
         lengths = out_lens.lengths if hasattr(out_lens, "lengths") else out_lens
@@ -182,9 +191,9 @@ class RADMMMFlow(RADMMM):
         lens_g = torch.div(lengths, self.n_group_size, rounding_mode="floor")
         seq = _Lens(lens_g)
         z_out, log_s_list, log_det_W_list = [], [], []
-        if prep_done is not None:
-            torch.cuda.current_stream(mel.device).wait_event(prep_done)
         for i, flow_step in enumerate(self.flows):
+            if prep_done is not None:
+                torch.cuda.current_stream(mel.device).wait_event(prep_done[i])
             if i in self.exit_steps:
                 z_out.append(mel[:, :self.n_early_size])
                 mel = mel[:, self.n_early_size:]

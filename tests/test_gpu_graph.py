@@ -47,9 +47,14 @@ def test_graphed_step_matches_eager(precision):
         torch.cuda.synchronize()
         # atomics in the split-K weight-gradient reductions make the last bits order-dependent
         close(loss, ref[0], 1e-6, rtol=1e-6, what="graph loss")
+        bad = []
         for n, p in dec.named_parameters():
             if n in ref[1]:
-                close(p.grad, ref[1][n], 1e-5, rtol=2e-4, what="graph grad " + n)
+                g = ref[1][n]
+                e = (p.grad - g).abs().max().item()
+                if e > 1e-4 + 2e-4 * g.abs().max().item():
+                    bad.append(f"{n}: err {e:.3e} (max |g| {g.abs().max().item():.3e})")
+        assert not bad, "graph gradients differ from eager:\n" + "\n".join(bad)
     # a parameter update between replays must be seen (weight preparation is inside the graph)
     with torch.no_grad():
         for p in dec.parameters():
@@ -61,4 +66,4 @@ def test_graphed_step_matches_eager(precision):
     assert abs(float(loss_new) - float(ref_a[0])) > 1e-4
     close(loss_new, ref_new[0], 1e-6, rtol=1e-6, what="graph loss after update")
     for n, g in ref_new[1].items():
-        close(grads_graph[n], g, 1e-5, rtol=2e-4, what="graph grad after update " + n)
+        close(grads_graph[n], g, 1e-4, rtol=2e-4, what="graph grad after update " + n)

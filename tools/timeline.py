@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--frames", type=int, default=800)
     ap.add_argument("--out", default="gpurun_out/timeline")
     ap.add_argument("--infer", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="profile one replay of the CUDA-graphed step instead")
     args = ap.parse_args()
     from radmmm_b200 import decoders, loss as L, synthetic as syn
     from radmmm_b200.common import SequenceLength
@@ -42,6 +43,13 @@ def main():
     for _ in range(4):
         step()
     torch.cuda.synchronize()
+    if args.graph:
+        from radmmm_b200.graphs import GraphedTrainStep
+        gstep = GraphedTrainStep(dec, bt)
+        for _ in range(3):
+            gstep(bt)
+        torch.cuda.synchronize()
+        step = lambda: gstep(bt)      # noqa: E731
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize()
