@@ -343,8 +343,7 @@ def run_ours(args):
                 "executed_tflops": kfl[1] / (kms[1] * 1e9)}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     value = world * valid_frames / (ms * 1e-3)
     e2e_value = world * valid_frames / (ms_e2e * 1e-3)
@@ -383,8 +382,21 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample()
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank teardown.  destroy_process_group() can block for minutes when CUDA graphs that captured NCCL
+    collectives are still alive, so every rank synchronises, meets at a last barrier and leaves without running the
+    NCCL / graph destructors."""
+    if world <= 1:
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
