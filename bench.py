@@ -31,6 +31,7 @@ UNIT = "mel-frames/s"
 FWD_MFLOP_PER_FRAME = 218.8      # BASELINE.md section 3 (8 flows + context LSTM)
 TRAIN_MFLOP_PER_FRAME = 656.4    # 3 x forward (fwd + dgrad + wgrad; recompute not counted)
 K5_FLOP_PER_GROUPED_FRAME = 2 * 1024 * 1024 * 5      # one dilated k=5 layer (the dominant kernel), per grouped frame
+K5_DRAM_BYTES_NCU = 17337344                         # measured once with ncu --set full (see roofline.traffic_note)
 
 
 def peaks():
@@ -131,38 +132,22 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def cpu_baseline_sample(seconds_budget=25.0):
-    """Bounded CPU run of the oracle port on rank 0 (reported baseline, not the target)."""
-    from oracle import flow as of
-    from radmmm_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    batch, frames = 2, 256
-    cfg = of.DecoderConfig.radmmm()
-    sd = syn.synthetic_state_dict()
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
-              if v.dtype == torch.float32 and not any(s in k for s in ("invtbl_conv.p", "lower_diag", "input_mean"))}
-    sdp = dict(sd)
-    sdp.update(params)
-    lstm = of.build_context_lstm(sd, cfg)
-    bt = syn.synthetic_batch(batch, frames, tag="bench.ref")
-    valid = int(bt["out_lens"].sum())
-    times = []
-    t_start = time.perf_counter()
-    for i in range(4):
-        for p in params.values():
-            p.grad = None
-        t0 = time.perf_counter()
-        out = of.decoder_forward(sdp, cfg, bt["mel"], bt["spk_vecs"], bt["context"], bt["out_lens"], bt["f0"],
-                                 bt["energy_avg"], bt["accent_vecs"], lstm=lstm)
-        loss, _ = of.flow_loss(out["z_mel"], out["log_det_W_list"], out["log_s_list"], bt["out_lens"] // 2)
-        loss.backward()
-        times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_start > seconds_budget and i >= 1:
-            break
-    dt = min(times[1:]) if len(times) > 1 else times[0]
-    return {"value": valid / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle port train step, {batch} x {frames} frames ({valid} valid), fp32, best of {len(times) - 1 or 1} after warm-up"}
+def cpu_baseline_sample(timeout_s=240.0):
+    """Bounded CPU run of the oracle port on rank 0 (reported baseline, not the target).  Runs in a FRESH process
+    (`bench.py --impl reference`, two timed steps of 2 x 256 frames): the CPU port shares nothing with the CUDA process
+    (thread pools, allocator, autograd device threads), and a hard timeout keeps the default run bounded."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                             capture_output=True, text=True, timeout=timeout_s, env=env)
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        cb = line["cpu_baseline"]
+        cb["sample"] += ", 2 timed steps after 1 warm-up, separate process"
+        return cb
+    except Exception as exc:
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": f"CPU sample failed: {type(exc).__name__}: {str(exc)[:200]}"}
 
 
 # ------------------------------------------------------------------------------------------------------- our arm
@@ -337,7 +322,10 @@ def run_ours(args):
         achieved = algo_flops / (per_launch_ms * 1e-3) / 1e12
         peak = pk["bf16_burst"] / (3.0 if precision == "bf16x3" else 1.0)
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EPI_IN> (dilated k=5 conv forward)", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": K5_DRAM_BYTES_NCU if (precision == "bf16" and batch == 8 and frames == 800) else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                "(profiles/r1_ncu_full_k5_s12.md); algorithmic bytes A 6.8 MB + W 10.5 MB + out 6.8 MB",
                 "peak_source": pk["source"] + (", bf16 burst / 3 for the 3-pass split" if precision == "bf16x3" else ", bf16 burst"),
                 "per_launch_ms": per_launch_ms, "algorithmic_flops_per_launch": algo_flops,
                 "executed_tflops": kfl[1] / (kms[1] * 1e9)}
@@ -352,8 +340,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (hi/lo split, fp32-grade)", "fp32": "f32"}[precision], "data": "synthetic",
-        "config": {"workload": "RADMMM decoder train step: forward + flow NLL + backward (+ grad all-reduce), "
-                               "configs/RADMMM_model_config.yaml (8 flows, 219M params)",
+        "config": {"workload": "RADMMM decoder train step: weight norm of all 219M params + forward + flow NLL + backward "
+                               "(+ grad all-reduce), configs/RADMMM_model_config.yaml (8 flows), B=8 x T=800 per GPU, "
+                               "replayed as one CUDA graph",
                    "batch_per_gpu": batch, "frames": frames, "valid_frames_per_gpu": valid_frames,
                    "padded_frames_per_gpu": batch * frames, "precision": precision,
                    "l2": "working set (0.9 GB prepared weights + ~1 GB activations per step) exceeds the 126 MB L2",

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libradmmm_b200.so")
+LIB_PATH = os.environ.get("RADMMM_B200_LIB") or os.path.join(_HERE, "libradmmm_b200.so")   # env override: A/B builds
 MAX_LAYERS = 8
 ROW_GAP = 16
 MODE_F32, MODE_BF16, MODE_BF16X3 = 0, 1, 2

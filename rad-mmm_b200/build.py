@@ -16,6 +16,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
+# gemm_tc.cu: 128 registers per thread (384 threads -> 48 K of the SM's 64 K registers) and at most 5 pipeline stages
+# (~180 KB of shared memory) so that one small CTA of a memory-bound helper kernel (weight-norm backward, bias column sums,
+# 1x1 convs ...) can be co-resident with a contraction CTA instead of waiting for a free SM.
+PER_SOURCE_FLAGS = {"gemm_tc.cu": os.environ.get("RADMMM_B200_TC_FLAGS", "").split()}
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for root, _, files in os.walk(CSRC):
@@ -25,6 +31,7 @@ def _digest() -> str:
     with open(os.path.join(os.path.dirname(HERE), "include", "radmmm_b200.h"), "rb") as fh:
         h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(PER_SOURCE_FLAGS.items())).encode())
     return h.hexdigest()
 
 
@@ -38,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *PER_SOURCE_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(r.stdout + r.stderr)

@@ -198,7 +198,10 @@ struct Cfg {
     static constexpr int b_rows = BN / CL;                      // cta_group::2: each CTA of the pair holds half of B's N extent
     static constexpr int b_bytes = b_rows * BK * 2;
     static constexpr int stage_bytes = planes * (a_bytes + b_bytes);
-    static constexpr int stages = (200 * 1024) / stage_bytes > 8 ? 8 : (200 * 1024) / stage_bytes;
+#ifndef RADMMM_TC_SMEM_KB
+#define RADMMM_TC_SMEM_KB 200
+#endif
+    static constexpr int stages = (RADMMM_TC_SMEM_KB * 1024) / stage_bytes > 8 ? 8 : (RADMMM_TC_SMEM_KB * 1024) / stage_bytes;
     static constexpr int tmem_cols = 2 * BN;      // 256 or 512: powers of two
     static constexpr int stage_tile_bytes = 32 * kStageLd * 2;     // epilogue staging tile, per epilogue warp
     static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * stage_tile_bytes;
@@ -210,8 +213,13 @@ struct Cfg {
 //          128 accumulator rows in its own TMEM.  Per-CTA shared-memory traffic per MMA drops from 48 KB to 32 KB
 //          (BN = 256), which buys 6 pipeline stages instead of 4 -- the 1-CTA kernel was TMA-latency bound with the
 //          tensor pipe 57 % active (profiles/).
+#ifdef RADMMM_TC_MAXNREG
+#define RADMMM_TC_BOUNDS __maxnreg__(RADMMM_TC_MAXNREG)
+#else
+#define RADMMM_TC_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <int MODE, int KIND, int BN, bool WGRAD, int CL>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
+__global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams P) {
     using C = Cfg<MODE, BN, CL>;
     static_assert(CL == 1 || CL == 2, "cluster size");
     const uint32_t crank = (CL == 2) ? cluster_rank() : 0u;

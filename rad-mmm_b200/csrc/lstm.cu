@@ -13,6 +13,7 @@
 // Both directions run concurrently; variable lengths follow the packed semantics (the reverse direction of sequence b
 // starts at frame len_b-1; frames beyond len_b stay zero).  All arithmetic fp32.
 // Latency-bound by construction: T' dependent steps of (17 KB exchange + barrier); no roofline applies.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -36,9 +37,16 @@ struct LstmParams {
     float* xchg;              // exchange buffers
     unsigned int* counters;   // [2] per-direction barrier counters (zeroed before launch)
     int B, Bp, Tp, H, pitch, G;
+    int probe;                // tools/lstm_probe.py: 1 skip the mat-vec, 2 skip the exchange reload, 4 skip the barrier
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Gate non-linearities on the MUFU exponential (abs error ~1e-7, far inside the fp32 parity tolerance); tanh through
+// exp(-2|x|) so that it never overflows.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) {
+    const float t = __expf(-2.0f * fabsf(x));
+    return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
 
 // L2 -> shared copy of n4 float4 with up to BATCH loads per thread in flight (the exchange buffers were just written by
 // the other CTAs, so every load is an L2 round trip: issuing them back to back instead of load/store/load/store cuts the
@@ -110,6 +118,7 @@ __device__ __forceinline__ float reduce8(float* v, int lane) {       // 8 values
     return r;
 }
 
+template <bool ONE>      // ONE: a single sequence tile (B <= 8): per-tile state lives in registers, not local memory
 __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
     extern __shared__ float sm[];
     const int H = p.H, Bp = p.Bp;
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
     for (int b = 0; b < p.B; ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
     __syncthreads();
 
-    const int n_tiles = Bp / BT;
+    const int n_tiles = ONE ? 1 : Bp / BT;
     float c_state[8];                                       // supports Bp <= 64
 #pragma unroll
     for (int i = 0; i < 8; ++i) c_state[i] = 0.0f;
@@ -145,19 +154,37 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
         p.out[k.o * 2 * H + (size_t)dir * H + unit] = k.h;
     };
 
+    // lengths are loop invariant; with a single sequence tile (B <= 8) the input projection of step s+1 is fetched
+    // before the barrier of step s, so its DRAM latency never sits on the step's critical path
+    const int my_len0 = (lane < 8 && (lane & 7) < p.B) ? min(p.lens[lane & 7], p.Tp) : 0;
+    auto fetch_xp = [&](int s, int bb, int len, float* xp) {
+        xp[0] = xp[1] = xp[2] = xp[3] = 0.f;
+        if (lane < 8 && bb < p.B && s < len) {
+            const int t = dir ? len - 1 - s : s;
+            const long long r = (long long)bb * p.pitch + t;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xp[g] = __ldg(p.xproj + r * 8 * H + (size_t)dir * 4 * H + g * H + unit);
+        }
+    };
+    float xp_next[4];
+    if (ONE) fetch_xp(0, lane & 7, my_len0, xp_next);
+
     for (int s = 0; s < tmax; ++s) {
 #pragma unroll 1
         for (int bt = 0; bt < n_tiles; ++bt) {
-            // prefetch this step's input projection for (unit, sequence bt*8 + lane) while the mat-vec runs
             const int bb = bt * BT + (lane & 7);
-            int len = 0, t = 0;
-            if (lane < 8 && bb < p.B) { len = min(p.lens[bb], p.Tp); t = dir ? len - 1 - s : s; }
+            int len = my_len0, t = 0;
+            if (!ONE) len = (lane < 8 && bb < p.B) ? min(p.lens[bb], p.Tp) : 0;
+            if (lane < 8 && bb < p.B) t = dir ? len - 1 - s : s;
             const bool active = lane < 8 && bb < p.B && s < len;
             const long long r = (long long)bb * p.pitch + t;
-            float xp[4] = {0.f, 0.f, 0.f, 0.f};
-            if (active) {
+            float xp[4];
+            if (ONE) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) xp[g] = __ldg(p.xproj + r * 8 * H + (size_t)dir * 4 * H + g * H + unit);
+                for (int g = 0; g < 4; ++g) xp[g] = xp_next[g];
+                fetch_xp(s + 1, bb, len, xp_next);           // consumed after the next barrier
+            } else {
+                fetch_xp(s, bb, len, xp);
             }
             float acc[32];
 #pragma unroll
@@ -165,7 +192,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
             const float4* ha = hs4 + (size_t)(2 * bt) * H;      // sequences bt*8 .. +3
             const float4* hb = ha + H;                           // sequences bt*8+4 .. +7
 #pragma unroll 2
-            for (int k = lane; k < H; k += 32) {
+            for (int k = lane; k < ((p.probe & 1) ? 0 : H); k += 32) {
                 const float4 w4 = Wt[w * H + k];
                 const float4 h0 = ha[k], h1 = hb[k];
                 const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
@@ -186,9 +213,9 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
                 float h = 0.0f;
                 if (active) {
                     const float gi = sigmoidf_(a_i + xp[0]), gf = sigmoidf_(a_f + xp[1]);
-                    const float gg = tanhf(a_g + xp[2]), go = sigmoidf_(a_o + xp[3]);
+                    const float gg = tanhf_(a_g + xp[2]), go = sigmoidf_(a_o + xp[3]);
                     const float c = gf * c_state[bt] + gi * gg;
-                    h = go * tanhf(c);
+                    h = go * tanhf_(c);
                     c_state[bt] = c;
                     // publish h; the copies kept for the backward pass (6 stores to HBM-homed lines) are deferred past the
                     // barrier so that the release fence only has this one store to wait for
@@ -204,15 +231,17 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmParams p) {
             }
         }
         if (s + 1 == tmax) { store_kept(keep); break; }
-        dir_barrier(p.counters + dir, (unsigned int)p.G * (s + 1));
+        if (!(p.probe & 4)) dir_barrier(p.counters + dir, (unsigned int)p.G * (s + 1));
+        else __syncthreads();
         const float4* src = reinterpret_cast<const float4*>(xbuf + (size_t)(s & 1) * Bp * H);
-        copy_f4_batched<5>(hs4, src, n4, tid, [](int i) { return i; });
+        if (!(p.probe & 2)) copy_f4_batched<5>(hs4, src, n4, tid, [](int i) { return i; });
         store_kept(keep);
         keep.valid = false;
         __syncthreads();
     }
 }
 
+template <bool ONE>
 __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
     extern __shared__ float sm[];
     const int H = p.H, Bp = p.Bp, H4 = 4 * p.H;
@@ -229,7 +258,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
     int tmax = 0;
     for (int b = 0; b < p.B; ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
     __syncthreads();
-    const int n_tiles = Bp / BT;
+    const int n_tiles = ONE ? 1 : Bp / BT;
     float dh_rec[8], dc_next[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dh_rec[i] = 0.0f; dc_next[i] = 0.0f; }
@@ -240,9 +269,10 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
 
     // saved values of (unit, sequence lane&7) for one step; prefetched one step ahead when the batch is a single tile
     struct Saved { float gi, gf, gg, go, c, c_prev, dout; };
+    const int my_len0 = ((lane & 7) < p.B) ? min(p.lens[lane & 7], p.Tp) : 0;      // lengths are loop invariant
     auto load_saved = [&](int s, int bb, Saved& v) -> bool {
-        int len = 0;
-        if (bb < p.B) len = min(p.lens[bb], p.Tp);
+        int len = my_len0;
+        if (!ONE) len = (bb < p.B) ? min(p.lens[bb], p.Tp) : 0;
         const bool active = bb < p.B && s >= 0 && s < len;
         if (active) {
             const int t = dir ? len - 1 - s : s;
@@ -274,8 +304,8 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
         for (int bt = 0; bt < n_tiles; ++bt) {
             const int bb = bt * BT + (lane & 7);
             if (lane < 8 && bb < Bp) {
-                int len = 0;
-                if (bb < p.B) len = min(p.lens[bb], p.Tp);
+                int len = my_len0;
+                if (!ONE) len = (bb < p.B) ? min(p.lens[bb], p.Tp) : 0;
                 Saved v = pre;
                 const bool active = (n_tiles == 1) ? pre_active : load_saved(s, bb, v);
                 float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
@@ -285,7 +315,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(const LstmParams p) {
                     r = (long long)bb * p.pitch + t;
                     const float gi = v.gi, gf = v.gf, gg = v.gg, go = v.go, c = v.c, c_prev = v.c_prev;
                     const float dh = v.dout + dh_rec[bt];
-                    const float tc = tanhf(c);
+                    const float tc = tanhf_(c);
                     const float dc = dh * go * (1.0f - tc * tc) + dc_next[bt];
                     d_o = dh * tc * go * (1.0f - go);
                     d_i = dc * gg * gi * (1.0f - gi);
@@ -371,6 +401,7 @@ static int lstm_common(LstmParams& p, const int* lens, int B, int Tp, int H, voi
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     RADMMM_REQUIRE(2 * p.G <= sms, "lstm: needs %d co-resident CTAs but the device has %d SMs", 2 * p.G, sms);
+    { const char* e = getenv("RADMMM_B200_LSTM_PROBE"); p.probe = e ? atoi(e) : 0; }
     return RADMMM_OK;
 }
 
@@ -384,12 +415,14 @@ int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, con
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d, B=%d)", smem, H, B);
     static size_t smem_set_fwd = 0;
     if (smem > smem_set_fwd) {
-        RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set_fwd = smem;
     }
     RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
     void* args[] = {&p};
-    RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
+    RADMMM_CUDA(cudaLaunchCooperativeKernel(p.Bp == BT ? (void*)lstm_fwd_kernel<true> : (void*)lstm_fwd_kernel<false>,
+                                            dim3(2 * p.G), dim3(NT), args, smem, st));
     count_launch();
     return RADMMM_OK;
 }
@@ -405,12 +438,14 @@ int lstm_backward(const float* dout, const float* gates, const float* cstate, co
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d)", smem, H);
     static size_t smem_set_bwd = 0;
     if (smem > smem_set_bwd) {
-        RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set_bwd = smem;
     }
     RADMMM_CUDA(cudaMemsetAsync(p.counters, 0, 256, st));
     void* args[] = {&p};
-    RADMMM_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_kernel, dim3(2 * p.G), dim3(NT), args, smem, st));
+    RADMMM_CUDA(cudaLaunchCooperativeKernel(p.Bp == BT ? (void*)lstm_bwd_kernel<true> : (void*)lstm_bwd_kernel<false>,
+                                            dim3(2 * p.G), dim3(NT), args, smem, st));
     count_launch();
     return RADMMM_OK;
 }
