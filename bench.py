@@ -291,7 +291,7 @@ def run_ours(args):
 
     for _ in range(3):
         infer_step()
-    ms_infer = timed(infer_step, max(5, args.steps))
+    ms_infer_eager = timed(infer_step, max(5, args.steps))
     dec.train()
 
     # ---- per-kernel roofline of the dominant kernel (dilated k=5 conv forward, tcgen05): events around every launch
@@ -307,6 +307,21 @@ def run_ours(args):
     kfl = (ctypes.c_double * n_tags)()
     lib.radmmm_profile_collect(n_tags, cnt, kms, kfl)
     lib.radmmm_profile_enable(0)
+    # ---- graphed inference LAST: a failed capture must not be able to disturb any other number
+    dec.eval()
+    ms_infer, infer_graph_error = ms_infer_eager, None
+    if not args.eager and world == 1:          # inference does not shard: replicas only, measured on one GPU
+        try:
+            from radmmm_b200.graphs import GraphedInfer
+            ex = {"spk_vec": resident["spk_vecs"], "txt_enc": txt_enc, "dur": dur, "f0": resident["f0"],
+                  "energy_avg": resident["energy_avg"], "out_lens": lens_dev}
+            ginfer = GraphedInfer(dec, ex, sigma=0.8)
+            for _ in range(3):
+                ginfer(ex)
+            ms_infer = timed(lambda: ginfer(ex), max(5, args.steps))
+        except Exception as exc:
+            infer_graph_error = f"{type(exc).__name__}: {exc}"[:300]
+    dec.train()
     names = {0: "start", 1: "k5_conv_fwd", 2: "res_skip_fwd", 3: "end", 4: "dgrad_end", 5: "dgrad_layer", 6: "dgrad_h0",
              7: "dgrad_z0", 8: "dgrad_ctx", 17: "wgrad_1x1", 21: "wgrad_k5"}
     kernels = {names.get(i, f"tag{i}"): {"launches": cnt[i], "ms": round(kms[i], 4),
@@ -351,7 +366,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4},
         "infer": {"value": world * valid_frames / (ms_infer * 1e-3), "unit": UNIT, "ms_per_call": ms_infer,
-                  "note": "RADMMMFlow.infer (length regulation + context LSTM + 8 inverse flow steps), sigma 0.8",
+                  "eager_ms_per_call": ms_infer_eager, "graph_error": infer_graph_error,
+                  "note": "RADMMMFlow.infer (length regulation + context LSTM + 8 inverse flow steps), sigma 0.8, replayed "
+                          "as a CUDA graph (radmmm_b200.graphs.GraphedInfer); eager_ms_per_call = the plain module call",
                   "tensor_roofline_frac": (world * valid_frames / (ms_infer * 1e-3)) * FWD_MFLOP_PER_FRAME * 1e6 / 1e12 / world / pk["bf16_sustained"]},
         "gpu_launches": int(launches) if gstep is None else int(launches_per_eager_step) * args.steps,
         "graph": {"captured": gstep is not None, "error": graph_error,

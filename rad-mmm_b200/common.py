@@ -60,10 +60,12 @@ def _lens_of(seq_lens, batch: int, tp: int, device) -> torch.Tensor:
 class LengthRegulator(nn.Module):
     """common.py:208-237 without the per-token Python loops: x (B,T2,C), dur (B,T2) -> (B, max sum dur, C)."""
 
-    def forward(self, x: torch.Tensor, dur: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, dur: torch.Tensor, total: Optional[int] = None) -> torch.Tensor:
+        """``total`` (the padded output length) avoids the device sync when the caller already knows it."""
         dur = dur.long().clamp(min=0)
         ends = torch.cumsum(dur, dim=1)                               # (B,T2)
-        total = int(ends[:, -1].max().item())
+        if total is None:
+            total = int(ends[:, -1].max().item())
         frames = torch.arange(total, device=x.device)[None, :]        # (1,T)
         idx = torch.searchsorted(ends, frames.expand(x.shape[0], -1).contiguous(), right=True)
         valid = frames < ends[:, -1:]

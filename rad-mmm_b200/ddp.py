@@ -18,9 +18,13 @@ import torch.distributed as dist
 
 
 def default_bucket_key(name: str) -> str:
-    """Bucket assignment by parameter name: 'flows.<i>.' -> one bucket per flow step; everything else -> 'rest'."""
+    """Bucket assignment by parameter name: 'flows.<i>.coupling_tfn...' -> one bucket per flow step; everything else
+    -> 'rest'.  The invertible-1x1-conv parameters (flows.<i>.invtbl_conv.*, 3 x 160 x 160 floats) go to 'rest' as well:
+    their matrix is assembled once per step ahead of the flow chain (RADMMMFlow._prepare_weights_async), so their
+    gradients only materialise at the very END of the backward pass -- in the flow's own bucket they would hold its
+    all-reduce back until nothing is left to overlap it with."""
     parts = name.split(".")
-    if len(parts) > 2 and parts[0] == "flows" and parts[1].isdigit():
+    if len(parts) > 2 and parts[0] == "flows" and parts[1].isdigit() and parts[2] != "invtbl_conv":
         return "flow%s" % parts[1]
     return "rest"
 
@@ -109,9 +113,13 @@ class BucketedGradReducer:
 
     def _launch(self, b: dict):
         if self.world > 1:
+            op = dist.ReduceOp.SUM
             if self.average:
-                b["flat"].div_(self.world)
-            self._handles.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                if dist.get_backend(self.group) == "nccl":
+                    op = dist.ReduceOp.AVG              # averaged inside the collective: no extra pass over the bucket
+                else:
+                    b["flat"].div_(self.world)
+            self._handles.append(dist.all_reduce(b["flat"], op=op, group=self.group, async_op=True))
 
     def finish(self):
         """Wait for every outstanding all-reduce (call after ``backward``), then re-arm for the next step."""

@@ -205,13 +205,15 @@ class RADMMMFlow(RADMMM):
                 "context_w_spkvec": context_w_spkvec}
 
     def infer(self, spk_vec, txt_enc, sigma, dur=None, f0=None, energy_avg=None, out_lens=None, accent_vecs=None,
-              residual=None):
+              residual=None, max_frames: Optional[int] = None):
         """decoders.py:207-248.  ``residual`` (B, n_mel*g, T') optionally injects the latent sample instead of
         drawing it (the reference draws from the CUDA RNG, decoders.py:221-225); it is multiplied by nothing."""
         if out_lens is None:
             out_lens = dur.sum(1).long().to(txt_enc.device)
-        max_n_frames = int(out_lens.max())
-        txt_enc_time_expanded = self.length_regulator(txt_enc.transpose(1, 2), dur).transpose(1, 2)
+        # ``max_frames`` (the padded output length, e.g. f0.shape[1]) avoids two device syncs; radmmm_b200.graphs.GraphedInfer
+        # needs it because a captured call cannot read device values on the host
+        max_n_frames = int(out_lens.max()) if max_frames is None else int(max_frames)
+        txt_enc_time_expanded = self.length_regulator(txt_enc.transpose(1, 2), dur, total=max_frames).transpose(1, 2)
         context_w_spkvec = self.preprocess_context(txt_enc_time_expanded, spk_vec, out_lens, f0, energy_avg,
                                                    accent_vecs=accent_vecs)
         g = self.n_group_size

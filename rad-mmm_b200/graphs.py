@@ -78,3 +78,57 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+
+_INFER_KEYS = ("spk_vec", "txt_enc", "dur", "f0", "energy_avg", "out_lens", "accent_vecs", "residual")
+
+
+class GraphedInfer:
+    """``RADMMMFlow.infer`` (length regulation, context LSTM, 8 inverse flow steps, fold) for one fixed
+    (batch, tokens, max_frames) shape as a replayable CUDA graph.
+
+    ``example``: spk_vec (B,16), txt_enc (B,n_text,T2), dur (B,T2) long, f0 / energy_avg (B,max_frames), out_lens (B),
+    optional accent_vecs and ``residual`` (B, n_mel*g, max_frames//g: the latent sample; drawn inside the graph from the
+    CUDA generator when absent).  Durations and lengths are device data: one graph serves every utterance batch padded
+    to the captured shape.  Weights are taken as fixed (inference): the inverse 1x1 matrices are cached and the prepared
+    WN weights are not re-derived inside the graph.
+    """
+
+    def __init__(self, decoder, example: Dict[str, torch.Tensor], sigma: float = 0.8, warmup: int = 2):
+        dev = next(decoder.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.decoder, self.sigma = decoder, float(sigma)
+        self.static = {k: example[k].detach().to(dev).clone() for k in _INFER_KEYS if example.get(k) is not None}
+        self.max_frames = int(self.static["f0"].shape[1])
+        decoder.enable_inverse_cache()
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):
+                self._call()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.mel = self._call()
+
+    def _call(self) -> torch.Tensor:
+        st = self.static
+        with torch.no_grad():
+            return self.decoder.infer(st["spk_vec"], st["txt_enc"], self.sigma, dur=st["dur"], f0=st.get("f0"),
+                                      energy_avg=st.get("energy_avg"), out_lens=st["out_lens"],
+                                      accent_vecs=st.get("accent_vecs"), residual=st.get("residual"),
+                                      max_frames=self.max_frames)["mel"]
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Copy ``batch`` into the static buffers and replay; returns the static mel tensor (B, n_mel, max_frames)."""
+        for k, dst in self.static.items():
+            src = batch[k]
+            if src.shape != dst.shape:
+                raise RuntimeError(f"GraphedInfer: '{k}' has shape {tuple(src.shape)}, the graph was captured for "
+                                   f"{tuple(dst.shape)}")
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.mel

@@ -82,3 +82,13 @@ def test_bucketed_reducer_world2():
     ref = _single([110, 111])          # step 1 seeds of rank 0 and rank 1
     assert torch.allclose(out[0], out[1])
     assert torch.allclose(out[0], ref, atol=1e-6)
+
+
+def test_bucket_key_keeps_late_gradients_out_of_the_flow_buckets():
+    """The 1x1-conv parameters receive their gradients at the end of backward (their matrix is assembled ahead of the flow
+    chain): they must not delay a flow bucket's all-reduce."""
+    from radmmm_b200.ddp import default_bucket_key
+    assert default_bucket_key("flows.3.invtbl_conv.upper_diag") == "rest"
+    assert default_bucket_key("flows.0.invtbl_conv.upper") == "rest"
+    assert default_bucket_key("flows.7.coupling_tfn.affine_param_predictor.end.weight") == "flow7"
+    assert default_bucket_key("context_lstm.weight_ih_l0") == "rest"

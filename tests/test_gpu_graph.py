@@ -67,3 +67,36 @@ def test_graphed_step_matches_eager(precision):
     close(loss_new, ref_new[0], 1e-6, rtol=1e-6, what="graph loss after update")
     for n, g in ref_new[1].items():
         close(grads_graph[n], g, 1e-4, rtol=2e-4, what="graph grad after update " + n)
+
+
+def test_graphed_infer_matches_eager():
+    """GraphedInfer replays RADMMMFlow.infer; with an injected latent sample it must reproduce the eager call exactly,
+    and follow new durations / lengths written into its static buffers."""
+    from radmmm_b200.graphs import GraphedInfer
+    dec = _decoder("bf16x3").eval()
+    B, T2, T = 2, 8, 48
+
+    def example(tag, lens):
+        dur = torch.zeros(B, T2, dtype=torch.long)
+        for b, n in enumerate(lens):
+            dur[b] = n // T2
+            dur[b, 0] += n - (n // T2) * T2
+        ex = {"spk_vec": syn.hash_uniform(tag + ".spk", (B, 16), -1, 1), "txt_enc": syn.hash_uniform(tag + ".txt", (B, 520, T2), -1, 1),
+              "dur": dur, "f0": syn.hash_uniform(tag + ".f0", (B, T), 4.4, 6.4), "energy_avg": syn.hash_uniform(tag + ".en", (B, T), 0.5, 1.0),
+              "out_lens": torch.tensor(lens), "residual": syn.hash_uniform(tag + ".res", (B, 160, T // 2), -1, 1) * 0.7}
+        return {k: v.to(DEV) for k, v in ex.items()}
+
+    def eager(ex):
+        with torch.no_grad():
+            return dec.infer(ex["spk_vec"], ex["txt_enc"], 0.7, dur=ex["dur"], f0=ex["f0"], energy_avg=ex["energy_avg"],
+                             out_lens=ex["out_lens"], residual=ex["residual"], max_frames=T)["mel"].clone()
+
+    a, b = example("ginf.a", [48, 40]), example("ginf.b", [36, 48])
+    ref_a, ref_b = eager(a), eager(b)
+    g = GraphedInfer(dec, a, sigma=0.7)
+    for ref, ex in ((ref_a, a), (ref_b, b), (ref_a, a)):
+        mel = g(ex)
+        torch.cuda.synchronize()
+        assert mel.shape == ref.shape
+        for i, n in enumerate(ex["out_lens"].tolist()):
+            close(mel[i, :, :n // 2 * 2], ref[i, :, :n // 2 * 2], 1e-6, what="graphed infer mel")
