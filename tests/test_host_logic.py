@@ -90,3 +90,32 @@ def test_synthetic_data_is_deterministic():
     assert float(bt["mel"][1, :, int(bt["out_lens"][1]):].abs().sum()) == 0.0
     p = syn.hash_permutation("p", 16)
     assert sorted(p.tolist()) == list(range(16))
+
+
+def test_graph_helpers_refuse_cpu_modules():
+    """GraphedTrainStep / GraphedInfer are CUDA-graph wrappers: on a CPU module they must fail loudly (no fallback)."""
+    import pytest
+    import torch
+    from radmmm_b200 import decoders, graphs
+    dec = decoders.RADMMMFlow(n_accent_dim=8, n_text_dim=520, n_group_size=2, n_flows=1)
+    ex = {"mel": torch.zeros(1, 80, 8), "spk_vecs": torch.zeros(1, 16), "context": torch.zeros(1, 520, 8),
+          "out_lens": torch.tensor([8]), "f0": torch.zeros(1, 8), "energy_avg": torch.zeros(1, 8), "accent_vecs": torch.zeros(1, 8)}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        graphs.GraphedTrainStep(dec, ex)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        graphs.GraphedInfer(dec, {"spk_vec": ex["spk_vecs"], "txt_enc": torch.zeros(1, 520, 2), "dur": torch.ones(1, 2).long(),
+                                  "f0": ex["f0"], "energy_avg": ex["energy_avg"], "out_lens": ex["out_lens"]})
+
+
+def test_length_regulator_total_argument():
+    """LengthRegulator with a caller-supplied padded length (no device sync) equals the synced default, zero padded."""
+    import torch
+    from radmmm_b200.common import LengthRegulator
+    x = torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 4)
+    dur = torch.tensor([[2, 0, 3], [1, 1, 1]])
+    lr = LengthRegulator()
+    a = lr(x, dur)
+    b = lr(x, dur, total=7)
+    assert a.shape == (2, 5, 4) and b.shape == (2, 7, 4)
+    assert torch.equal(b[:, :5], a) and float(b[:, 5:].abs().sum()) == 0.0
+    assert torch.equal(a[0, :, 0], torch.tensor([0., 0., 8., 8., 8.]))
