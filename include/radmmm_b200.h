@@ -4,8 +4,10 @@
  * replaces is therefore a Python call site of the reference, cited per function (paths relative to the reference
  * repository).  Conventions:
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
- *   - caller-allocated outputs and workspaces (query the *_bytes functions); no allocation, no synchronisation
- *     and no global mutable state inside; work is enqueued on the `stream` argument (a cudaStream_t);
+ *   - caller-allocated outputs and workspaces (query the *_bytes functions); no device allocation and no
+ *     synchronisation inside; work is enqueued on the `stream` argument (a cudaStream_t).  The only library-owned
+ *     state: per-host-thread auxiliary streams / events (see radmmm_flow_desc.side_stream), the launch counter and
+ *     the optional profiler slots;
  *   - return 0 on success, a negative code on failure; radmmm_last_error() gives a thread-local message;
  *   - re-entrant across host threads and CUDA streams.
  *
@@ -90,9 +92,13 @@ typedef struct radmmm_flow_desc {
     const void* ctx_rows;
     /* per-call activation workspace (radmmm_flow_workspace_bytes()); must outlive backward when training */
     void* workspace;
-    /* optional second cudaStream_t: radmmm_flow_backward forks the weight-gradient work (weight-grad GEMMs, weight-norm
-     * backward, bias sums) onto it so it overlaps the input-gradient chain, and joins it back before returning work to
-     * `stream`.  NULL = everything on `stream`. */
+    /* optional second cudaStream_t; non-NULL enables intra-call concurrency (NULL = everything on `stream`):
+     *   forward / inverse: the dependent GEMM chain runs on a library-owned high-priority stream, the res-skip GEMMs
+     *     (which only feed the final `end` GEMM) on `side_stream`;
+     *   backward: the input-gradient chain runs on the high-priority stream, the weight-gradient work (bias column sums,
+     *     weight-grad GEMMs, weight-norm backward) on four more library-owned streams.
+     * The auxiliary streams and fork/join events are created once per host thread; every fork is joined back into
+     * `stream` before the call returns, so callers (and CUDA-graph capture of `stream`) see ordinary stream semantics. */
     void* side_stream;
 } radmmm_flow_desc;
 
