@@ -43,6 +43,25 @@ def main():
         print(f"probe={bits} (matvec={'off' if bits & 1 else 'on '} reload={'off' if bits & 2 else 'on '} "
               f"barrier={'off' if bits & 4 else 'on '}): {ms * 1e3:8.1f} us  = {ms * 1e3 / T:6.2f} us/step")
     os.environ["RADMMM_B200_LSTM_PROBE"] = "0"
+    # backward recurrence (no probe bits): gates / cell states from the forward pass above, random incoming gradient
+    run()
+    dout = torch.randn(B, T, 2 * H, device=dev) * 0.1
+    dg = torch.zeros(R, 8 * H, device=dev)
+
+    def run_bwd():
+        N.check(lib.radmmm_lstm_backward(N.fptr(dout), N.fptr(gates), N.fptr(cst), N.fptr(whf), N.fptr(whr), N.ptr(lens), B, T, H,
+                                         N.fptr(dg), N.ptr(ws), N.stream()))
+
+    run_bwd()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        run_bwd()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"backward: {ms * 1e3:8.1f} us  = {ms * 1e3 / T:6.2f} us/step")
 
 
 if __name__ == "__main__":
