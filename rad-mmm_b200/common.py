@@ -15,14 +15,12 @@ standalone modules route through the same native entry points, so there is exact
 from __future__ import annotations
 
 import ctypes as C
-import math
 import os
 from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _native as N
 

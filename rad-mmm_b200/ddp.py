@@ -11,7 +11,7 @@ Works with any ``torch.distributed`` backend (NCCL on GPUs; gloo in the CPU test
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional
 
 import torch
 import torch.distributed as dist

@@ -8,8 +8,6 @@ network's convolutions (k=1 and dilated k=5 partial convs, hidden width 512) run
 """
 from __future__ import annotations
 
-import math
-from typing import Optional
 
 import numpy as np
 import torch
