@@ -419,6 +419,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="skip the CUDA-graph capture; time the eager module path only")
     args = ap.parse_args()
+    # safety net: a wedged collective / rendezvous must not hold a GPU box for its whole lease
+    watchdog = threading.Timer(float(os.environ.get("RADMMM_BENCH_WATCHDOG_S", "1200")), lambda: os._exit(3))
+    watchdog.daemon = True
+    watchdog.start()
     if args.impl == "reference":
         run_reference(args)
     else:
