@@ -132,3 +132,54 @@ class GraphedInfer:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.mel
+
+
+_TIME_KEYS = {"mel": 2, "context": 2, "f0": 1, "energy_avg": 1}      # tensors with a time axis, and which axis it is
+
+
+def pad_batch(batch: Dict[str, torch.Tensor], frames: int) -> Dict[str, torch.Tensor]:
+    """Zero-pad the time axis of a decoder batch to ``frames`` (lengths stay as they are).  The decoder's outputs on the
+    valid frames do not depend on the padding (everything beyond ``out_lens`` is masked), so a batch padded to a captured
+    shape gives the same loss and gradients as the un-padded one."""
+    out = dict(batch)
+    for k, axis in _TIME_KEYS.items():
+        x = batch.get(k)
+        if x is None:
+            continue
+        t = x.shape[axis]
+        if t > frames:
+            raise ValueError(f"pad_batch: '{k}' has {t} frames, more than the target {frames}")
+        if t < frames:
+            out[k] = torch.nn.functional.pad(x, (0, frames - t))       # the time axis is the last one in all of them
+    return out
+
+
+class GraphedTrainStepPool:
+    """One ``GraphedTrainStep`` per frame bucket, captured on first use: a loop with variable-length batches pads each
+    batch up to the next bucket (e.g. 512 / 640 / 768 / 896 frames) and replays that bucket's graph.
+
+    ``step_factory(decoder, example)`` builds the step object (default: GraphedTrainStep); the batch size is fixed by the
+    first batch of each bucket.
+    """
+
+    def __init__(self, decoder, frame_buckets, step_factory=None, **step_kwargs):
+        self.decoder = decoder
+        self.buckets = sorted(int(b) for b in frame_buckets)
+        if not self.buckets:
+            raise ValueError("GraphedTrainStepPool: at least one frame bucket is needed")
+        self._factory = step_factory or (lambda dec, ex: GraphedTrainStep(dec, ex, **step_kwargs))
+        self._steps: Dict[int, object] = {}
+
+    def bucket_for(self, frames: int) -> int:
+        for b in self.buckets:
+            if frames <= b:
+                return b
+        raise ValueError(f"GraphedTrainStepPool: {frames} frames exceed the largest bucket ({self.buckets[-1]})")
+
+    def __call__(self, batch: Dict[str, torch.Tensor]):
+        b = self.bucket_for(int(batch["mel"].shape[2]))
+        padded = pad_batch(batch, b)
+        step = self._steps.get(b)
+        if step is None:
+            step = self._steps[b] = self._factory(self.decoder, padded)
+        return step(padded)

@@ -119,3 +119,36 @@ def test_length_regulator_total_argument():
     assert a.shape == (2, 5, 4) and b.shape == (2, 7, 4)
     assert torch.equal(b[:, :5], a) and float(b[:, 5:].abs().sum()) == 0.0
     assert torch.equal(a[0, :, 0], torch.tensor([0., 0., 8., 8., 8.]))
+
+
+def test_pad_batch_and_step_pool_bucketing():
+    """pad_batch zero-pads the time axes only; GraphedTrainStepPool picks the smallest bucket, builds one step per bucket
+    (here a stub instead of a CUDA graph) and feeds it the padded batch."""
+    import pytest
+    import torch
+    from radmmm_b200.graphs import GraphedTrainStepPool, pad_batch
+    bt = {"mel": torch.ones(2, 80, 10), "context": torch.ones(2, 520, 10), "f0": torch.ones(2, 10), "energy_avg": torch.ones(2, 10),
+          "spk_vecs": torch.ones(2, 16), "out_lens": torch.tensor([10, 7]), "accent_vecs": torch.ones(2, 8)}
+    p = pad_batch(bt, 16)
+    assert p["mel"].shape == (2, 80, 16) and p["context"].shape == (2, 520, 16) and p["f0"].shape == (2, 16)
+    assert float(p["mel"][:, :, 10:].abs().sum()) == 0.0 and torch.equal(p["mel"][:, :, :10], bt["mel"])
+    assert p["spk_vecs"] is bt["spk_vecs"] and torch.equal(p["out_lens"], bt["out_lens"])
+    with pytest.raises(ValueError):
+        pad_batch(bt, 8)
+    built = []
+
+    class Stub:
+        def __init__(self, dec, ex):
+            built.append(ex["mel"].shape[2])
+            self.frames = ex["mel"].shape[2]
+
+        def __call__(self, b):
+            assert b["mel"].shape[2] == self.frames
+            return self.frames
+
+    pool = GraphedTrainStepPool(object(), [32, 16, 64], step_factory=Stub)
+    assert pool(bt) == 16 and pool(bt) == 16 and built == [16]
+    bt2 = dict(bt, mel=torch.ones(2, 80, 20), context=torch.ones(2, 520, 20), f0=torch.ones(2, 20), energy_avg=torch.ones(2, 20))
+    assert pool(bt2) == 32 and built == [16, 32]
+    with pytest.raises(ValueError):
+        pool.bucket_for(65)
