@@ -2,12 +2,16 @@
 """Benchmark of the RAD-MMM flow-decoder train step (BASELINE.json metric: mel-frames/s of a decoder train step).
 
     python bench.py --gpus N --steps K --warmup W            # ours, one process per GPU (torchrun for N > 1)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm (CPU oracle port) on host cores
+    python bench.py --impl reference --steps K --warmup W    # the reference itself on the host cores (same config)
 
 A step is one pass of the hot path over one synthetic batch: RADMMMFlow.forward + flow NLL + backward
 (+ the gradient all-reduce when N > 1).  Workload at N=1: BASELINE.json configs[1] -- the full-depth RADMMM decoder
 (configs/RADMMM_model_config.yaml, 8 flows, 219 M parameters), B=8 utterances padded to T=800 frames with lengths in
 [400, 800].  Weak scaling: every rank gets its own batch of the same shape.
+
+The reference arm runs the UNMODIFIED reference modules (``/root/reference`` or the copy staged under ``oracle/_ref`` by
+``python -m oracle.stage_ref``) -- ``decoders.RADMMMFlow`` + ``loss.compute_flow_loss`` + backward, fp32, all host
+threads, on the SAME config; if neither is present it falls back to the oracle port and says so (``kind: "port"``).
 """
 from __future__ import annotations
 
@@ -31,7 +35,11 @@ UNIT = "mel-frames/s"
 FWD_MFLOP_PER_FRAME = 218.8      # BASELINE.md section 3 (8 flows + context LSTM)
 TRAIN_MFLOP_PER_FRAME = 656.4    # 3 x forward (fwd + dgrad + wgrad; recompute not counted)
 K5_FLOP_PER_GROUPED_FRAME = 2 * 1024 * 1024 * 5      # one dilated k=5 layer (the dominant kernel), per grouped frame
-K5_DRAM_BYTES_NCU = 17337344                         # measured once with ncu --set full (see roofline.traffic_note)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at B=8 x T=800, bf16, from the
+# committed `ncu --set full` capture named below (re-measured whenever the kernel changes)
+K5_DRAM_BYTES_NCU = {"bytes": 17337856, "source": "profiles/r1_ncu_full_k5_final.md"}
+MODEL_ARGS = dict(n_speaker_dim=16, use_accent=True, n_accent_dim=8, n_text_dim=520, n_group_size=2, n_mel_channels=80,
+                  n_flows=8)
 
 
 def peaks():
@@ -83,71 +91,259 @@ def make_batch(batch, frames, rank):
 
 
 # ------------------------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """The reference algorithm on the host CPU: the oracle port (torch-CPU restatement pinned to the unmodified
-    reference by tests/golden; the Python reference itself cannot travel to the GPU box).  A bounded sample of the same
-    workload: same model, fewer / shorter utterances."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import flow as of
+def _reference_step_fn(batch, frames):
+    """(step(), valid_frames, kind, description).  The unmodified reference when it can be imported, else the port."""
     from radmmm_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    batch, frames = args.ref_batch, args.ref_frames
-    cfg = of.DecoderConfig.radmmm()
+    from oracle import ref_import
+    bt = syn.synthetic_batch(batch, frames, tag="bench.rank0")          # the batch rank 0 of our arm trains on
+    valid = int(bt["out_lens"].sum())
     sd = syn.synthetic_state_dict()
+    if ref_import.available():
+        root, mods = ref_import.import_reference()
+        dec = mods["decoders"].RADMMMFlow(**MODEL_ARGS, n_conv_layers_per_step=4, n_early_size=2, n_early_every=2,
+                                          affine_model="wavenet", scaling_fn="tanh", affine_activation="softplus",
+                                          use_partial_padding=True)
+        dec.load_state_dict(sd, strict=True)                          # flow 0's whitening layer arrives initialised
+        dec.train()
+        SL, cfl = mods["common"].SequenceLength, mods["loss"].compute_flow_loss
+
+        def step():
+            for p in dec.parameters():
+                p.grad = None
+            out = dec(bt["mel"], bt["spk_vecs"], bt["context"], SL(bt["out_lens"]), f0=bt["f0"],
+                      energy_avg=bt["energy_avg"], accent_vecs=bt["accent_vecs"])
+            lens_g = bt["out_lens"] // 2
+            mask = (torch.arange(frames // 2)[None] < lens_g[:, None])[:, None].float()
+            n_el = torch.div(bt["out_lens"].sum(), 2, rounding_mode="floor")                 # loss.py:520
+            loss, _ = cfl(out["z_mel"], list(out["log_det_W_list"]), out["log_s_list"], n_el, out["z_mel"].size(1), mask, 1.0)
+            loss.backward()
+            return float(loss)
+        where = "staged copy oracle/_ref" if root.endswith("_ref") else root
+        return step, valid, "reference", f"unmodified reference decoders.RADMMMFlow + loss.compute_flow_loss + backward ({where})"
+    from oracle import flow as of
+    cfg = of.DecoderConfig.radmmm()
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
               if v.dtype == torch.float32 and not any(s in k for s in ("invtbl_conv.p", "lower_diag", "input_mean"))}
     sdp = dict(sd)
     sdp.update(params)
     lstm = of.build_context_lstm(sd, cfg)
-    bt = syn.synthetic_batch(batch, frames, tag="bench.ref")
-    valid = int(bt["out_lens"].sum())
 
     def step():
         for p in params.values():
             p.grad = None
         out = of.decoder_forward(sdp, cfg, bt["mel"], bt["spk_vecs"], bt["context"], bt["out_lens"], bt["f0"],
                                  bt["energy_avg"], bt["accent_vecs"], lstm=lstm)
-        loss, _ = of.flow_loss(out["z_mel"], out["log_det_W_list"], out["log_s_list"], bt["out_lens"] // 2)
+        loss, _ = of.flow_loss(out["z_mel"], out["log_det_W_list"], out["log_s_list"], bt["out_lens"] // 2,
+                               n_elements=torch.div(bt["out_lens"].sum(), 2, rounding_mode="floor"))
         loss.backward()
         return float(loss)
+    return step, valid, "port", "oracle port (oracle/_ref not staged on this box)"
 
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores, SAME config as our arm (B x T), fp32."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch, frames = args.ref_batch or args.batch, args.ref_frames or args.frames
+    step, valid, kind, what = _reference_step_fn(batch, frames)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
-    dt = (time.perf_counter() - t0) / args.steps
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = valid / dt
-    sample = f"oracle port, {batch} utterances x {frames} frames (lengths {bt['out_lens'].tolist()}), fp32, torch CPU"
+    sample = f"{what}; {batch} utterances x {frames} frames ({valid} valid frames), fp32, torch CPU, {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "RADMMM decoder train step (configs/RADMMM_model_config.yaml, 8 flows, 219M params); "
-                                   "bounded CPU sample", "batch": batch, "frames": frames, "valid_frames": valid},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "RADMMM decoder train step (configs/RADMMM_model_config.yaml, 8 flows, 219M params), "
+                                   f"B={batch} x T={frames}: forward + flow NLL + backward on the host CPU",
+                       "batch_per_gpu": batch, "frames": frames, "valid_frames_per_gpu": valid, "precision": "fp32",
+                       "same_config_as_gpu_arm": batch == args.batch and frames == args.frames},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def cpu_baseline_sample(timeout_s=240.0):
-    """Bounded CPU run of the oracle port on rank 0 (reported baseline, not the target).  Runs in a FRESH process
-    (`bench.py --impl reference`, two timed steps of 2 x 256 frames): the CPU port shares nothing with the CUDA process
-    (thread pools, allocator, autograd device threads), and a hard timeout keeps the default run bounded."""
+def cpu_baseline_sample(batch, frames, timeout_s=420.0):
+    """Bounded CPU run of the reference on rank 0 (reported baseline, not the target): `bench.py --impl reference` on the
+    SAME config in a fresh process, 1 warm-up + 2 timed steps (~20 s of CPU work at B=8 x T=800).  A separate process:
+    the CPU run shares nothing with the CUDA process (thread pools, allocator, autograd device threads), and a hard
+    timeout keeps the default run bounded."""
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     env["CUDA_VISIBLE_DEVICES"] = ""
     try:
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                              "--batch", str(batch), "--frames", str(frames)],
                              capture_output=True, text=True, timeout=timeout_s, env=env)
         line = json.loads(out.stdout.strip().splitlines()[-1])
         cb = line["cpu_baseline"]
-        cb["sample"] += ", 2 timed steps after 1 warm-up, separate process"
+        cb["sample"] += "; 2 timed steps after 1 warm-up, separate process"
+        cb["ms_per_step"] = line["ms_per_step"]
         return cb
     except Exception as exc:
-        return {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
                 "sample": f"CPU sample failed: {type(exc).__name__}: {str(exc)[:200]}"}
+
+
+# ------------------------------------------------------------------------------------------------------- HBM-bound kernels
+def hbm_rooflines(dev, pk, batch, frames):
+    """Every HBM-bound kernel of the path timed ALONE through the C ABI at the benchmark's shapes: CUDA events around one
+    launch, L2 flushed (a 512 MB memset) before every timed launch, median of 7.  achieved = algorithmic bytes / time."""
+    from radmmm_b200 import _native as N
+    from radmmm_b200 import synthetic as syn
+    lib = N.lib()
+    B, Tp, C, D, H = batch, frames // 2, 160, 1056, 1024
+    R = N.rows(B, Tp)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    st = N.stream()
+    lens = torch.full((B,), Tp, dtype=torch.int32, device=dev)
+    f32 = lambda *s: torch.randn(*s, device=dev)          # noqa: E731
+    out = []
+
+    def timed(name, nbytes, fn, note=""):
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "us": round(ms * 1e3, 2), "algorithmic_bytes": int(nbytes), "achieved": round(gbs, 1),
+                    "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": round(gbs / pk["hbm_gbs"], 3), "note": note})
+
+    # weight preparation of one flow step (weight norm + both layouts), bf16
+    d = N.FlowDesc()
+    d.mode, d.B, d.C, d.Tp, d.D, d.H, d.L = N.MODE_BF16, 1, C, 1, D, H, 4
+    sd = {k: v.to(dev) for k, v in syn.synthetic_state_dict(n_flows=1).items() if "coupling_tfn" in k}
+    pre = "flows.0.coupling_tfn.affine_param_predictor."
+    keep = []
+
+    def P(name):
+        t = sd[pre + name].contiguous()
+        keep.append(t)
+        return N.fptr(t)
+    d.start_g, d.start_v, d.start_b = P("start.weight_g"), P("start.weight_v"), P("start.bias")
+    for i in range(4):
+        d.in_g[i], d.in_v[i], d.in_b[i] = P(f"in_layers.{i}.conv.weight_g"), P(f"in_layers.{i}.conv.weight_v"), P(f"in_layers.{i}.conv.bias")
+        d.rs_g[i], d.rs_v[i], d.rs_b[i] = P(f"res_skip_layers.{i}.weight_g"), P(f"res_skip_layers.{i}.weight_v"), P(f"res_skip_layers.{i}.bias")
+    d.end_w, d.end_b = P("end.weight"), P("end.bias")
+    prepared = torch.zeros(lib.radmmm_flow_prepared_bytes(N.MODE_BF16, C, D, H, 4), dtype=torch.uint8, device=dev)
+    d.prepared = N.ptr(prepared)
+    n_w = sum(t.numel() for t in keep)
+    timed("weight_prep (weight norm + K-major and transposed bf16 layouts, one flow step)", n_w * (4 + 2 * 2),
+          lambda: N.check(lib.radmmm_flow_prepare(ctypes.byref(d), st)), "4 B read + 2 x 2 B written per weight")
+    # 1x1 invertible conv and its weight gradient
+    z, W, zo = f32(B, C, Tp), f32(C, C), torch.empty(B, C, Tp, device=dev)
+    timed("inv1x1", 2 * z.numel() * 4, lambda: N.check(lib.radmmm_inv1x1(N.fptr(z), N.fptr(W), None, None, N.fptr(zo), B, C, C, Tp, st)))
+    dW = torch.empty(C, C, device=dev)
+    timed("inv1x1_wgrad", 2 * z.numel() * 4, lambda: N.check(lib.radmmm_inv1x1_wgrad(N.fptr(z), N.fptr(zo), None, N.ptr(lens), N.fptr(dW), B, C, Tp, st)))
+    # coupling tail forward / backward
+    prm, ls = f32(B, C, Tp) * 0.1, torch.empty(B, C // 2, Tp, device=dev)
+    timed("coupling_fwd", int(3.5 * z.numel() * 4), lambda: N.check(lib.radmmm_coupling_forward(N.fptr(z), N.fptr(prm), N.fptr(zo), N.fptr(ls), B, C, Tp, 0, 0, st)))
+    dz, dp = torch.empty_like(z), torch.empty_like(z)
+    timed("coupling_bwd", int(5.5 * z.numel() * 4), lambda: N.check(lib.radmmm_coupling_backward(
+        N.fptr(zo), N.fptr(ls), N.fptr(z), N.fptr(prm), N.ptr(lens), N.fptr(dz), N.fptr(dp), B, C, Tp, 0, st)))
+    # flow-NLL reductions
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    timed("masked_sum (flow NLL)", z.numel() * 4, lambda: N.check(lib.radmmm_masked_sum(N.fptr(z), N.ptr(lens), B, C, Tp, 1, N.ptr(acc), st)))
+    coef = torch.ones(1, device=dev)
+    timed("masked_sum_bwd", 2 * z.numel() * 4, lambda: N.check(lib.radmmm_masked_sum_backward(N.fptr(z), N.ptr(lens), B, C, Tp, 1, N.fptr(coef), 1.0, N.fptr(dz), st)))
+    # conditioning (B, Tp, D) fp32 -> bf16 rows
+    ctx = f32(B, Tp, D)
+    rows = torch.empty(lib.radmmm_context_rows_bytes(N.MODE_BF16, B, Tp, D), dtype=torch.uint8, device=dev)
+    timed("rows_from_btd (context -> rows)", ctx.numel() * 4 + rows.numel(),
+          lambda: N.check(lib.radmmm_context_rows(N.MODE_BF16, N.fptr(ctx), N.ptr(lens), B, Tp, D, N.ptr(rows), st)))
+    # spline coupling (80 channels x 65 parameters per grouped frame)
+    z1, q = f32(B, 80, Tp), f32(B, 80 * 65, Tp)
+    z1o, lsp = torch.empty_like(z1), torch.empty(B, 1, Tp, device=dev)
+    timed("spline_fwd", (q.numel() + 2 * z1.numel()) * 4, lambda: N.check(lib.radmmm_spline_forward(
+        N.fptr(z1), N.fptr(q), N.ptr(lens), N.fptr(z1o), N.fptr(lsp), B, 80, Tp, 32, -3.0, 3.0, 0, st)))
+    dq, dz1 = torch.empty_like(q), torch.empty_like(z1)
+    timed("spline_bwd", (2 * q.numel() + 3 * z1.numel()) * 4, lambda: N.check(lib.radmmm_spline_backward(
+        N.fptr(z1), N.fptr(q), N.ptr(lens), N.fptr(z1o), N.fptr(lsp), N.fptr(dz1), N.fptr(dq), B, 80, Tp, 32, -3.0, 3.0, st)))
+    # soft attention with the fused context matmul (T1 = frames, T2 = frames / 6 tokens)
+    T1, T2, Ca, Dt = frames, max(4, frames // 6), 80, 520
+    qq, kk, prior, txt = f32(B, Ca, T1), f32(B, Ca, T2), torch.rand(B, T1, T2, device=dev), f32(B, Dt, T2)
+    attn, logp, cx = torch.empty(B, 1, T1, T2, device=dev), torch.empty(B, 1, T1, T2, device=dev), torch.empty(B, Dt, T1, device=dev)
+    in_lens = torch.full((B,), T2, dtype=torch.int32, device=dev)
+    att_bytes = B * ((Ca * (T1 + T2) + 3 * T1 * T2) + Dt * (T1 + T2)) * 4
+    timed("soft_attention (+ context matmul)", att_bytes, lambda: N.check(lib.radmmm_soft_attention(
+        N.fptr(qq), N.fptr(kk), N.fptr(prior), N.ptr(in_lens), N.fptr(attn), N.fptr(logp), N.fptr(txt), N.fptr(cx), B, Ca, T1, T2, Dt,
+        0.0005, st)))
+    return out
+
+
+def frontend_bench(dev, pk, batch, frames):
+    """STFT + mel front end (audio_processing.TacotronSTFT.mel_spectrogram): GPU kernel vs the oracle on the host cores."""
+    from radmmm_b200 import audio_processing as AP
+    from oracle import frontend as ofe
+    S = frames * 256
+    stft = AP.TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(dev)
+    y = (torch.rand(batch, S, device=dev) - 0.5).clamp(-1, 1)
+    for _ in range(3):
+        mel = stft.mel_spectrogram(y)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(7):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mel = stft.mel_spectrogram(y)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    n_frames = batch * mel.shape[2]
+    gbs = n_frames * 1344 / (ms * 1e-3) / 1e9
+    yc = y[:2].cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    ofe.mel_spectrogram(yc)
+    t0 = time.perf_counter()
+    ofe.mel_spectrogram(yc)
+    cpu_s = time.perf_counter() - t0
+    return {"kernel": "stft_mel", "frames_per_s": n_frames / (ms * 1e-3), "audio_s_per_s": batch * S / 22050 / (ms * 1e-3),
+            "us": ms * 1e3, "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"],
+            "algorithmic_bytes_per_frame": 1344,
+            "cpu_frames_per_s": 2 * mel.shape[2] / cpu_s, "cpu_note": f"oracle dense-DFT restatement of TacotronSTFT on {os.cpu_count()} host threads, 2 utterances"}
+
+
+def precision_errors(dev, precisions):
+    """max-abs z error and relative loss error of each contraction mode against the oracle (fp32 CPU) on a small sample:
+    the 8-flow decoder, 2 utterances x 96 frames (the shape of tests/golden/decoder_full.npz)."""
+    from oracle import flow as of
+    from radmmm_b200 import decoders, loss as L, synthetic as syn
+    from radmmm_b200.common import SequenceLength
+    sd = syn.synthetic_state_dict()
+    bt = syn.synthetic_batch(2, 96, tag="bench.parity")
+    cfg = of.DecoderConfig.radmmm()
+    with torch.no_grad():
+        ref = of.decoder_forward(sd, cfg, bt["mel"], bt["spk_vecs"], bt["context"], bt["out_lens"], bt["f0"], bt["energy_avg"], bt["accent_vecs"])
+        n_el = torch.div(bt["out_lens"].sum(), 2, rounding_mode="floor")
+        rl, _ = of.flow_loss(ref["z_mel"], ref["log_det_W_list"], ref["log_s_list"], bt["out_lens"] // 2, n_elements=n_el)
+    m = of.length_mask(bt["out_lens"] // 2, 48)[:, None]
+    res = {}
+    for prec in precisions:
+        dec = decoders.RADMMMFlow(**MODEL_ARGS)
+        dec.load_state_dict(sd)
+        dec = dec.to(dev).set_precision(prec).eval()
+        b = {k: v.to(dev) for k, v in bt.items()}
+        with torch.no_grad():
+            out = dec(b["mel"], b["spk_vecs"], b["context"], SequenceLength(b["out_lens"], 96), f0=b["f0"],
+                      energy_avg=b["energy_avg"], accent_vecs=b["accent_vecs"])
+            l = L.RADMMMFlowLoss(1.0, 2)(out, b["out_lens"])["loss_mel"][0]
+        res[prec] = {"z_max_abs_err": float(((out["z_mel"].cpu() - ref["z_mel"]) * m).abs().max()),
+                     "loss_rel_err": abs(float(l) - float(rl)) / abs(float(rl))}
+        del dec
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------- our arm
@@ -155,22 +351,27 @@ def run_ours(args):
     from radmmm_b200 import _native as N
     from radmmm_b200 import decoders, loss as L, synthetic as syn
     from radmmm_b200.common import SequenceLength
+    from radmmm_b200.graphs import GraphedInfer, GraphedTrainStep
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the single JSON line (no "NCCL version" banner)
+        # NCCL_DEBUG is left as the caller set it (the driver reads the rank count from NCCL's INFO lines); the JSON line is
+        # the LAST thing on stdout (printed after the final barrier, see _finish)
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.allow_tf32 = False          # keep the (cuDNN) context LSTM in fp32 like the reference default
+    torch.backends.cudnn.allow_tf32 = False
     precision = args.precision
     batch, frames = args.batch, args.frames
+    sd = syn.synthetic_state_dict()
 
-    dec = decoders.RADMMMFlow(n_speaker_dim=16, use_accent=True, n_accent_dim=8, n_text_dim=520, n_group_size=2,
-                              n_mel_channels=80, n_flows=8)
-    dec.load_state_dict(syn.synthetic_state_dict())
-    dec = dec.to(dev).set_precision(precision).train()
+    def build(prec):
+        d = decoders.RADMMMFlow(**MODEL_ARGS)
+        d.load_state_dict(sd)
+        return d.to(dev).set_precision(prec).train()
+
+    dec = build(precision)
     reducer = None
     if world > 1:
         from radmmm_b200.ddp import BucketedGradReducer
@@ -180,19 +381,18 @@ def run_ours(args):
     valid_frames = int(host["out_lens"].sum())
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
+    crit = L.RADMMMFlowLoss(1.0, 2)
 
-    def train_step(bt):
-        # no optimizer in the timed loop: mark the parameters as changed so that every step re-runs the weight norm +
-        # re-layout of all 219 M parameters, as it must after a real optimizer step (nothing is served from a cache)
-        dec.invalidate_weight_cache()
-        for p in dec.parameters():
+    def train_step(d, bt, red=None):
+        """What an unmodified Lightning loop executes per step for this path (tts_lightning_modules.py:672-685 + backward)."""
+        for p in d.parameters():
             p.grad = None
-        out = dec(bt["mel"], bt["spk_vecs"], bt["context"], SequenceLength(bt["out_lens"], frames), f0=bt["f0"],
-                  energy_avg=bt["energy_avg"], accent_vecs=bt["accent_vecs"])
-        loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], bt["out_lens"] // 2)
+        out = d(bt["mel"], bt["spk_vecs"], bt["context"], SequenceLength(bt["out_lens"], frames), f0=bt["f0"],
+                energy_avg=bt["energy_avg"], accent_vecs=bt["accent_vecs"])
+        loss = crit(out, bt["out_lens"])["loss_mel"][0]
         loss.backward()
-        if reducer is not None:
-            reducer.finish()
+        if red is not None:
+            red.finish()
         return loss
 
     def barrier():
@@ -220,26 +420,22 @@ def run_ours(args):
             ms = float(t)
         return ms
 
-    # ---- eager module path (what a Lightning loop calls): kept as a secondary number -- at this shape the host needs
-    #      about as long to enqueue the ~1000 launches of a step as the GPU needs to run them
+    # ---- eager module path (what a Lightning loop calls unchanged): secondary number
     def e2e_eager_step():
         bt = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        return float(train_step(bt).detach().cpu())
+        return float(train_step(dec, bt, reducer).detach().cpu())
 
     for _ in range(args.warmup):
-        train_step(resident)
-    eager_steps = max(3, args.steps // 2)
-    ms_eager = timed(lambda: train_step(resident), eager_steps, "train_eager")
+        train_step(dec, resident, reducer)
+    ms_eager = timed(lambda: train_step(dec, resident, reducer), max(3, args.steps // 2), "train_eager")
     e2e_eager_step()
     ms_e2e_eager = timed(e2e_eager_step, max(3, args.steps // 4))
 
-    # ---- headline path: the same step captured once into a CUDA graph (radmmm_b200.graphs.GraphedTrainStep) and
-    #      replayed; inputs are copied into the graph's static buffers every step
+    # ---- headline path: the same step captured once into a CUDA graph (radmmm_b200.graphs.GraphedTrainStep), replayed
     gstep, graph_error = None, None
     if not args.eager:
         try:
-            from radmmm_b200.graphs import GraphedTrainStep
-            gstep = GraphedTrainStep(dec, resident, after_backward=(reducer.finish if reducer is not None else None))
+            gstep = GraphedTrainStep(dec, resident, reducer=reducer)
         except Exception as exc:                                   # report, then fall back to the eager numbers
             graph_error = f"{type(exc).__name__}: {exc}"[:300]
             gstep = None
@@ -248,7 +444,7 @@ def run_ours(args):
         dist.all_reduce(graph_ok, op=dist.ReduceOp.MIN)
     if int(graph_ok) == 0:
         gstep = None
-    run_step = (lambda: gstep(resident)) if gstep is not None else (lambda: train_step(resident))
+    run_step = (lambda: gstep(resident)) if gstep is not None else (lambda: train_step(dec, resident, reducer))
 
     # ---- value: inputs resident in HBM
     for _ in range(args.warmup):
@@ -269,12 +465,29 @@ def run_ours(args):
 
     e2e_step()
     ms_e2e = timed(e2e_step, max(3, args.steps // 2))
-    if gstep is not None:
-        for p in dec.parameters():        # leave graph mode: the remaining (eager) sections own their gradients again
-            p.grad = None
 
-    # ---- inference (BASELINE metric "infer frames/s"): RADMMMFlow.infer on the same shapes (text tokens ~ T/6,
-    #      durations summing to each length), sigma = 0.8
+    # ---- N > 1: the in-graph NCCL-averaged gradients against an explicit all_gather + mean of the local gradients
+    allreduce_check = None
+    if world > 1 and reducer is not None:
+        run_step()
+        torch.cuda.synchronize()
+        got = {k: b["flat"].clone() for k, b in reducer.buckets.items()}
+        w0, reducer.world = reducer.world, 1                       # local gradients only: no collective is issued
+        train_step(dec, resident, reducer)
+        reducer.world = w0
+        worst, gmax = 0.0, 0.0
+        for k, b in reducer.buckets.items():
+            parts = [torch.empty_like(b["flat"]) for _ in range(world)]
+            dist.all_gather(parts, b["flat"].contiguous())
+            mean = torch.stack(parts).double().mean(0)
+            worst = max(worst, float((got[k].double() - mean).abs().max()))
+            gmax = max(gmax, float(mean.abs().max()))
+        allreduce_check = {"max_abs_diff": worst, "max_abs_grad": gmax, "buckets": len(reducer.buckets),
+                           "bytes_per_step": reducer.bytes_per_step(),
+                           "note": "gradients of the captured step (bucketed NCCL AVG inside the CUDA graph) vs all_gather + "
+                                   "mean of the ranks' local gradients of the same step, fp64 compare"}
+
+    # ---- inference (BASELINE metric "infer frames/s"): RADMMMFlow.infer on the same shapes, sigma = 0.8
     dec.eval()
     n_tok = max(4, frames // 6)
     lens_dev = resident["out_lens"]
@@ -297,28 +510,28 @@ def run_ours(args):
     # ---- per-kernel roofline of the dominant kernel (dilated k=5 conv forward, tcgen05): events around every launch
     lib = N.lib()
     l0 = lib.radmmm_launch_count()
-    train_step(resident)
+    train_step(dec, resident, reducer)
     launches_per_eager_step = lib.radmmm_launch_count() - l0
     lib.radmmm_profile_enable(1)
-    train_step(resident)
+    train_step(dec, resident, reducer)
     n_tags = 32
     cnt = (ctypes.c_int * n_tags)()
     kms = (ctypes.c_double * n_tags)()
     kfl = (ctypes.c_double * n_tags)()
     lib.radmmm_profile_collect(n_tags, cnt, kms, kfl)
     lib.radmmm_profile_enable(0)
-    # ---- graphed inference LAST: a failed capture must not be able to disturb any other number
+    # ---- graphed inference: a failed capture must not be able to disturb the numbers above
     dec.eval()
     ms_infer, infer_graph_error = ms_infer_eager, None
     if not args.eager and world == 1:          # inference does not shard: replicas only, measured on one GPU
         try:
-            from radmmm_b200.graphs import GraphedInfer
             ex = {"spk_vec": resident["spk_vecs"], "txt_enc": txt_enc, "dur": dur, "f0": resident["f0"],
                   "energy_avg": resident["energy_avg"], "out_lens": lens_dev}
             ginfer = GraphedInfer(dec, ex, sigma=0.8)
             for _ in range(3):
                 ginfer(ex)
             ms_infer = timed(lambda: ginfer(ex), max(5, args.steps))
+            del ginfer
         except Exception as exc:
             infer_graph_error = f"{type(exc).__name__}: {exc}"[:300]
     dec.train()
@@ -336,14 +549,55 @@ def run_ours(args):
         algo_flops = K5_FLOP_PER_GROUPED_FRAME * valid_grouped              # valid frames only (conservative)
         achieved = algo_flops / (per_launch_ms * 1e-3) / 1e12
         peak = pk["bf16_burst"] / (3.0 if precision == "bf16x3" else 1.0)
+        same_shape = precision == "bf16" and batch == 8 and frames == 800
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EPI_IN> (dilated k=5 conv forward)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": K5_DRAM_BYTES_NCU if (precision == "bf16" and batch == 8 and frames == 800) else None,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                "(profiles/r1_ncu_full_k5_s12.md); algorithmic bytes A 6.8 MB + W 10.5 MB + out 6.8 MB",
+                "traffic": K5_DRAM_BYTES_NCU["bytes"] if same_shape else None,
+                "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                f"({K5_DRAM_BYTES_NCU['source']}); algorithmic bytes A 6.8 MB + W 10.5 MB + out 6.8 MB (the output "
+                                "stays in the 126 MB L2)",
                 "peak_source": pk["source"] + (", bf16 burst / 3 for the 3-pass split" if precision == "bf16x3" else ", bf16 burst"),
                 "per_launch_ms": per_launch_ms, "algorithmic_flops_per_launch": algo_flops,
-                "executed_tflops": kfl[1] / (kms[1] * 1e9)}
+                "executed_tflops": kfl[1] / (kms[1] * 1e9),
+                "timing": "CUDA events on the launching stream around every launch of one eager train step (radmmm_profile_enable)"}
+
+    # ---- rank 0, N = 1 only: parity-grade mode beside the headline, measured errors, HBM-bound kernels, front end, CPU arm
+    extras = {}
+    if world == 1 and not args.quick:
+        if gstep is not None:
+            del gstep
+            gstep = None
+        torch.cuda.empty_cache()
+        try:
+            dec3 = build("bf16x3")
+            g3 = GraphedTrainStep(dec3, resident)
+            for _ in range(3):
+                g3(resident)
+            ms3 = timed(lambda: g3(resident), max(5, args.steps // 2))
+            ms3_e2e = timed(lambda: float(g3(host).cpu()), max(3, args.steps // 4))
+            errs = precision_errors(dev, ["bf16x3", precision] if precision != "bf16x3" else ["bf16x3"])
+            v3 = valid_frames / (ms3 * 1e-3)
+            extras["parity_mode"] = {
+                "precision": "bf16x3", "value": v3, "unit": UNIT, "ms_per_step": ms3, "e2e_value": valid_frames / (ms3_e2e * 1e-3),
+                "e2e_ms_per_step": ms3_e2e,
+                "step_tensor_roofline": {"achieved_tflops": v3 * TRAIN_MFLOP_PER_FRAME * 1e-6, "peak_tflops": pk["bf16_sustained"] / 3.0,
+                                         "frac": v3 * TRAIN_MFLOP_PER_FRAME * 1e-6 / (pk["bf16_sustained"] / 3.0),
+                                         "note": "3 tensor-core passes per product (hi*hi + lo*hi + hi*lo): peak = sustained bf16 / 3"},
+                "errors_vs_oracle": errs,
+                "note": "same step, same graph machinery, contractions in the fp32-grade split-bf16 mode that meets north_star's "
+                        "tolerances (mel 1e-3 max-abs, log-det 1e-4 rel); errors_vs_oracle: 8-flow decoder, 2 x 96 frames, vs oracle fp32"}
+            del g3, dec3
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            extras["parity_mode"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            extras["roofline_hbm"] = hbm_rooflines(dev, pk, batch, frames)
+        except Exception as exc:
+            extras["roofline_hbm"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            extras["frontend"] = frontend_bench(dev, pk, batch, frames)
+        except Exception as exc:
+            extras["frontend"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         _finish(world)
@@ -351,12 +605,13 @@ def run_ours(args):
     value = world * valid_frames / (ms * 1e-3)
     e2e_value = world * valid_frames / (ms_e2e * 1e-3)
     step_tflops = value * TRAIN_MFLOP_PER_FRAME * 1e6 / 1e12 / world
+    graphed = graph_error is None and not args.eager
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (hi/lo split, fp32-grade)", "fp32": "f32"}[precision], "data": "synthetic",
         "config": {"workload": "RADMMM decoder train step: weight norm of all 219M params + forward + flow NLL + backward "
-                               "(+ grad all-reduce), configs/RADMMM_model_config.yaml (8 flows), B=8 x T=800 per GPU, "
+                               f"(+ grad all-reduce), configs/RADMMM_model_config.yaml (8 flows), B={batch} x T={frames} per GPU, "
                                "replayed as one CUDA graph",
                    "batch_per_gpu": batch, "frames": frames, "valid_frames_per_gpu": valid_frames,
                    "padded_frames_per_gpu": batch * frames, "precision": precision,
@@ -370,14 +625,15 @@ def run_ours(args):
                   "note": "RADMMMFlow.infer (length regulation + context LSTM + 8 inverse flow steps), sigma 0.8, replayed "
                           "as a CUDA graph (radmmm_b200.graphs.GraphedInfer); eager_ms_per_call = the plain module call",
                   "tensor_roofline_frac": (world * valid_frames / (ms_infer * 1e-3)) * FWD_MFLOP_PER_FRAME * 1e6 / 1e12 / world / pk["bf16_sustained"]},
-        "gpu_launches": int(launches) if gstep is None else int(launches_per_eager_step) * args.steps,
-        "graph": {"captured": gstep is not None, "error": graph_error,
+        "gpu_launches": int(launches) if not graphed else int(launches_per_eager_step) * args.steps,
+        "graph": {"captured": graphed, "error": graph_error,
                   "note": "one whole train step (weight prep, LSTM, 8 flows, NLL, backward) replayed as a CUDA graph; "
                           "gpu_launches counts the kernels inside the graph x steps"},
         "eager": {"ms_per_step": ms_eager, "e2e_ms_per_step": ms_e2e_eager,
                   "value": world * valid_frames / (ms_eager * 1e-3), "e2e_value": world * valid_frames / (ms_e2e_eager * 1e-3),
                   "host_enqueue_ms_per_step": host_ms.get("train_eager"),
-                  "note": "RADMMMFlow.forward + flow_nll + backward called eagerly (the Lightning-loop path)"},
+                  "note": "RADMMMFlow.forward + RADMMMFlowLoss + backward called eagerly: the path an UNMODIFIED Lightning loop "
+                          "takes (class_path swap only); the headline needs GraphedTrainStep, i.e. a host-code edit"},
         "host_enqueue_ms_per_step": host_ms.get("train"),
         "roofline": roof,
         "step_tensor_roofline": {"achieved_tflops": step_tflops, "peak_tflops": pk["bf16_sustained"],
@@ -385,21 +641,28 @@ def run_ours(args):
                                  "note": "valid frames x 656.4 MFLOP / step time vs sustained bf16 peak"},
         "contraction_kernels_one_step": kernels, "contraction_ms_one_step": gemm_ms,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample()
-    print(json.dumps(line))
-    _finish(world)
+    if allreduce_check is not None:
+        line["allreduce_check"] = allreduce_check
+    line.update(extras)
+    if world == 1 and not args.no_cpu_baseline and not args.quick:
+        line["cpu_baseline"] = cpu_baseline_sample(batch, frames)
+    _finish(world, json.dumps(line))
 
 
-def _finish(world):
-    """Multi-rank teardown.  destroy_process_group() can block for minutes when CUDA graphs that captured NCCL
-    collectives are still alive, so every rank synchronises, meets at a last barrier and leaves without running the
-    NCCL / graph destructors."""
+def _finish(world, line=None):
+    """Single process: print.  Multi-rank: every rank synchronises and meets at a last barrier, THEN rank 0 prints its JSON
+    line (so it is the last line on stdout even with NCCL_DEBUG=INFO) and all leave without running the NCCL / graph
+    destructors -- destroy_process_group() can block for minutes while CUDA graphs that captured NCCL collectives are alive."""
     if world <= 1:
+        if line is not None:
+            print(line)
         return
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    if line is not None:
+        time.sleep(0.5)
+        print(line)
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(0)
@@ -414,13 +677,14 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("RADMMM_BENCH_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--frames", type=int, default=800)
-    ap.add_argument("--ref-batch", type=int, default=2)
-    ap.add_argument("--ref-frames", type=int, default=256)
+    ap.add_argument("--ref-batch", type=int, default=0, help="reference arm: utterances (default: --batch, the same config)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames (default: --frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (no parity-mode / HBM-kernel / front-end / CPU sections)")
     ap.add_argument("--eager", action="store_true", help="skip the CUDA-graph capture; time the eager module path only")
     args = ap.parse_args()
     # safety net: a wedged collective / rendezvous must not hold a GPU box for its whole lease
-    watchdog = threading.Timer(float(os.environ.get("RADMMM_BENCH_WATCHDOG_S", "1200")), lambda: os._exit(3))
+    watchdog = threading.Timer(float(os.environ.get("RADMMM_BENCH_WATCHDOG_S", "1500")), lambda: os._exit(3))
     watchdog.daemon = True
     watchdog.start()
     if args.impl == "reference":

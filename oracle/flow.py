@@ -352,9 +352,10 @@ def length_regulate(x: Tensor, dur: Tensor) -> Tensor:
 
 # --------------------------------------------------------------------------- loss
 def flow_loss(z: Tensor, log_det_list: Sequence[Tensor], log_s_list: Sequence[Tensor], lens_g: Tensor,
-              sigma: float = 1.0):
-    """compute_flow_loss (loss.py:85-110) as called from RADMMMLoss.forward (loss.py:520-528)."""
-    n = lens_g.sum()
+              sigma: float = 1.0, n_elements=None):
+    """compute_flow_loss (loss.py:85-110).  ``n_elements`` defaults to ``sum(lens_g)``; RADMMMLoss.forward
+    (loss.py:520) passes ``floor(sum(out_lens) / n_group_size)`` instead, which differs for odd lengths."""
+    n = lens_g.sum() if n_elements is None else n_elements
     mask = length_mask(lens_g, z.shape[2])[:, None].to(z.dtype)
     log_s_total = sum(torch.sum(ls * mask) for ls in log_s_list)
     log_det_total = sum(log_det_list) * n

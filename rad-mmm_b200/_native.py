@@ -5,6 +5,7 @@ library with ``python -m radmmm_b200.build`` (or ``__graft_entry__.build()``).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import Optional
@@ -139,7 +140,17 @@ def fptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def stream() -> int:
+    """Current stream of the CURRENT device.  The entry points that take tensors (RADMMMFlow.forward / infer, FlowStep,
+    the standalone modules via ``on_device_of``) switch to the tensors' device first; backward passes run on autograd's
+    per-device threads, which have the right device set already."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device_of(t: torch.Tensor):
+    """Context manager: make ``t``'s device current (a no-op when it already is)."""
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        return torch.cuda.device(t.device)
+    return contextlib.nullcontext()
 
 
 def rows(batch: int, tp: int) -> int:

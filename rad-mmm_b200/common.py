@@ -141,19 +141,38 @@ def _prep_stream(device):
 
 # Optional gradient sink (radmmm_b200.ddp.BucketedGradReducer): maps a parameter's storage pointer to a fresh view of
 # its all-reduce bucket so FlowStepFunction.backward writes parameter gradients straight into bucket storage.
-_grad_sink = None
+_grad_sinks: list = []
 
 
 def set_grad_sink(fn):
-    """``fn(param_tensor) -> Tensor | None`` or None to clear."""
-    global _grad_sink
-    _grad_sink = fn
+    """Register ``fn(param_tensor) -> Tensor | None`` (tried in registration order; the first non-None answer wins), or
+    clear every sink with ``None``."""
+    if fn is None:
+        _grad_sinks.clear()
+    elif fn not in _grad_sinks:
+        _grad_sinks.append(fn)
+
+
+def _grad_sink(p):
+    for fn in _grad_sinks:
+        buf = fn(p)
+        if buf is not None:
+            return buf
+    return None
+
+
+_scratch_retired: list = []
 
 
 def _backward_scratch(nbytes: int, device) -> torch.Tensor:
+    """Backward scratch shared by all flow steps of a device (they run one after the other).  A buffer that has to grow
+    is RETIRED, not freed: CUDA graphs captured at a smaller shape keep replaying into the old one
+    (radmmm_b200.graphs.GraphedTrainStepPool holds several shapes at once)."""
     key = (device.index,)
     buf = _scratch_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _scratch_retired.append(buf)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _scratch_cache[key] = buf
     return buf
@@ -214,7 +233,8 @@ class WN(nn.Module):
         for _ in range(n_layers):
             self.in_layers.append(_ConvNormHolder(n_channels, n_channels, kernel_size))
             self.res_skip_layers.append(_NormedConv1d(n_channels, n_channels, 1, xavier=False))
-        self._prepared = {}        # mode -> (version key, uint8 tensor)
+        self._prepared = {}        # mode -> (version key | None = stale, uint8 tensor)
+        self._fresh_mode = None    # mode whose weights were prepared for the forward in flight (see ``prepare``)
 
     # -- raw parameter list in the fixed order FlowStepFunction uses
     def raw_params(self) -> List[Optional[torch.Tensor]]:
@@ -239,35 +259,54 @@ class WN(nn.Module):
             d.rs_g[i], d.rs_v[i], d.rs_b[i] = (N.fptr(p) for p in params[o: o + 3])
         d.end_w, d.end_b = N.fptr(params[3 + 6 * L]), N.fptr(params[4 + 6 * L])
 
-    def prepared(self, d: N.FlowDesc, params: List[Optional[torch.Tensor]]) -> torch.Tensor:
-        """Weight-normed, re-laid-out weights for ``d.mode``; recomputed only when a raw parameter changed."""
+    def prepared(self, d: N.FlowDesc, params: List[Optional[torch.Tensor]], training: bool = False,
+                 consume_fresh: bool = True) -> torch.Tensor:
+        """Weight-normed, re-laid-out weights for ``d.mode``.
+
+        ``training`` (a forward that will be differentiated): the preparation runs on EVERY call -- optimizers that
+        update ``p.data`` in place (the reference's RAdam, radam.py:63-142) do not bump the tensors' version counters, so
+        a version-keyed cache would keep serving the step-0 weights.  The one exception is the preparation RADMMMFlow
+        enqueued for this very forward on its preparation stream (``prepare`` leaves a one-shot token).
+        Otherwise (inference, no grad): cached on (data_ptr, version) of every raw parameter; a training-mode
+        preparation leaves the cache marked stale, so the first inference call after training steps re-derives them.
+        """
         lib = N.lib()
-        key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
         hit = self._prepared.get(d.mode)
         if hit is None or hit[1].device != params[1].device:
             nbytes = lib.radmmm_flow_prepared_bytes(d.mode, d.C, d.D, d.H, d.L)
             hit = (None, torch.zeros(nbytes, dtype=torch.uint8, device=params[1].device))
         d.prepared = N.ptr(hit[1])
+        if training:
+            if consume_fresh and self._fresh_mode == d.mode:
+                self._fresh_mode = None
+            else:
+                N.check(lib.radmmm_flow_prepare(C.byref(d), N.stream()))
+            self._prepared[d.mode] = (None, hit[1])
+            return hit[1]
+        key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
         if hit[0] != key:
             N.check(lib.radmmm_flow_prepare(C.byref(d), N.stream()))
-            hit = (key, hit[1])
-            self._prepared[d.mode] = hit
+        self._prepared[d.mode] = (key, hit[1])
         return hit[1]
 
     def invalidate_prepared(self) -> None:
-        """Forget the prepared weights (as after an optimizer step that bypassed the tensors' version counters)."""
+        """Forget the prepared weights (e.g. after parameters were swapped through ``p.data`` outside a training step)."""
         self._prepared = {m: (None, buf) for m, (_, buf) in self._prepared.items()}
+        self._fresh_mode = None
 
-    def prepare(self, precision: str) -> None:
-        """Weight-norm + re-layout for ``precision`` if any raw parameter changed since the last call (enqueued on the
-        current stream).  RADMMMFlow.forward runs this for every flow on the side stream while the context LSTM runs."""
+    def prepare(self, precision: str, training: bool = False) -> None:
+        """Weight-norm + re-layout for ``precision`` (enqueued on the current stream).  RADMMMFlow.forward runs this for
+        every flow on its preparation stream while the context LSTM runs; in training it always recomputes and leaves
+        a one-shot token that the flow step of the same forward consumes."""
         d = N.FlowDesc()
         d.mode, d.B, d.C, d.Tp = N.MODES[precision], 1, 2 * self.n_in_channels, 1
         d.D, d.H, d.L = self.n_context_dim, self.n_channels, self.n_layers
         params = self.raw_params()
         with torch.no_grad():
             self.fill_desc(d, params)
-            self.prepared(d, params)
+            self.prepared(d, params, training=training, consume_fresh=False)
+        if training:
+            self._fresh_mode = d.mode
 
     def forward(self, forward_input, seq_lens=None):
         """(z0 (B,Cin,T), context (B,D,T)) -> (B, 2*Cin, T).  Inference-only when called on its own; training goes
@@ -312,7 +351,7 @@ class FlowStepFunction(torch.autograd.Function):
         d = _make_desc(wn, mode, batch, chans, tp, scaling_fn, training, lens)
         plist = list(params)
         wn.fill_desc(d, plist)
-        prepared = wn.prepared(d, plist)
+        prepared = wn.prepared(d, plist, training=training)
         rows = _context_rows(ctx_btd, lens, mode)
         d.ctx_rows = N.ptr(rows.rows)
         ws = torch.empty(lib.radmmm_flow_workspace_bytes(mode, int(training), batch, tp, chans, d.D, d.H, d.L),
@@ -353,7 +392,7 @@ class FlowStepFunction(torch.autograd.Function):
         dlog_s = dlog_s.contiguous() if dlog_s is not None else None
         grads = []
         for p in plist:
-            buf = _grad_sink(p) if _grad_sink is not None else None
+            buf = _grad_sink(p)
             grads.append(buf if buf is not None else torch.empty_like(p))
         g = N.FlowGrads()
         L = wn.n_layers
@@ -387,6 +426,9 @@ def _flow_apply(wn: WN, W, W_inv, mean, z, context, seq_lens, scaling_fn: str, p
     """Shared driver.  ``context`` is (B, D, Tp) like the reference's ``context_w_spkvec``."""
     if not z.is_cuda:
         raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    if z.device.index != torch.cuda.current_device():
+        with torch.cuda.device(z.device):
+            return _flow_apply(wn, W, W_inv, mean, z, context, seq_lens, scaling_fn, precision, inverse, want_params)
     mode = N.MODES[precision]
     batch, chans, tp = z.shape
     lens = _lens_of(seq_lens, batch, tp, z.device)

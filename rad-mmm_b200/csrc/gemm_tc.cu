@@ -513,23 +513,31 @@ static int make_map(CUtensorMap* map, const void* ptr, long long inner, long lon
     return RADMMM_OK;
 }
 
+constexpr int kMaxDevices = 64;      // function attributes and SM counts are per device
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 template <int MODE, int KIND, int BN, bool WGRAD, int CL>
 static int launch_inst(const TcParams& P, int n_tiles_total, cudaStream_t st) {
     using C = Cfg<MODE, BN, CL>;
     auto kern = gemm_tc_kernel<MODE, KIND, BN, WGRAD, CL>;
-    static bool configured = false;
-    static int max_clusters = 0;
+    static bool configured_dev[kMaxDevices] = {};
+    static int max_clusters_dev[kMaxDevices] = {};
+    const int dev = current_device();
+    bool& configured = configured_dev[dev];
+    int& max_clusters = max_clusters_dev[dev];
     if (!configured) {
         RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
         if (CL > 1) {

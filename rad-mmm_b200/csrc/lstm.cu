@@ -413,7 +413,10 @@ int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, con
     p.xproj = xproj; p.whh[0] = whh_f; p.whh[1] = whh_r; p.out = out; p.gates = gates; p.cstate = cstate;
     const size_t smem = sizeof(float) * ((size_t)U * H * 4 + (size_t)p.Bp * H);
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d, B=%d)", smem, H, B);
-    static size_t smem_set_fwd = 0;
+    static size_t smem_set_fwd_dev[64] = {};        // function attributes are per device
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    size_t& smem_set_fwd = smem_set_fwd_dev[dev_id & 63];
     if (smem > smem_set_fwd) {
         RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RADMMM_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -436,7 +439,10 @@ int lstm_backward(const float* dout, const float* gates, const float* cstate, co
     p.whh[0] = whh_f; p.whh[1] = whh_r; p.dgates = dgates;
     const size_t smem = sizeof(float) * ((size_t)U * 4 * H + (size_t)BT * 4 * H + 8 * U * BT);
     RADMMM_REQUIRE(smem <= 220 * 1024, "lstm: shared memory %zu B exceeds the SM (H=%d)", smem, H);
-    static size_t smem_set_bwd = 0;
+    static size_t smem_set_bwd_dev[64] = {};
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    size_t& smem_set_bwd = smem_set_bwd_dev[dev_id & 63];
     if (smem > smem_set_bwd) {
         RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RADMMM_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

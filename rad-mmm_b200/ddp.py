@@ -40,9 +40,9 @@ class BucketedGradReducer:
     ALIGN = 64      # elements
 
     def __init__(self, module: torch.nn.Module, bucket_key: Callable[[str], str] = default_bucket_key,
-                 process_group=None, average: bool = True):
+                 process_group=None, average: bool = True, force_single: bool = False):
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.world = dist.get_world_size(process_group) if (dist.is_initialized() and not force_single) else 1
         self.average = average
         self.buckets: Dict[str, dict] = {}
         self._handles: List = []
@@ -63,6 +63,7 @@ class BucketedGradReducer:
             b["flat"] = torch.zeros(n, dtype=p0.dtype, device=p0.device)
             b["views"] = [b["flat"][off:off + p.numel()].view_as(p) for p, off in zip(b["params"], b["offsets"])]
             b["pending"] = len(b["params"])
+            b["launched"] = False
             for p, v in zip(b["params"], b["views"]):
                 p.register_post_accumulate_grad_hook(self._make_hook(key, v))
         self.reset()
@@ -73,11 +74,16 @@ class BucketedGradReducer:
 
     def fresh_view(self, param: torch.Tensor) -> Optional[torch.Tensor]:
         """A NEW tensor object viewing ``param``'s slot of its bucket (autograd adopts it as ``.grad`` without a copy
-        because nothing else references the object)."""
+        because nothing else references the object).  Returns None -- the caller then writes into a private tensor and
+        autograd accumulates normally -- when the parameter already holds a gradient (``zero_grad(set_to_none=False)``,
+        gradient accumulation, a second backward): that gradient lives in the very slot a view would alias, and the
+        kernels OVERWRITE their output."""
         slot = self._slot_of.get(param.data_ptr())
         if slot is None:
             return None
-        flat, off, shape = slot
+        flat, off, shape, owner = slot
+        if owner.grad is not None:
+            return None
         n = 1
         for d in shape:
             n *= d
@@ -94,14 +100,18 @@ class BucketedGradReducer:
         self._slot_of = {}
         for b in self.buckets.values():
             b["pending"] = len(b["params"])
+            b["launched"] = False
             for p, v, off in zip(b["params"], b["views"], b["offsets"]):
                 self._view_of[id(p)] = v
-                self._slot_of[p.data_ptr()] = (b["flat"], off, tuple(p.shape))
+                self._slot_of[p.data_ptr()] = (b["flat"], off, tuple(p.shape), p)
         self._handles = []
 
     def _make_hook(self, key: str, view: torch.Tensor):
         def hook(param: torch.Tensor):
             b = self.buckets[key]
+            if b["launched"]:          # a new backward began without finish() (single-process eager use): re-arm
+                b["launched"] = False
+                b["pending"] = len(b["params"])
             g = param.grad
             if g.data_ptr() != view.data_ptr():      # gradient did not land in the bucket: copy it in and alias
                 view.copy_(g)
@@ -112,6 +122,7 @@ class BucketedGradReducer:
         return hook
 
     def _launch(self, b: dict):
+        b["launched"] = True
         if self.world > 1:
             op = dist.ReduceOp.SUM
             if self.average:
@@ -122,9 +133,12 @@ class BucketedGradReducer:
             self._handles.append(dist.all_reduce(b["flat"], op=op, group=self.group, async_op=True))
 
     def finish(self):
-        """Wait for every outstanding all-reduce (call after ``backward``), then re-arm for the next step."""
-        for b in self.buckets.values():         # buckets with parameters that received no gradient this step
-            if 0 < b["pending"] < len(b["params"]):
+        """Wait for every outstanding all-reduce (call after ``backward``), then re-arm for the next step.  EVERY bucket
+        is reduced every step: parameters that received no gradient contribute zeros (all ranks must issue the same
+        collectives; buckets completed during backward go first, in backward order, the rest here in bucket order --
+        ranks whose sets of unused parameters differ per step are not supported, as with DDP's static graph)."""
+        for b in self.buckets.values():
+            if not b["launched"]:
                 for p, v in zip(b["params"], b["views"]):
                     if p.grad is None:
                         v.zero_()

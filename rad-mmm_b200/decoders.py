@@ -142,8 +142,9 @@ class RADMMMFlow(RADMMM):
 
     def invalidate_weight_cache(self):
         """Treat every parameter as changed: the next forward re-runs weight norm + re-layout for all flows and the
-        LSTM input weights, exactly as it does after an optimizer step (which bumps the tensors' version counters).
-        bench.py calls this every step because its timed loop has no optimizer."""
+        LSTM input weights.  Training forwards do that on every call anyway (they never trust version counters: the
+        reference RAdam updates ``p.data`` without bumping them); this is for INFERENCE after weights were swapped
+        through ``p.data`` outside a training step (EMA copies and the like)."""
         from . import lstm as _lstm
         for fs in self.flows:
             tfn = fs.coupling_tfn
@@ -161,11 +162,14 @@ class RADMMMFlow(RADMMM):
         main_stream = torch.cuda.current_stream(device)
         prep.wait_stream(main_stream)
         events = []
+        grad_on = torch.is_grad_enabled()
         with torch.cuda.stream(prep):
             for fs in self.flows:
                 tfn = fs.coupling_tfn
                 if hasattr(tfn, "affine_param_predictor"):
-                    tfn.affine_param_predictor.prepare(tfn.precision)
+                    wn = tfn.affine_param_predictor
+                    # a forward that will be differentiated re-derives the weights every time (see WN.prepared)
+                    wn.prepare(tfn.precision, training=grad_on and any(p.requires_grad for p in wn.parameters()))
                 # the 1x1-conv matrix W = P (L + I) (U + diag) and log|det W| depend on the parameters only: assemble
                 # them here too (a dozen tiny kernels per flow, forward and backward) instead of on the flow chain
                 conv = fs.invtbl_conv
@@ -183,6 +187,9 @@ class RADMMMFlow(RADMMM):
         return events
 
     def forward(self, mel, spk_vecs, context, out_lens, f0=None, energy_avg=None, accent_vecs=None):
+        if mel.is_cuda and mel.device.index != torch.cuda.current_device():
+            with torch.cuda.device(mel.device):      # the native launches go to the CURRENT device's current stream
+                return self.forward(mel, spk_vecs, context, out_lens, f0, energy_avg, accent_vecs)
         lengths = out_lens.lengths if hasattr(out_lens, "lengths") else out_lens
         prep_done = self._prepare_weights_async(mel.device) if mel.is_cuda else None
         context_w_spkvec = self.preprocess_context(context, spk_vecs, lengths, f0, energy_avg, accent_vecs=accent_vecs)
@@ -208,6 +215,9 @@ class RADMMMFlow(RADMMM):
               residual=None, max_frames: Optional[int] = None):
         """decoders.py:207-248.  ``residual`` (B, n_mel*g, T') optionally injects the latent sample instead of
         drawing it (the reference draws from the CUDA RNG, decoders.py:221-225); it is multiplied by nothing."""
+        if txt_enc.is_cuda and txt_enc.device.index != torch.cuda.current_device():
+            with torch.cuda.device(txt_enc.device):
+                return self.infer(spk_vec, txt_enc, sigma, dur, f0, energy_avg, out_lens, accent_vecs, residual, max_frames)
         if out_lens is None:
             out_lens = dur.sum(1).long().to(txt_enc.device)
         # ``max_frames`` (the padded output length, e.g. f0.shape[1]) avoids two device syncs; radmmm_b200.graphs.GraphedInfer

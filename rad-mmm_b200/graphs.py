@@ -7,8 +7,11 @@ the flow NLL and the complete backward pass, including the side-stream forks -- 
 buffers; every later step is ``copy inputs -> replay``.  Sequence lengths are device data, so one graph serves every
 batch that is padded to the captured (batch, frames) shape.
 
-Gradients land in the parameters' ``.grad`` tensors, which are allocated during capture and re-written by every replay
-(do not set them to None between steps; zeroing is unnecessary because a replay overwrites them).
+Gradients land in ONE persistent arena per decoder (flat buckets of ``radmmm_b200.ddp.BucketedGradReducer``, allocated
+outside any graph): the backward kernels write straight into it, ``p.grad`` is a view of it, and every graph captured
+for that decoder -- ``GraphedTrainStepPool`` keeps one per frame bucket -- writes the same memory, so an optimizer
+always reads the gradients of the step that ran last.  Do not set ``.grad`` to None between steps; zeroing is
+unnecessary because a replay overwrites every gradient.
 """
 from __future__ import annotations
 
@@ -19,6 +22,20 @@ import torch
 from . import loss as L
 from .common import SequenceLength
 
+
+def grad_arena(decoder, reducer=None):
+    """The decoder's persistent gradient arena: ``reducer`` if given (multi-GPU: the caller's BucketedGradReducer, whose
+    buckets are also the all-reduce buffers), else a private single-process BucketedGradReducer created once per decoder."""
+    from .ddp import BucketedGradReducer
+    if reducer is not None:
+        decoder._radmmm_grad_arena = reducer
+        return reducer
+    arena = getattr(decoder, "_radmmm_grad_arena", None)
+    if arena is None:
+        arena = BucketedGradReducer(decoder, process_group=None, force_single=True).install()
+        decoder._radmmm_grad_arena = arena
+    return arena
+
 _INPUT_KEYS = ("mel", "spk_vecs", "context", "out_lens", "f0", "energy_avg", "accent_vecs")
 
 
@@ -26,17 +43,23 @@ class GraphedTrainStep:
     """decoder forward + flow NLL + backward as one replayable CUDA graph.
 
     ``example`` is a dict with the keys of ``radmmm_b200.synthetic.synthetic_batch`` (mel (B,80,T), spk_vecs (B,16),
-    context (B,n_text,T), out_lens (B), f0 (B,T), energy_avg (B,T), accent_vecs (B,n_acc)); only shapes and dtypes matter.
-    ``after_backward`` (optional) is called inside the captured region after ``loss.backward()`` (e.g. the gradient
-    all-reduce of ``radmmm_b200.ddp.BucketedGradReducer.finish``).
+    context (B,n_text,T), out_lens (B), f0 (B,T), energy_avg (B,T), accent_vecs (B,n_acc)).  For a decoder whose
+    whitening layer is already initialised only shapes and dtypes matter; for a FRESH decoder the warm-up steps run the
+    reference's data-dependent initialisation (common.py:569-591) on ``example``, so pass a real first batch.
+    ``reducer``: the ``BucketedGradReducer`` of a multi-GPU run (its ``finish`` -- the bucketed all-reduce -- is captured
+    after ``backward``); single-process runs get a private gradient arena.  ``after_backward`` (optional) is called inside
+    the captured region after that.  The loss follows ``RADMMMLoss.forward`` (loss.py:518-528):
+    ``n_elements = floor(sum(out_lens) / n_group_size)``.
     """
 
     def __init__(self, decoder, example: Dict[str, torch.Tensor], sigma: float = 1.0, warmup: int = 3,
-                 after_backward: Optional[Callable[[], None]] = None):
+                 after_backward: Optional[Callable[[], None]] = None, reducer=None):
         dev = next(decoder.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         self.decoder, self.sigma, self.after_backward = decoder, sigma, after_backward
+        self.arena = grad_arena(decoder, reducer)
+        self.params = [p for p in decoder.parameters() if p.requires_grad]
         self.static = {k: example[k].detach().to(dev).clone() for k in _INPUT_KEYS if example.get(k) is not None}
         self.frames = int(self.static["mel"].shape[2])
         self.group = decoder.n_group_size
@@ -48,20 +71,23 @@ class GraphedTrainStep:
                 self._step()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        for p in decoder.parameters():
-            p.grad = None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._step()
 
     def _step(self) -> torch.Tensor:
         st, dec = self.static, self.decoder
-        dec.invalidate_weight_cache()          # parameters change between replays: re-run weight norm / re-layout
+        # every captured / warm-up step starts without gradients, so autograd ADOPTS the arena views the backward
+        # kernels wrote into (no copy, no accumulate) and ``p.grad`` ends up aliasing the persistent arena
+        for p in self.params:
+            p.grad = None
         out = dec(st["mel"], st["spk_vecs"], st["context"], SequenceLength(st["out_lens"], self.frames),
                   f0=st.get("f0"), energy_avg=st.get("energy_avg"), accent_vecs=st.get("accent_vecs"))
         lens_g = torch.div(st["out_lens"], self.group, rounding_mode="floor")
-        loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g, self.sigma)
+        loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g, self.sigma,
+                             n_elements=L.n_elements_like_reference(st["out_lens"], self.group))
         loss.backward()
+        self.arena.finish()                    # multi-GPU: the bucketed all-reduce; always: re-arm the arena
         if self.after_backward is not None:
             self.after_backward()
         return loss.detach()
@@ -159,7 +185,8 @@ class GraphedTrainStepPool:
     batch up to the next bucket (e.g. 512 / 640 / 768 / 896 frames) and replays that bucket's graph.
 
     ``step_factory(decoder, example)`` builds the step object (default: GraphedTrainStep); the batch size is fixed by the
-    first batch of each bucket.
+    first batch of each bucket.  All buckets share the decoder's gradient arena (see the module docstring), so
+    ``optimizer.step()`` after any bucket's replay consumes that replay's gradients.
     """
 
     def __init__(self, decoder, frame_buckets, step_factory=None, **step_kwargs):

@@ -33,22 +33,35 @@ class _MaskedSum(torch.autograd.Function):
         return dx, None, None
 
 
-def flow_nll(z, log_det_W_list, log_s_list, lens_g, sigma: float = 1.0):
-    """(loss, loss_prior) of loss.py:85-110 from grouped lengths instead of a dense mask."""
+def flow_nll(z, log_det_W_list, log_s_list, lens_g, sigma: float = 1.0, n_elements=None, n_dims=None):
+    """(loss, loss_prior) of loss.py:85-110 from grouped lengths instead of a dense mask.
+
+    ``n_elements`` is the log-det multiplier and, times ``n_dims``, the normaliser.  The reference's caller passes
+    ``floor(sum(out_lens) / n_group_size)`` (RADMMMLoss.forward, loss.py:520), which differs from ``sum(lens_g)`` when
+    lengths are odd; use :func:`n_elements_like_reference` for that convention.  Defaults: ``sum(lens_g)`` and ``z.size(1)``.
+    """
     lens = lens_g.to(device=z.device, dtype=torch.int32).contiguous()
-    n = lens.sum().to(torch.float32)
+    if n_elements is None:
+        n_elements = lens.sum()
+    n = torch.as_tensor(n_elements, device=z.device).to(torch.float32)
     log_s_total = sum(_MaskedSum.apply(ls, lens, False) for ls in log_s_list)
     log_det_total = sum(log_det_W_list) * n if len(log_det_W_list) else 0.0
     prior = _MaskedSum.apply(z, lens, True) / (2 * sigma * sigma)
-    denom = n * z.size(1)
+    denom = n * (z.size(1) if n_dims is None else n_dims)
     return (prior - log_s_total - log_det_total) / denom, prior / denom
 
 
+def n_elements_like_reference(out_lens, n_group_size: int):
+    """``torch.div(out_lens.sum(), n_group_size, rounding_mode='floor')`` -- RADMMMLoss.forward, loss.py:520."""
+    return torch.div(out_lens.sum(), n_group_size, rounding_mode="floor")
+
+
 def compute_flow_loss(z, log_det_W_list, log_s_list, n_elements, n_dims, mask, sigma=1.0):
-    """Same signature as the reference (loss.py:85).  ``mask`` is the (B,1,T') prefix mask; lengths are recovered
-    from it.  Unlike the reference, ``log_det_W_list[0]`` is NOT modified in place."""
+    """Same signature and arithmetic as the reference (loss.py:85-110): ``n_elements`` and ``n_dims`` are honoured as
+    passed.  ``mask`` is the (B,1,T') prefix mask; the per-utterance lengths are recovered from it.  Unlike the
+    reference, ``log_det_W_list[0]`` is NOT modified in place."""
     lens = mask.reshape(mask.shape[0], -1).sum(1).to(torch.int32)
-    return flow_nll(z, list(log_det_W_list), log_s_list, lens, sigma)
+    return flow_nll(z, list(log_det_W_list), log_s_list, lens, sigma, n_elements=n_elements, n_dims=n_dims)
 
 
 class RADMMMFlowLoss(torch.nn.Module):
@@ -63,5 +76,5 @@ class RADMMMFlowLoss(torch.nn.Module):
         lengths = out_lens.lengths if hasattr(out_lens, "lengths") else out_lens
         lens_g = torch.div(lengths, self.n_group_size, rounding_mode="floor")
         loss, prior = flow_nll(model_output["z_mel"], model_output["log_det_W_list"], model_output["log_s_list"],
-                               lens_g, self.sigma)
+                               lens_g, self.sigma, n_elements=n_elements_like_reference(lengths, self.n_group_size))
         return {"loss_mel": (loss, 1.0), "loss_prior_mel": (prior, 0.0)}

@@ -15,14 +15,16 @@ from . import _native as N
 _wcache = {}
 
 
-def _prepared_weights(lstm: torch.nn.LSTM, mode: int, params):
+def _prepared_weights(lstm: torch.nn.LSTM, mode: int, params, training: bool):
     """[W_ih_fwd; W_ih_rev] zero-padded to (8H_pad, In_pad) and its transpose, in the act format of ``mode``.
-    Cached on the parameter versions (re-done after every optimizer step, never at inference)."""
+    Training forwards redo it every call (optimizers that write ``p.data`` do not bump version counters, so a
+    version-keyed cache would go stale -- see common.WN.prepared); inference caches on (data_ptr, version), and a
+    training call leaves that cache marked stale."""
     lib = N.lib()
     wih_f, wih_r = params[0], params[4]
-    key = (id(lstm), mode, wih_f.data_ptr(), wih_f._version, wih_r.data_ptr(), wih_r._version)
+    key = None if training else (id(lstm), mode, wih_f.data_ptr(), wih_f._version, wih_r.data_ptr(), wih_r._version)
     hit = _wcache.get(id(lstm))
-    if hit is not None and hit[0] == key:
+    if key is not None and hit is not None and hit[0] == key:
         return hit[1]
     h4, n_in = wih_f.shape
     inp = N.round_up(n_in, 128)
@@ -75,7 +77,8 @@ class ContextLSTMFunction(torch.autograd.Function):
         hid = whh_f.shape[1]
         r = N.rows(b, t)
         params = (wih_f, whh_f, bih_f, bhh_f, wih_r, whh_r, bih_r, bhh_r)
-        wa, wta, inp, n8 = _prepared_weights(lstm, mode, params)
+        wa, wta, inp, n8 = _prepared_weights(lstm, mode, params, training=any(ctx.needs_input_grad))
+        ctx.wta = wta
         x_rows = _rows(mode, x, lens)
         bias = torch.zeros(n8, device=x.device)
         bias[:4 * hid] = bih_f + bhh_f
@@ -107,7 +110,7 @@ class ContextLSTMFunction(torch.autograd.Function):
         ws = torch.empty(lib.radmmm_lstm_workspace_bytes(b, hid), dtype=torch.uint8, device=dev)
         N.check(lib.radmmm_lstm_backward(N.fptr(dout), N.fptr(gates), N.fptr(cstate), N.fptr(whf), N.fptr(whr),
                                          N.ptr(lens), b, t, hid, N.fptr(dg), N.ptr(ws), N.stream()))
-        wa, wta, _, _ = _prepared_weights(ctx.lstm, mode, (wih_f, None, None, None, wih_r))
+        wta = ctx.wta                       # the transposed input weights the forward pass prepared
         dg_act = _cast(mode, dg)
         k8 = 8 * hid
         # dX = dG . [W_ih_f; W_ih_r]  (row GEMM, K = 8H)
@@ -143,6 +146,9 @@ def context_lstm(lstm: torch.nn.LSTM, x_btd: torch.Tensor, lens_g: torch.Tensor,
     """Drop-in for the packed bi-LSTM call.  Batches larger than 64 are processed in chunks (sequences are independent)."""
     if not x_btd.is_cuda:
         raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    if x_btd.device.index != torch.cuda.current_device():
+        with torch.cuda.device(x_btd.device):
+            return context_lstm(lstm, x_btd, lens_g, precision)
     mode = N.MODES[precision]
     lens = lens_g.to(device=x_btd.device, dtype=torch.int32).contiguous()
     p = (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,

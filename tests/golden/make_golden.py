@@ -84,8 +84,10 @@ def decoder_case(fname, n_flows, batch, frames, n_splines=0):
     mask = (torch.arange(frames // 2)[None] < lens_g[:, None])[:, None].float()
     # NB compute_flow_loss accumulates INTO log_det_W_list[0] in place (loss.py:92-100): snapshot it first.
     log_det_snapshot = torch.stack([t.detach().clone() for t in out["log_det_W_list"]])
+    # n_elements exactly as RADMMMLoss.forward computes it (loss.py:520): floor(sum(out_lens) / n_group_size)
+    n_elements = torch.div(lens.sum(), 2, rounding_mode="floor")
     loss, loss_prior = compute_flow_loss(out["z_mel"], list(out["log_det_W_list"]), out["log_s_list"],
-                                         lens_g.sum(), out["z_mel"].size(1), mask, 1.0)
+                                         n_elements, out["z_mel"].size(1), mask, 1.0)
     loss.backward()
     gnames, gsums = grad_checksums(dec.named_parameters())
     # inverse: replay decoders.py:227-246 with an injected residual (infer() itself hard-codes CUDA at :221)

@@ -20,12 +20,12 @@ def _decoder(precision):
 def _eager(dec, bt, frames):
     from radmmm_b200 import loss as L
     from radmmm_b200.common import SequenceLength
-    dec.invalidate_weight_cache()
     for p in dec.parameters():
         p.grad = None
     out = dec(bt["mel"], bt["spk_vecs"], bt["context"], SequenceLength(bt["out_lens"], frames), f0=bt["f0"],
               energy_avg=bt["energy_avg"], accent_vecs=bt["accent_vecs"])
-    loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], bt["out_lens"] // 2)
+    loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], bt["out_lens"] // 2,
+                         n_elements=L.n_elements_like_reference(bt["out_lens"], 2))
     loss.backward()
     return loss.detach().clone(), {n: p.grad.detach().clone() for n, p in dec.named_parameters() if p.grad is not None}
 

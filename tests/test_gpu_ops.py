@@ -21,7 +21,12 @@ MODE_TOL = {"fp32": 2e-5, "bf16x3": 2e-4, "bf16": 3e-2}
 @pytest.mark.parametrize("taps,dil,K,Nout,R", [(1, 1, 128, 256, 384), (5, 1, 128, 256, 384), (5, 8, 256, 128, 384),
                                                 (1, 1, 192, 160, 384), (5, 4, 64, 1024, 384),
                                                 # even tile counts -> 2x2 cluster multicast variant
-                                                (5, 2, 256, 1024, 512), (1, 1, 1024, 512, 1024), (5, 8, 128, 256, 256)])
+                                                (5, 2, 256, 1024, 512), (1, 1, 1024, 512, 1024), (5, 8, 128, 256, 256),
+                                                # 416 tiles of 128 x 256 on 74 CTA-pair slots: every CTA walks 5-6 tiles
+                                                # (TMEM double-buffer phase flips, smem ring wrap-around across tiles)
+                                                (1, 1, 1024, 1024, 13312), (5, 2, 1024, 1024, 13312),
+                                                # odd row-tile count -> the 1-CTA kernel, several tiles per CTA
+                                                (5, 4, 1024, 1024, 13312 + 128)])
 def test_conv_rows(precision, taps, dil, K, Nout, R):
     """Row GEMM (the WN conv): y[r] = sum_j W_j x[r + (j-c)d] + bias, zero outside [0,R)."""
     lib = N.lib()
@@ -38,27 +43,29 @@ def test_conv_rows(precision, taps, dil, K, Nout, R):
     N.check(lib.radmmm_conv_rows(mode, N.ptr(xb), xld, xpl, N.ptr(wb), wld, wpl, npad * K, N.fptr(bias), N.fptr(y), npad,
                                  R, K, Nout, taps, dil, N.stream()))
     torch.cuda.synchronize()
-    xd, wd = x.double().cpu(), w.double().cpu()
-    ref = torch.zeros(R, npad, dtype=torch.float64)
+    big = R * K * Nout * taps > 1 << 31          # the checker is a plain fp64 matmul either way; big cases run it on the GPU
+    xd, wd = (x.double(), w.double()) if big else (x.double().cpu(), w.double().cpu())
+    ref = torch.zeros(R, npad, dtype=torch.float64, device=xd.device)
     for j in range(taps):
         s = (j - taps // 2) * dil
         xs = torch.zeros_like(xd)
         lo, hi = max(0, -s), min(R, R - s)
         xs[lo:hi] = xd[lo + s:hi + s]
         ref += xs @ wd[j].t()
-    ref += bias.double().cpu()[None]
+    ref += bias.double().to(ref.device)[None]
     scale = ref.abs().max().item()
-    close(y[:, :Nout], ref[:, :Nout], MODE_TOL[precision] * scale, what=f"conv_rows {precision}")
+    close(y[:, :Nout], ref[:, :Nout].cpu(), MODE_TOL[precision] * scale, what=f"conv_rows {precision}")
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
-@pytest.mark.parametrize("taps,dil,M,Nx", [(1, 1, 128, 256), (5, 2, 256, 128), (1, 1, 256, 1152), (5, 8, 128, 128),
-                                            (5, 1, 1024, 1024)])
-def test_wgrad_rows(precision, taps, dil, M, Nx):
+@pytest.mark.parametrize("taps,dil,M,Nx,R", [(1, 1, 128, 256, 640), (5, 2, 256, 128, 640), (1, 1, 256, 1152, 640),
+                                              (5, 8, 128, 128, 640), (5, 1, 1024, 1024, 640),
+                                              # the shapes the train step launches (res-skip / dilated-conv weight grads)
+                                              (1, 1, 1024, 1024, 3328), (5, 2, 1024, 1024, 3328), (1, 1, 1024, 1024, 13312)])
+def test_wgrad_rows(precision, taps, dil, M, Nx, R):
     """Weight-grad GEMM: out[j][m][n] = sum_r dy[r][m] x[r + (j-c)d][n]."""
     lib = N.lib()
     mode = N.MODES[precision]
-    R = 640
     dy = syn.hash_uniform(f"wg.dy{M}", (R, M)).to(DEV)
     x = syn.hash_uniform(f"wg.x{Nx}", (R, Nx)).to(DEV)
     dyb, dld, dpl = cast_rows(dy, mode)
@@ -67,15 +74,16 @@ def test_wgrad_rows(precision, taps, dil, M, Nx):
     N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dyb), dld, dpl, N.ptr(xb), xld, xpl, N.fptr(out), Nx,
                                   M * Nx, R, M, Nx, taps, dil, 0, N.stream()))
     torch.cuda.synchronize()
-    dyd, xd = dy.double().cpu(), x.double().cpu()
-    ref = torch.zeros(taps, M, Nx, dtype=torch.float64)
+    big = R * M * Nx * taps > 1 << 31
+    dyd, xd = (dy.double(), x.double()) if big else (dy.double().cpu(), x.double().cpu())
+    ref = torch.zeros(taps, M, Nx, dtype=torch.float64, device=xd.device)
     for j in range(taps):
         s = (j - taps // 2) * dil
         xs = torch.zeros_like(xd)
         lo, hi = max(0, -s), min(R, R - s)
         xs[lo:hi] = xd[lo + s:hi + s]
         ref[j] = dyd.t() @ xs
-    close(out, ref, MODE_TOL[precision] * ref.abs().max().item(), what=f"wgrad_rows {precision}")
+    close(out, ref.cpu(), MODE_TOL[precision] * ref.abs().max().item(), what=f"wgrad_rows {precision}")
 
 
 # ------------------------------------------------------------------------------------------------ invertible convs

@@ -246,7 +246,8 @@ def test_decoder_forward_loss_grads_inverse(fname, n_flows, batch, frames):
     close(torch.stack(out["log_det_W_list"]), gd["log_det"], 1e-5)
     close(out["context_w_spkvec"][:, ::33], gd["context"], 1e-5)
     lens_g = bt["out_lens"] // 2
-    loss, prior = of.flow_loss(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g)
+    n_el = torch.div(bt["out_lens"].sum(), 2, rounding_mode="floor")          # RADMMMLoss.forward, loss.py:520
+    loss, prior = of.flow_loss(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g, n_elements=n_el)
     close(loss, gd["loss"], 2e-6)
     close(prior, gd["loss_prior"], 2e-6)
     loss.backward()
