@@ -58,6 +58,7 @@ SIGNATURES = {
     "radmmm_abi_version": (_i, []),
     "radmmm_last_error": (C.c_char_p, []),
     "radmmm_launch_count": (_ll, []),
+    "radmmm_debug_trace": (None, [_fp, _i, _i]),
     "radmmm_profile_enable": (None, [_i]),
     "radmmm_profile_collect": (_i, [_i, _P(C.c_int), _P(C.c_double), _P(C.c_double)]),
     "radmmm_sizeof_flow_desc": (_sz, []),

@@ -86,6 +86,7 @@ extern "C" {
 int radmmm_abi_version(void) { return RADMMM_ABI_VERSION; }
 long long radmmm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+void radmmm_debug_trace(void* device_buf, int max_ctas, int max_launches) { gemm_tc_set_trace(device_buf, max_ctas, max_launches); }
 void radmmm_profile_enable(int on) { g_prof_on = on != 0; if (on) g_prof_n = 0; }
 int radmmm_profile_collect(int max_tags, int* counts, double* ms, double* flops) {
     cudaDeviceSynchronize();

@@ -434,5 +434,6 @@ __device__ __forceinline__ void epi_wgrad(const EpiParams& p, int tap, int m, in
 int launch_gemm_ffma(const GemmArgs& args, cudaStream_t stream);
 int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream);
 int launch_gemm(const GemmArgs& args, int mode, cudaStream_t stream);
+void gemm_tc_set_trace(void* buf, int max_ctas, int max_launches);      // diagnostic in-kernel timeline (tools/gemm_probe.py)
 
 }  // namespace radmmm

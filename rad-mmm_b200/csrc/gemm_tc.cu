@@ -44,8 +44,22 @@ struct TcParams {
     int m_tiles, n_tiles, taps, split_k, k_blocks_total;   // weight-grad: k_blocks_total = R/64
     int acc_segs;                                          // weight-grad: all segments accumulate into one output
     int debug;                                             // probe bits (tools/gemm_probe.py): 1 no epilogue, 2 no MMA, 4 no TMA
+    unsigned long long* trace;                             // tools/gemm_probe.py: [CTA][kTraceSlots] SM-clock / globaltimer stamps
+    int trace_ctas;
     EpiParams epi;
 };
+
+// In-kernel timeline (diagnostic, tools/gemm_probe.py).  Slots per CTA: 0 entry, 1 set-up done, 2 first TMA issued,
+// 3 first operand stage landed, 4 last MMA committed, 5 accumulator visible to the epilogue, 6 epilogue done (warp 4),
+// 7 after the final CTA / cluster barrier (all clock64 of this SM); 8 / 9 globaltimer at entry / exit (ns, device-wide).
+constexpr int kTraceSlots = 10;
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RADMMM_TRACE(slot) do { if (P.trace != nullptr && (int)blockIdx.x < P.trace_ctas) \
+        P.trace[(size_t)blockIdx.x * kTraceSlots + (slot)] = (unsigned long long)clock64(); } while (0)
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -235,6 +249,10 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
     __nv_bfloat16* stage_tiles = reinterpret_cast<__nv_bfloat16*>(smem + C::stages * C::stage_bytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        RADMMM_TRACE(0);
+        if (P.trace != nullptr && (int)blockIdx.x < P.trace_ctas) P.trace[(size_t)blockIdx.x * kTraceSlots + 8] = gtimer();
+    }
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < P.n_a_maps; ++i) { prefetch_tmap(&P.a_hi[i]); if (C::planes == 2) prefetch_tmap(&P.a_lo[i]); }
@@ -259,6 +277,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
     if (CL == 2) cluster_sync_all();          // the peer's barriers exist before any remote arrive / 2-CTA TMA / MMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) RADMMM_TRACE(1);
 
     // Tile walk.  A "walk" position is one 128 x BN tile (CL == 1) or one 256 x BN pair tile (CL == 2, CTA `crank` takes
     // row tile 2*pm + crank).  Weight-grad: the (tap, split-K range) pair is the slowest index.
@@ -339,6 +358,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
                             if (leader) mbar_expect_tx(fb, 2 * C::stage_bytes);
                             else mbar_arrive_remote(fb, 0);
                         }
+                        if (walk == walk_begin && s == seg_begin && kb == kb0) RADMMM_TRACE(2);
                         if (++stage == C::stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -370,6 +390,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (it == 0 && kb == 0 && lane == 0) RADMMM_TRACE(3);
                     if (P.debug & 2) {                            // probe: no MMAs, release the slot at once
                         if (elect_one()) {
                             mbar_arrive(&empty[stage]);
@@ -400,7 +421,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
                             }
                         }
                         tc_commit<CL>(&empty[stage]);                       // smem slot(s) reusable once these MMAs retire
-                        if (kb == total_kb - 1) tc_commit<CL>(&tfull[as]);  // accumulator complete (both CTAs' epilogues)
+                        if (kb == total_kb - 1) { tc_commit<CL>(&tfull[as]); RADMMM_TRACE(4); }  // accumulator complete (both CTAs' epilogues)
                     }
                     __syncwarp();
                     if (++stage == C::stages) { stage = 0; phase ^= 1; }
@@ -448,6 +469,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
             }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
+            if (warp == 4 && lane == 0) RADMMM_TRACE(5);
             bool has_acc = true;
             if (WGRAD) { int kb0, kb1; k_range(split, kb0, kb1); has_acc = kb1 > kb0; }
 #pragma unroll 1
@@ -464,6 +486,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
                 }
             }
             tc_fence_before();
+            if (warp == 4 && lane == 0) RADMMM_TRACE(6);
             if (CL == 2 && !leader) mbar_arrive_remote(&tempty[as], 0);     // the leader's MMA warp owns the wait
             else mbar_arrive(&tempty[as]);
         }
@@ -472,6 +495,10 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
     tc_fence_before();
     __syncthreads();
     if (CL == 2) cluster_sync_all();          // no CTA may exit while its peer can still arrive on its barriers / read its smem
+    if (threadIdx.x == 0) {
+        RADMMM_TRACE(7);
+        if (P.trace != nullptr && (int)blockIdx.x < P.trace_ctas) P.trace[(size_t)blockIdx.x * kTraceSlots + 9] = gtimer();
+    }
     if (warp == 2) {
         tc_fence_after();
         if (CL == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::tmem_cols) : "memory");
@@ -605,8 +632,15 @@ static int probe_bits() {
     const char* e = getenv("RADMMM_B200_TC_PROBE");
     return e ? atoi(e) : 0;
 }
+static unsigned long long* g_trace = nullptr;
+static int g_trace_ctas = 0, g_trace_launches = 0, g_trace_next = 0;
 
 }  // namespace
+
+void gemm_tc_set_trace(void* buf, int max_ctas, int max_launches) {
+    g_trace = reinterpret_cast<unsigned long long*>(buf);
+    g_trace_ctas = max_ctas; g_trace_launches = max_launches; g_trace_next = 0;
+}
 
 int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     RADMMM_REQUIRE(mode == MODE_BF16 || mode == MODE_BF16X3, "gemm_tc: bad mode %d", mode);
@@ -618,6 +652,10 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     P.epi = args.epi;
     P.n_seg = args.n_seg;
     P.debug = probe_bits();
+    if (g_trace != nullptr && g_trace_next < g_trace_launches) {       // launch i writes region i of the buffer
+        P.trace = g_trace + (size_t)g_trace_next++ * g_trace_ctas * kTraceSlots;
+        P.trace_ctas = g_trace_ctas;
+    }
 
     // output tiling
     const int N = args.epi.N;
