@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RADMMM_ABI_VERSION 1
+#define RADMMM_ABI_VERSION 2
 
 /* precision of the WN contractions */
 #define RADMMM_MODE_F32 0     /* fp32 FFMA, exact-parity path                                   */
@@ -146,14 +146,17 @@ int radmmm_flow_backward(const radmmm_flow_desc* d, const float* z_in, const flo
 
 /* Context bi-LSTM recurrence (models/radmmm.py:137-146: pack_padded_sequence -> nn.LSTM(bidirectional, batch_first)
  * -> pad_packed_sequence).  xproj [R][8H] fp32 holds W_ih x + b_ih + b_hh for every row (columns: direction, gate
- * i|f|g|o, unit) and is produced by radmmm_conv_rows; the recurrence runs as ONE cooperative kernel per pass.
+ * i|f|g|o, unit) and is produced by radmmm_conv_rows; the recurrence runs as ONE kernel per pass:
+ *   mode RADMMM_MODE_BF16 (H <= 528): two thread-block clusters of 16 CTAs (one per direction), W_hh as bf16 mma.sync
+ *     fragments in registers, h exchanged through distributed shared memory (st.async + mbarrier), fp32 state;
+ *   other modes: the fp32 cooperative kernel (W_hh in shared memory, exchange through L2 behind a grid barrier).
  * out (B,Tp,2H) must be zero-initialised (frames beyond each length stay zero); gates [R][8H] and cstate [R][2H] are
  * saved for the backward pass; dgates [R][8H] (zero-initialised) receives the pre-activation gate gradients, from which
  * the weight / input gradients follow as contractions (radmmm_wgrad_rows / radmmm_conv_rows).  B <= 64 per call. */
 size_t radmmm_lstm_workspace_bytes(int B, int H);
-int radmmm_lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int32_t* lens, int B, int Tp,
+int radmmm_lstm_forward(int mode, const float* xproj, const float* whh_f, const float* whh_r, const int32_t* lens, int B, int Tp,
                         int H, float* out, float* gates, float* cstate, void* workspace, void* stream);
-int radmmm_lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f,
+int radmmm_lstm_backward(int mode, const float* dout, const float* gates, const float* cstate, const float* whh_f,
                          const float* whh_r, const int32_t* lens, int B, int Tp, int H, float* dgates, void* workspace,
                          void* stream);
 

@@ -15,6 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RADMMM_B200_LIB") or os.path.join(_HERE, "libradmmm_b200.so")   # env override: A/B builds
 MAX_LAYERS = 8
+ABI_VERSION = 2
 ROW_GAP = 16
 MODE_F32, MODE_BF16, MODE_BF16X3 = 0, 1, 2
 MODES = {"fp32": MODE_F32, "bf16": MODE_BF16, "bf16x3": MODE_BF16X3}
@@ -84,8 +85,8 @@ SIGNATURES = {
     "radmmm_conv_rows": (_i, [_i, _fp, _ll, _ll, _fp, _ll, _ll, _ll, _fp, _fp, _ll, _i, _i, _i, _i, _i, _fp]),
     "radmmm_wgrad_rows": (_i, [_i, _fp, _ll, _ll, _fp, _ll, _ll, _fp, _ll, _ll, _i, _i, _i, _i, _i, _i, _fp]),
     "radmmm_lstm_workspace_bytes": (_sz, [_i, _i]),
-    "radmmm_lstm_forward": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp]),
-    "radmmm_lstm_backward": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp]),
+    "radmmm_lstm_forward": (_i, [_i, _fp, _fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp]),
+    "radmmm_lstm_backward": (_i, [_i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp]),
     "radmmm_cast_rows": (_i, [_i, _fp, _ll, _fp, _ll, _fp]),
     "radmmm_spline_forward": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _i, _fp]),
     "radmmm_spline_backward": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _fp]),
@@ -109,7 +110,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.radmmm_abi_version() != 1:
+        if handle.radmmm_abi_version() != ABI_VERSION:
             raise RuntimeError("radmmm_b200: ABI version mismatch between the Python binding and the library")
         if handle.radmmm_sizeof_flow_desc() != C.sizeof(FlowDesc) or handle.radmmm_sizeof_flow_grads() != C.sizeof(FlowGrads):
             raise RuntimeError("radmmm_b200: struct layout mismatch between the Python binding and the library")

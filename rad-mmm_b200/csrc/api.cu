@@ -141,14 +141,14 @@ int radmmm_flow_backward(const radmmm_flow_desc* d, const float* z_in, const flo
 }
 
 size_t radmmm_lstm_workspace_bytes(int B, int H) { return lstm_workspace_bytes(B, H); }
-int radmmm_lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int32_t* lens, int B, int Tp,
+int radmmm_lstm_forward(int mode, const float* xproj, const float* whh_f, const float* whh_r, const int32_t* lens, int B, int Tp,
                         int H, float* out, float* gates, float* cstate, void* workspace, void* stream) {
-    return lstm_forward(xproj, whh_f, whh_r, lens, B, Tp, H, out, gates, cstate, workspace, ST(stream));
+    return lstm_forward(mode, xproj, whh_f, whh_r, lens, B, Tp, H, out, gates, cstate, workspace, ST(stream));
 }
-int radmmm_lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f,
+int radmmm_lstm_backward(int mode, const float* dout, const float* gates, const float* cstate, const float* whh_f,
                          const float* whh_r, const int32_t* lens, int B, int Tp, int H, float* dgates, void* workspace,
                          void* stream) {
-    return lstm_backward(dout, gates, cstate, whh_f, whh_r, lens, B, Tp, H, dgates, workspace, ST(stream));
+    return lstm_backward(mode, dout, gates, cstate, whh_f, whh_r, lens, B, Tp, H, dgates, workspace, ST(stream));
 }
 
 int radmmm_inv1x1(const float* in, const float* W, const float* pre, const float* post, float* out, int B, int Cin,

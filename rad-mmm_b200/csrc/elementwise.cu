@@ -183,51 +183,91 @@ int coupling_bwd(const float* dz_out, const float* dlog_s, const float* z, const
 // as is); a thread owns 2 channels x 4 consecutive frames.  Every global access is a full 128-byte row segment.
 // HBM-bound: 2*C*4 bytes per grouped frame; W (100 KB) comes from L2.
 // =========================================================================================================
-constexpr int INV_TC = 32, INV_TN = 64, INV_TK = 32;
-__global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
+constexpr int INV_TC = 32, INV_TN = 128, INV_TK = 32;
+// One CTA (128 threads) per 32 (co) x 128 (t) output tile; a thread owns 4 channels x 8 consecutive frames, so one k step
+// is three 16-byte shared loads for 32 FMAs (the earlier 2 x 4 micro-tile was shared-memory-bandwidth bound: 28 us per call
+// at B=8, T'=400).  The next K chunk is fetched into registers while the current one is being multiplied.
+__global__ void __launch_bounds__(128) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
                                                      const float* __restrict__ W, const float* __restrict__ pre,
                                                      const float* __restrict__ post, float* __restrict__ out,
                                                      long long out_bs, int Cin, int Cout, int Tp) {
-    __shared__ float ws[INV_TK][INV_TC + 2];      // [k][co]  (+2: float2 reads stay 8-byte aligned, conflict-light)
+    __shared__ __align__(16) float ws[INV_TK][INV_TC + 4];      // [k][co]
     __shared__ __align__(16) float xs[INV_TK][INV_TN];          // [k][t]
     const int t0 = blockIdx.x * INV_TN, co0 = blockIdx.y * INV_TC, b = blockIdx.z;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // 16 (t quads) x 16 (co pairs)
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // 16 (t octets) x 8 (co quads)
     const float* inb = in + (long long)b * in_bs;
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const bool vec_ok = (Tp & 3) == 0 && (in_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    float wreg[8];
+    float4 xreg[8];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                              // W tile: 32 co x 32 ci, rows of 32 consecutive ci
+            const int i = j * 128 + tid, c = i >> 5, k = i & 31;
+            wreg[j] = (co0 + c < Cout && k0 + k < Cin) ? __ldg(W + (long long)(co0 + c) * Cin + k0 + k) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                              // x tile: 32 ci x 128 t, 16-byte pieces
+            const int i = j * 128 + tid, k = i >> 5, q = i & 31;
+            const int ci = k0 + k, t = t0 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ci < Cin && t < Tp) {
+                const float* src = inb + (long long)ci * Tp + t;
+                if (vec_ok && t + 3 < Tp) {
+                    v = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    v.x = __ldg(src);
+                    if (t + 1 < Tp) v.y = __ldg(src + 1);
+                    if (t + 2 < Tp) v.z = __ldg(src + 2);
+                    if (t + 3 < Tp) v.w = __ldg(src + 3);
+                }
+                if (pre) {
+                    const float m = __ldg(pre + ci);
+                    v.x -= m; v.y -= m; v.z -= m; v.w -= m;      // frames past Tp are never stored
+                }
+            }
+            xreg[j] = v;
+        }
+    };
+    fetch(0);
     for (int k0 = 0; k0 < Cin; k0 += INV_TK) {
-        for (int i = tid; i < INV_TC * INV_TK; i += 256) {          // W tile: rows co, 32 consecutive ci each
-            const int c = i >> 5, k = i & 31;
-            ws[k][c] = (co0 + c < Cout && k0 + k < Cin) ? W[(long long)(co0 + c) * Cin + k0 + k] : 0.0f;
-        }
-        for (int i = tid; i < INV_TK * INV_TN; i += 256) {          // x tile: rows ci, 64 consecutive frames each
-            const int k = i >> 6, t = i & 63;
-            const int ci = k0 + k;
-            xs[k][t] = (ci < Cin && t0 + t < Tp) ? inb[(long long)ci * Tp + t0 + t] - (pre ? pre[ci] : 0.0f) : 0.0f;
-        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = j * 128 + tid; ws[i & 31][i >> 5] = wreg[j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = j * 128 + tid; *reinterpret_cast<float4*>(&xs[i >> 5][4 * (i & 31)]) = xreg[j]; }
         __syncthreads();
+        if (k0 + INV_TK < Cin) fetch(k0 + INV_TK);
 #pragma unroll 8
         for (int k = 0; k < INV_TK; ++k) {
-            const float2 w2 = *reinterpret_cast<const float2*>(&ws[k][2 * ty]);
-            const float4 x4 = *reinterpret_cast<const float4*>(&xs[k][4 * tx]);
-            acc[0][0] = fmaf(w2.x, x4.x, acc[0][0]); acc[0][1] = fmaf(w2.x, x4.y, acc[0][1]);
-            acc[0][2] = fmaf(w2.x, x4.z, acc[0][2]); acc[0][3] = fmaf(w2.x, x4.w, acc[0][3]);
-            acc[1][0] = fmaf(w2.y, x4.x, acc[1][0]); acc[1][1] = fmaf(w2.y, x4.y, acc[1][1]);
-            acc[1][2] = fmaf(w2.y, x4.z, acc[1][2]); acc[1][3] = fmaf(w2.y, x4.w, acc[1][3]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][4 * ty]);
+            const float4 xa = *reinterpret_cast<const float4*>(&xs[k][8 * tx]);
+            const float4 xb = *reinterpret_cast<const float4*>(&xs[k][8 * tx + 4]);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
         }
         __syncthreads();
     }
-    const int t = t0 + 4 * tx;
+    const int t = t0 + 8 * tx;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int co = co0 + 2 * ty + i;
-        if (co < Cout) {
-            const float pb = post ? post[co] : 0.0f;
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + 4 * ty + i;
+        if (co < Cout && t < Tp) {
+            const float pb = post ? __ldg(post + co) : 0.0f;
             float* o = out + (long long)b * out_bs + (long long)co * Tp + t;
-            if (t + 3 < Tp && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                *reinterpret_cast<float4*>(o) = make_float4(acc[i][0] + pb, acc[i][1] + pb, acc[i][2] + pb, acc[i][3] + pb);
+            if (t + 7 < Tp && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                reinterpret_cast<float4*>(o)[0] = make_float4(acc[i][0] + pb, acc[i][1] + pb, acc[i][2] + pb, acc[i][3] + pb);
+                reinterpret_cast<float4*>(o)[1] = make_float4(acc[i][4] + pb, acc[i][5] + pb, acc[i][6] + pb, acc[i][7] + pb);
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 8; ++j)
                     if (t + j < Tp) o[j] = acc[i][j] + pb;
             }
         }
@@ -238,7 +278,7 @@ int inv1x1(const float* in, long long in_bs, const float* W, const float* pre, c
            long long out_bs, int B, int Cin, int Cout, int Tp, cudaStream_t st) {
     RADMMM_REQUIRE(Cout >= 1 && Cin >= 1, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
     dim3 grid(cdiv(Tp, INV_TN), cdiv(Cout, INV_TC), B);
-    inv1x1_kernel<<<grid, 256, 0, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
+    inv1x1_kernel<<<grid, 128, 0, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }
@@ -361,16 +401,39 @@ int masked_sum_bwd(const float* x, const int* lens, int B, int C, int Tp, int sq
 // Weight preparation: weight-norm (w = g * v / ||v||, per output channel) and re-layout into the K-major
 // per-tap matrices the contraction kernels read, plus the transposed copies the dgrad GEMMs read.
 // =========================================================================================================
-// one CTA per output channel: norm[co] = ||v[co]||, rowsum[co] = sum v[co]   (fp64 accumulate)
-__global__ void wn_norm_kernel(const float* __restrict__ v, int per_co, float* __restrict__ norm,
-                               float* __restrict__ rowsum) {
+// one CTA per output channel: norm[co] = ||v[co]||, rowsum[co] = sum v[co].  16-byte loads, all of a thread's loads in
+// flight before the first use; fp32 partials over <= 32 products, then fp64 (a row has up to 5280 elements).
+__global__ void __launch_bounds__(256) wn_norm_kernel(const float* __restrict__ v, int per_co, float* __restrict__ norm,
+                                                      float* __restrict__ rowsum) {
     const int co = blockIdx.x;
     const float* p = v + (long long)co * per_co;
     double s2 = 0.0, s1 = 0.0;
-    for (int i = threadIdx.x; i < per_co; i += blockDim.x) {
-        const double x = p[i];
-        s2 += x * x;
-        s1 += x;
+    if ((per_co & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        const int n4 = per_co >> 2;
+        for (int base = 0; base < n4; base += 256 * 8) {
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = base + j * 256 + threadIdx.x;
+                t[j] = i < n4 ? __ldg(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float a2 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a2 = fmaf(t[j].x, t[j].x, a2); a2 = fmaf(t[j].y, t[j].y, a2);
+                a2 = fmaf(t[j].z, t[j].z, a2); a2 = fmaf(t[j].w, t[j].w, a2);
+                a1 += (t[j].x + t[j].y) + (t[j].z + t[j].w);
+            }
+            s2 += (double)a2;
+            s1 += (double)a1;
+        }
+    } else {
+        for (int i = threadIdx.x; i < per_co; i += blockDim.x) {
+            const double x = p[i];
+            s2 += x * x;
+            s1 += x;
+        }
     }
     __shared__ double r2[8], r1[8];
     s2 = warp_sum(s2);
@@ -392,40 +455,142 @@ int wn_norm(const float* v, int n_co, int per_co, float* norm, float* rowsum, cu
 }
 
 // v (co, ci_total, k) fp32; columns [ci_begin, ci_begin+n_ci) go to dst[tap][co][ci - ci_begin] (ld_dst, tap stride)
-// and dstT[tap][ci - ci_begin][co].  scale[co] = g/||v|| (or 1 when g == null).  32x32 tiles, smem transpose.
-template <int MODE>
-__global__ void wn_scatter_kernel(const float* __restrict__ v, const float* __restrict__ g,
-                                  const float* __restrict__ norm, int n_co, int ci_total, int ksize, int ci_begin,
-                                  int n_ci, ActMat dst, long long dst_tap, ActMat dstT, long long dstT_tap) {
-    __shared__ float tile[32][33];
-    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32, tap = blockIdx.z;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int i = ty; i < 32; i += 8) {
-        const int co = co0 + i, ci = ci0 + tx;
+// and dstT[tap][ci - ci_begin][co].  scale[co] = g/||v|| (or 1 when g == null).
+// One CTA per 32 (co) x 64 (ci) block, ALL taps: each output channel contributes one contiguous run of 64*KS floats,
+// read once with full-line loads into shared memory; both layouts are then written with 16-byte stores (8 bf16 per
+// lane: 128-byte runs along ci for the K-major copy, 64-byte runs along co for the transposed copy).
+constexpr int WS_CO = 32, WS_CI = 64;
+template <int MODE, int KS>
+__global__ void __launch_bounds__(256) wn_scatter_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                         const float* __restrict__ norm, int n_co, int ci_total, int ci_begin,
+                                                         int n_ci, ActMat dst, long long dst_tap, ActMat dstT, long long dstT_tap) {
+    constexpr int RUN = WS_CI * KS;               // floats per output channel in this block
+    constexpr int LDS_ = RUN + 1;                 // +1: conflict-light column reads
+    extern __shared__ float tile[];               // [WS_CO][LDS_]
+    const int co0 = blockIdx.x * WS_CO, ci0 = blockIdx.y * WS_CI;
+    const int tid = threadIdx.x;
+    const int ci_n = min(WS_CI, n_ci - ci0);      // valid input channels of this block
+    const int run_n = ci_n * KS;
+    for (int i = tid; i < WS_CO * RUN; i += 256) {
+        const int c = i / RUN, j = i - c * RUN;
         float val = 0.0f;
-        if (co < n_co && ci < n_ci) {
-            const float sc = g ? g[co] / norm[co] : 1.0f;
-            val = sc * v[((long long)co * ci_total + ci_begin + ci) * ksize + tap];
-            if (dst.ptr) act_store<MODE>(dst, tap * dst_tap + (long long)co * dst.ld + ci, val);
+        if (co0 + c < n_co && j < run_n) {
+            const float sc = g ? g[co0 + c] / norm[co0 + c] : 1.0f;
+            val = sc * __ldg(v + ((long long)(co0 + c) * ci_total + ci_begin + ci0) * KS + j);
         }
-        tile[i][tx] = val;
+        tile[c * LDS_ + j] = val;
     }
-    if (dstT.ptr == nullptr) return;
     __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int ci = ci0 + i, co = co0 + tx;
-        if (co < n_co && ci < n_ci) act_store<MODE>(dstT, tap * dstT_tap + (long long)ci * dstT.ld + co, tile[tx][i]);
+    constexpr int P = (MODE == MODE_BF16X3) ? 2 : 1;
+    // K-major copy: (tap, co) rows of 64 ci; a thread packs 8 consecutive ci
+    if (dst.ptr != nullptr) {
+        for (int i = tid; i < KS * WS_CO * (WS_CI / 8); i += 256) {
+            const int seg = i % (WS_CI / 8), c = (i / (WS_CI / 8)) % WS_CO, tap = i / ((WS_CI / 8) * WS_CO);
+            const int ci = seg * 8;
+            if (co0 + c >= n_co || ci >= ci_n) continue;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = (ci + e < ci_n) ? tile[c * LDS_ + (ci + e) * KS + tap] : 0.0f;
+            const long long off = tap * dst_tap + (long long)(co0 + c) * dst.ld + ci0 + ci;
+            if constexpr (MODE == MODE_F32) {
+                float* o = reinterpret_cast<float*>(dst.ptr) + off;
+                if (ci + 8 <= ci_n && ((dst.ld | (ci0 + ci)) & 3) == 0) {
+                    reinterpret_cast<float4*>(o)[0] = make_float4(x[0], x[1], x[2], x[3]);
+                    reinterpret_cast<float4*>(o)[1] = make_float4(x[4], x[5], x[6], x[7]);
+                } else {
+                    for (int e = 0; e < 8 && ci + e < ci_n; ++e) o[e] = x[e];
+                }
+            } else {
+#pragma unroll
+                for (int pl = 0; pl < P; ++pl) {
+                    __nv_bfloat162 h[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        h[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                        if (P == 2 && pl == 0) { x[2 * e] -= __bfloat162float(h[e].x); x[2 * e + 1] -= __bfloat162float(h[e].y); }
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dst.ptr) + pl * dst.plane_stride + off;
+                    if (ci + 8 <= ci_n && ((dst.ld | (ci0 + ci)) & 7) == 0) {
+                        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+                    } else {
+                        const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(h);
+                        for (int e = 0; e < 8 && ci + e < ci_n; ++e) o[e] = hs[e];
+                    }
+                }
+            }
+        }
     }
+    // transposed copy: (tap, ci) rows of 32 co; a thread packs 8 consecutive co
+    if (dstT.ptr != nullptr) {
+        for (int i = tid; i < KS * WS_CI * (WS_CO / 8); i += 256) {
+            const int seg = i % (WS_CO / 8), ci = (i / (WS_CO / 8)) % WS_CI, tap = i / ((WS_CO / 8) * WS_CI);
+            const int c = seg * 8;
+            if (ci >= ci_n || co0 + c >= n_co) continue;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = (co0 + c + e < n_co) ? tile[(c + e) * LDS_ + ci * KS + tap] : 0.0f;
+            const long long off = tap * dstT_tap + (long long)(ci0 + ci) * dstT.ld + co0 + c;
+            const bool full = co0 + c + 8 <= n_co;
+            if constexpr (MODE == MODE_F32) {
+                float* o = reinterpret_cast<float*>(dstT.ptr) + off;
+                if (full && ((dstT.ld | (co0 + c)) & 3) == 0) {
+                    reinterpret_cast<float4*>(o)[0] = make_float4(x[0], x[1], x[2], x[3]);
+                    reinterpret_cast<float4*>(o)[1] = make_float4(x[4], x[5], x[6], x[7]);
+                } else {
+                    for (int e = 0; e < 8 && co0 + c + e < n_co; ++e) o[e] = x[e];
+                }
+            } else {
+#pragma unroll
+                for (int pl = 0; pl < P; ++pl) {
+                    __nv_bfloat162 h[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        h[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                        if (P == 2 && pl == 0) { x[2 * e] -= __bfloat162float(h[e].x); x[2 * e + 1] -= __bfloat162float(h[e].y); }
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dstT.ptr) + pl * dstT.plane_stride + off;
+                    if (full && ((dstT.ld | (co0 + c)) & 7) == 0) {
+                        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+                    } else {
+                        const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(h);
+                        for (int e = 0; e < 8 && co0 + c + e < n_co; ++e) o[e] = hs[e];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int MODE, int KS>
+static int wn_scatter_launch(const float* v, const float* g, const float* norm, int n_co, int ci_total, int ci_begin,
+                             int n_ci, ActMat dst, long long dst_tap, ActMat dstT, long long dstT_tap, cudaStream_t st) {
+    const size_t smem = sizeof(float) * WS_CO * (WS_CI * KS + 1);
+    auto kern = wn_scatter_kernel<MODE, KS>;
+    if (smem > 48 * 1024) {
+        static bool set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!set[dev & 63]) {
+            RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set[dev & 63] = true;
+        }
+    }
+    dim3 grid(cdiv(n_co, WS_CO), cdiv(n_ci, WS_CI));
+    kern<<<grid, 256, smem, st>>>(v, g, norm, n_co, ci_total, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
 }
 
 int wn_scatter(int mode, const float* v, const float* g, const float* norm, int n_co, int ci_total, int ksize,
                int ci_begin, int n_ci, ActMat dst, long long dst_tap, ActMat dstT, long long dstT_tap, cudaStream_t st) {
-    dim3 grid(cdiv(n_co, 32), cdiv(n_ci, 32), ksize), block(32, 8);
-    if (mode == MODE_F32) wn_scatter_kernel<MODE_F32><<<grid, block, 0, st>>>(v, g, norm, n_co, ci_total, ksize, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap);
-    else if (mode == MODE_BF16) wn_scatter_kernel<MODE_BF16><<<grid, block, 0, st>>>(v, g, norm, n_co, ci_total, ksize, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap);
-    else wn_scatter_kernel<MODE_BF16X3><<<grid, block, 0, st>>>(v, g, norm, n_co, ci_total, ksize, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap);
-    RADMMM_LAUNCH_CHECK();
-    return RADMMM_OK;
+    RADMMM_REQUIRE(ksize == 1 || ksize == 5, "wn_scatter: kernel size %d (1 or 5)", ksize);
+#define RADMMM_WS(M)                                                                                                   \
+    return ksize == 5 ? wn_scatter_launch<M, 5>(v, g, norm, n_co, ci_total, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap, st) \
+                      : wn_scatter_launch<M, 1>(v, g, norm, n_co, ci_total, ci_begin, n_ci, dst, dst_tap, dstT, dstT_tap, st)
+    if (mode == MODE_F32) { RADMMM_WS(MODE_F32); }
+    if (mode == MODE_BF16) { RADMMM_WS(MODE_BF16); }
+    RADMMM_WS(MODE_BF16X3);
+#undef RADMMM_WS
 }
 
 // padq[co] = log(2) * (g/||v||) * rowsum(v[co]) + bias[co]: the res-skip pre-activation on frames beyond the
@@ -491,12 +656,52 @@ __global__ void __launch_bounds__(256) wn_bwd_staged_kernel(const float* __restr
     float* sv = wsm;                 // [ci][k]  (the layout of v)
     float* sd = wsm + per_co;        // [ci][k]
     const float* vp = v + (long long)co * per_co;
-    for (int i = threadIdx.x; i < per_co; i += 256) sv[i] = vp[i];
-    for (int k = 0; k < ksize; ++k) {
-        const float* p0 = src0 + k * tap0 + (long long)co * ld0;
-        const float* p1 = src1 ? src1 + k * tap1 + (long long)co * ld1 : nullptr;
-        for (int ci = threadIdx.x; ci < ci_total; ci += 256)
-            sd[ci * ksize + k] = ci < n_ci0 ? p0[ci] : p1[ci - n_ci0];
+    // loads are issued in batches of 8 per thread before the first store: enough bytes in flight to cover the DRAM latency
+    if ((per_co & 3) == 0 && (reinterpret_cast<uintptr_t>(vp) & 15) == 0) {
+        const float4* v4 = reinterpret_cast<const float4*>(vp);
+        const int n4 = per_co >> 2;
+        for (int base = 0; base < n4; base += 256 * 4) {
+            float4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int i = base + j * 256 + threadIdx.x; if (i < n4) t[j] = __ldg(v4 + i); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int i = base + j * 256 + threadIdx.x; if (i < n4) reinterpret_cast<float4*>(sv)[i] = t[j]; }
+        }
+    } else {
+        for (int base = 0; base < per_co; base += 256 * 8) {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int i = base + j * 256 + threadIdx.x; if (i < per_co) t[j] = __ldg(vp + i); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int i = base + j * 256 + threadIdx.x; if (i < per_co) sv[i] = t[j]; }
+        }
+    }
+    for (int k0 = 0; k0 < ksize; k0 += 5) {                       // all taps of a chunk of input channels in flight together
+        for (int c0 = 0; c0 < ci_total; c0 += 256 * 2) {
+            float t[5][2];
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk) {
+                const int k = k0 + kk;
+                if (k >= ksize) break;
+                const float* p0 = src0 + k * tap0 + (long long)co * ld0;
+                const float* p1 = src1 ? src1 + k * tap1 + (long long)co * ld1 : nullptr;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int ci = c0 + j * 256 + threadIdx.x;
+                    if (ci < ci_total) t[kk][j] = ci < n_ci0 ? __ldg(p0 + ci) : __ldg(p1 + ci - n_ci0);
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk) {
+                const int k = k0 + kk;
+                if (k >= ksize) break;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int ci = c0 + j * 256 + threadIdx.x;
+                    if (ci < ci_total) sd[ci * ksize + k] = t[kk][j];
+                }
+            }
+        }
     }
     __syncthreads();
     double dot = 0.0;
@@ -525,7 +730,15 @@ __global__ void __launch_bounds__(256) wn_bwd_staged_kernel(const float* __restr
     if (threadIdx.x == 0) dg[co] = d / nrm;
     const float sc = gg / nrm, coef = d / (nrm * nrm);
     float* o = dv + (long long)co * per_co;
-    for (int i = threadIdx.x; i < per_co; i += 256) o[i] = sc * (sd[i] - sv[i] * coef);
+    if ((per_co & 3) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        for (int i = threadIdx.x; i < (per_co >> 2); i += 256) {
+            const float4 a = reinterpret_cast<const float4*>(sd)[i], b = reinterpret_cast<const float4*>(sv)[i];
+            reinterpret_cast<float4*>(o)[i] = make_float4(sc * (a.x - b.x * coef), sc * (a.y - b.y * coef),
+                                                          sc * (a.z - b.z * coef), sc * (a.w - b.w * coef));
+        }
+    } else {
+        for (int i = threadIdx.x; i < per_co; i += 256) o[i] = sc * (sd[i] - sv[i] * coef);
+    }
 }
 
 int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const float* src1, long long ld1,

@@ -305,7 +305,10 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
         float bias[NV];
         load_vec_f32<NV>(p.bias + n0, bias);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) out[i] = valid ? softplus_f<FAST>(acc[i] * ratio + bias[i]) : 0.0f;
+        for (int i = 0; i < NV; ++i) {
+            const float y = softplus_f<FAST>(fmaf(acc[i], ratio, bias[i]));
+            out[i] = valid ? y : 0.0f;
+        }
         store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_RS) {
         // s_i = softplus(res_skip_i(h)); frames beyond the length carry the reference's constant softplus(padq).
@@ -313,7 +316,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
         float s[NV];
         load_vec_f32<NV>((valid ? p.bias : p.padq) + n0, s);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) out[i] = softplus_f<FAST>(valid ? acc[i] + s[i] : s[i]);
+        for (int i = 0; i < NV; ++i) out[i] = softplus_f<FAST>((valid ? acc[i] : 0.0f) + s[i]);
         store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_END || KIND == EPI_DZ0) {
         if (b < p.geom.B && t < p.geom.Tp && n0 < p.N) {
@@ -347,7 +350,10 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
                             float sv[NV];
                             staged_unpack32<MODE>(st, raw[j], sv);
 #pragma unroll
-                            for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<FAST>(sv[i]) : 0.0f;
+                            for (int i = 0; i < NV; ++i) {
+                                const float y = acc[i] * sigmoid_from_softplus<FAST>(sv[i]);
+                                out[i] = valid ? y : 0.0f;
+                            }
                             store_row_vec<MODE, NV>(st, p.dq[l0 + j], r, n0, out);
                         }
                     }
@@ -359,7 +365,10 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
             float sv[NV];
             load_row_vec<MODE, NV>(st, p.sig[l], r, n0, sv);          // s_l = softplus(q_l); d softplus = 1 - exp(-s)
 #pragma unroll
-            for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<FAST>(sv[i]) : 0.0f;
+            for (int i = 0; i < NV; ++i) {
+                const float y = acc[i] * sigmoid_from_softplus<FAST>(sv[i]);
+                out[i] = valid ? y : 0.0f;
+            }
             store_row_vec<MODE, NV>(st, p.dq[l], r, n0, out);
         }
     } else if constexpr (KIND == EPI_DH) {
@@ -367,7 +376,10 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
         load_row_vec<MODE, NV>(st, p.h, r, n0, hv);             // all lanes take part (staged, warp-cooperative)
         const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<FAST>(hv[i]) * ratio : 0.0f;
+        for (int i = 0; i < NV; ++i) {
+            const float y = acc[i] * sigmoid_from_softplus<FAST>(hv[i]) * ratio;
+            out[i] = valid ? y : 0.0f;
+        }
         store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
     } else if constexpr (KIND == EPI_DH0) {
 #pragma unroll
@@ -402,7 +414,10 @@ __device__ __forceinline__ void epi_dh_with_h(const EpiParams& p, const Stager& 
     const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
     float out[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) out[i] = valid ? acc[i] * sigmoid_from_softplus<true>(hv[i]) * ratio : 0.0f;
+    for (int i = 0; i < 32; ++i) {
+        const float y = acc[i] * sigmoid_from_softplus<true>(hv[i]) * ratio;
+        out[i] = valid ? y : 0.0f;
+    }
     store_row_vec<MODE, 32>(st, p.out0, r, n0, out);
 }
 

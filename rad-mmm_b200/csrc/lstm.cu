@@ -405,8 +405,22 @@ static int lstm_common(LstmParams& p, const int* lens, int B, int Tp, int H, voi
     return RADMMM_OK;
 }
 
-int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
+// lstm_cluster.cu
+bool lstm_cluster_supported(int B, int H);
+int lstm_cluster_forward(const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
+                         float* out, float* gates, float* cstate, cudaStream_t st);
+int lstm_cluster_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
+                          const int* lens, int B, int Tp, int H, float* dgates, cudaStream_t st);
+// MODE_BF16 -> the cluster-resident tensor-core recurrence; the fp32-grade modes -> the fp32 cooperative kernel below
+// (RADMMM_B200_LSTM_CLUSTER=0 forces the latter: A/B measurements)
+static bool use_cluster(int mode, int B, int H) {
+    static const bool on = []() { const char* e = getenv("RADMMM_B200_LSTM_CLUSTER"); return !(e && e[0] == '0'); }();
+    return on && mode == MODE_BF16 && lstm_cluster_supported(B, H);
+}
+
+int lstm_forward(int mode, const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
                  float* out, float* gates, float* cstate, void* workspace, cudaStream_t st) {
+    if (use_cluster(mode, B, H)) return lstm_cluster_forward(xproj, whh_f, whh_r, lens, B, Tp, H, out, gates, cstate, st);
     LstmParams p;
     memset(&p, 0, sizeof(p));
     RADMMM_TRY(lstm_common(p, lens, B, Tp, H, workspace));
@@ -430,8 +444,9 @@ int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, con
     return RADMMM_OK;
 }
 
-int lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
+int lstm_backward(int mode, const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
                   const int* lens, int B, int Tp, int H, float* dgates, void* workspace, cudaStream_t st) {
+    if (use_cluster(mode, B, H)) return lstm_cluster_backward(dout, gates, cstate, whh_f, whh_r, lens, B, Tp, H, dgates, st);
     LstmParams p;
     memset(&p, 0, sizeof(p));
     RADMMM_TRY(lstm_common(p, lens, B, Tp, H, workspace));

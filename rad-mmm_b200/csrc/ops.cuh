@@ -33,9 +33,9 @@ int colsum(int mode, ActMat x, const RowGeom& g, int n_cols, int dilation, int u
 int cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, cudaStream_t st);
 
 size_t lstm_workspace_bytes(int B, int H);
-int lstm_forward(const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
+int lstm_forward(int mode, const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
                  float* out, float* gates, float* cstate, void* workspace, cudaStream_t st);
-int lstm_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
+int lstm_backward(int mode, const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
                   const int* lens, int B, int Tp, int H, float* dgates, void* workspace, cudaStream_t st);
 
 int spline_fwd(const float* z1, const float* q, const int* lens, float* z1_out, float* log_s, int B, int Ch, int Tp,

@@ -123,7 +123,10 @@ class RADMMMFlow(RADMMM):
         for fs in self.flows:
             if hasattr(fs.coupling_tfn, "precision"):
                 fs.coupling_tfn.precision = precision
-        self.lstm_precision = precision if precision == "fp32" else "bf16x3"    # the conditioning stays fp32-grade
+        # the context LSTM follows the decoder's mode: "bf16" runs the cluster-resident tensor-core recurrence (bf16 W_hh / h,
+        # fp32 state), "bf16x3" / "fp32" keep the fp32 recurrence (RADMMM_B200_LSTM_FP32=1 pins the fp32-grade path everywhere)
+        pin = os.environ.get("RADMMM_B200_LSTM_FP32", "0") == "1"
+        self.lstm_precision = "bf16x3" if (pin and precision == "bf16") else precision
         return self
 
     def is_attribute_unconditional(self):

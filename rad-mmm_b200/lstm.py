@@ -91,7 +91,7 @@ class ContextLSTMFunction(torch.autograd.Function):
         cstate = torch.empty(r, 2 * hid, device=x.device)
         ws = torch.empty(lib.radmmm_lstm_workspace_bytes(b, hid), dtype=torch.uint8, device=x.device)
         whf, whr = whh_f.contiguous(), whh_r.contiguous()
-        N.check(lib.radmmm_lstm_forward(N.fptr(xproj), N.fptr(whf), N.fptr(whr), N.ptr(lens), b, t, hid, N.fptr(out),
+        N.check(lib.radmmm_lstm_forward(mode, N.fptr(xproj), N.fptr(whf), N.fptr(whr), N.ptr(lens), b, t, hid, N.fptr(out),
                                         N.fptr(gates), N.fptr(cstate), N.ptr(ws), N.stream()))
         ctx.lstm, ctx.mode = lstm, mode
         ctx.dims = (b, t, n_in, hid, r, inp, n8)
@@ -108,7 +108,7 @@ class ContextLSTMFunction(torch.autograd.Function):
         dout = dout.contiguous().float()
         dg = torch.zeros(r, 8 * hid, device=dev)
         ws = torch.empty(lib.radmmm_lstm_workspace_bytes(b, hid), dtype=torch.uint8, device=dev)
-        N.check(lib.radmmm_lstm_backward(N.fptr(dout), N.fptr(gates), N.fptr(cstate), N.fptr(whf), N.fptr(whr),
+        N.check(lib.radmmm_lstm_backward(mode, N.fptr(dout), N.fptr(gates), N.fptr(cstate), N.fptr(whf), N.fptr(whr),
                                          N.ptr(lens), b, t, hid, N.fptr(dg), N.ptr(ws), N.stream()))
         wta = ctx.wta                       # the transposed input weights the forward pass prepared
         dg_act = _cast(mode, dg)
@@ -143,7 +143,9 @@ class ContextLSTMFunction(torch.autograd.Function):
 
 
 def context_lstm(lstm: torch.nn.LSTM, x_btd: torch.Tensor, lens_g: torch.Tensor, precision: str) -> torch.Tensor:
-    """Drop-in for the packed bi-LSTM call.  Batches larger than 64 are processed in chunks (sequences are independent)."""
+    """Drop-in for the packed bi-LSTM call.  Large batches are processed in chunks (sequences are independent).
+    ``precision`` "bf16": contractions in bf16 and the cluster-resident tensor-core recurrence (bf16 W_hh / h, fp32 state);
+    "bf16x3" / "fp32": fp32-grade contractions and the fp32 recurrence."""
     if not x_btd.is_cuda:
         raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
     if x_btd.device.index != torch.cuda.current_device():
@@ -154,6 +156,7 @@ def context_lstm(lstm: torch.nn.LSTM, x_btd: torch.Tensor, lens_g: torch.Tensor,
     p = (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
          lstm.weight_ih_l0_reverse, lstm.weight_hh_l0_reverse, lstm.bias_ih_l0_reverse, lstm.bias_hh_l0_reverse)
     outs = []
-    for s in range(0, x_btd.shape[0], 64):
-        outs.append(ContextLSTMFunction.apply(lstm, mode, x_btd[s:s + 64], lens[s:s + 64].contiguous(), *p))
+    chunk = 32 if mode == N.MODE_BF16 else 64      # sequences per launch of the recurrence kernels (csrc/lstm_cluster.cu / lstm.cu)
+    for s in range(0, x_btd.shape[0], chunk):
+        outs.append(ContextLSTMFunction.apply(lstm, mode, x_btd[s:s + chunk], lens[s:s + chunk].contiguous(), *p))
     return outs[0] if len(outs) == 1 else torch.cat(outs, 0)

@@ -204,15 +204,25 @@ def test_infer_api():
     assert torch.equal(a, b) and torch.isfinite(c).all() and not torch.equal(a, c)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
-@pytest.mark.parametrize("batch,lens", [(3, [37, 20, 5]), (2, [9, 9]), (11, [40, 33, 31, 30, 25, 17, 16, 9, 3, 2, 1])])
-def test_context_lstm_vs_torch(precision, batch, lens):
-    """Persistent bi-LSTM kernel (forward + all gradients) vs torch's packed nn.LSTM in fp64 on the CPU."""
+_LSTM_CASES = [(3, [37, 20, 5], 20, 16), (2, [9, 9], 20, 16), (11, [40, 33, 31, 30, 25, 17, 16, 9, 3, 2, 1], 20, 16),
+               # the decoder's real width (hidden 528 = 16 CTAs x 33 units, no padding) and a width that leaves the last CTAs
+               # of the cluster partly / completely empty (RADTTS variant: 524)
+               (8, [24, 24, 21, 17, 12, 9, 4, 1], 40, 528), (3, [11, 7, 2], 24, 524),
+               # more than one 8-sequence tile per launch, more than one launch (chunks of 32 / 64 sequences)
+               (19, [13 - (i % 13) for i in range(19)], 20, 40), (70, [1 + (7 * i) % 12 for i in range(70)], 12, 16)]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("batch,lens,n_in,hid", _LSTM_CASES)
+def test_context_lstm_vs_torch(precision, batch, lens, n_in, hid):
+    """Context bi-LSTM kernels (forward + all gradients) vs torch's packed nn.LSTM in fp64 on the CPU: the fp32 cooperative
+    recurrence ("fp32", "bf16x3") and the cluster-resident tensor-core recurrence ("bf16": bf16 W_hh / h, fp32 state)."""
     from radmmm_b200.lstm import context_lstm
-    T, n_in, hid = max(lens), 20, 16
+    T = max(lens)
     ref = torch.nn.LSTM(n_in, hid, 1, batch_first=True, bidirectional=True)
+    wmax = min(0.4, 1.5 / hid ** 0.5)                  # nn.LSTM initialises with U(-1/sqrt(H), 1/sqrt(H))
     for n, p in ref.named_parameters():
-        p.data.copy_(syn.hash_uniform("lstm." + n, tuple(p.shape), -0.4, 0.4))
+        p.data.copy_(syn.hash_uniform("lstm." + n, tuple(p.shape), -wmax, wmax))
     x = syn.hash_uniform("lstm.x", (batch, T, n_in), -1, 1)
     lens_t = torch.tensor(lens)
     mask = of.length_mask(lens_t, T)[..., None].float()
@@ -229,7 +239,7 @@ def test_context_lstm_vs_torch(precision, batch, lens):
     mine = mine.to(DEV)
     xg = (x * mask).to(DEV).requires_grad_(True)
     y = context_lstm(mine, xg, lens_t.to(DEV), precision)
-    tol = 2e-5 if precision == "fp32" else 2e-4
+    tol = {"fp32": 2e-5, "bf16x3": 2e-4, "bf16": 1.5e-2}[precision]
     close(y, yo.detach(), tol, what="lstm out")
     (y * gout.to(DEV)).sum().backward()
     close(xg.grad.cpu().double() * mask.double(), xc.grad * mask.double(), tol * 5, what="lstm dx")

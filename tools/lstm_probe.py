@@ -11,6 +11,9 @@ import torch  # noqa: E402
 from radmmm_b200 import _native as N  # noqa: E402
 
 
+MODE = N.MODE_BF16 if (len(sys.argv) > 1 and sys.argv[1] == 'bf16') else N.MODE_F32
+
+
 def main():
     lib = N.lib()
     dev = "cuda"
@@ -26,7 +29,7 @@ def main():
     ws = torch.empty(lib.radmmm_lstm_workspace_bytes(B, H), dtype=torch.uint8, device=dev)
 
     def run():
-        N.check(lib.radmmm_lstm_forward(N.fptr(xproj), N.fptr(whf), N.fptr(whr), N.ptr(lens), B, T, H, N.fptr(out),
+        N.check(lib.radmmm_lstm_forward(MODE, N.fptr(xproj), N.fptr(whf), N.fptr(whr), N.ptr(lens), B, T, H, N.fptr(out),
                                         N.fptr(gates), N.fptr(cst), N.ptr(ws), N.stream()))
 
     for bits in (0, 1, 2, 3, 4, 5, 6, 7):
@@ -49,7 +52,7 @@ def main():
     dg = torch.zeros(R, 8 * H, device=dev)
 
     def run_bwd():
-        N.check(lib.radmmm_lstm_backward(N.fptr(dout), N.fptr(gates), N.fptr(cst), N.fptr(whf), N.fptr(whr), N.ptr(lens), B, T, H,
+        N.check(lib.radmmm_lstm_backward(MODE, N.fptr(dout), N.fptr(gates), N.fptr(cst), N.fptr(whf), N.fptr(whr), N.ptr(lens), B, T, H,
                                          N.fptr(dg), N.ptr(ws), N.stream()))
 
     run_bwd()
