@@ -536,7 +536,8 @@ def run_ours(args):
             infer_graph_error = f"{type(exc).__name__}: {exc}"[:300]
     dec.train()
     names = {0: "start", 1: "k5_conv_fwd", 2: "res_skip_fwd", 3: "end", 4: "dgrad_end", 5: "dgrad_layer", 6: "dgrad_h0",
-             7: "dgrad_z0", 8: "dgrad_ctx", 17: "wgrad_1x1", 21: "wgrad_k5"}
+             7: "dgrad_z0", 8: "dgrad_ctx", 10: "lstm_projections", 17: "wgrad_1x1", 20: "wgrad_end", 21: "wgrad_k5",
+             28: "wgrad_res_skip_grouped"}
     kernels = {names.get(i, f"tag{i}"): {"launches": cnt[i], "ms": round(kms[i], 4),
                                          "executed_tflops": round(kfl[i] / (kms[i] * 1e9), 1) if kms[i] > 0 else None}
                for i in range(n_tags) if cnt[i]}

@@ -51,7 +51,8 @@ int radmmm_profile_collect(int max_tags, int* counts, double* ms, double* flops)
 /* Diagnostic (tools/gemm_probe.py): when device_buf != NULL every tensor-core contraction launched afterwards writes an
  * in-kernel timeline into region i of the buffer (i = launches since this call, i < max_launches) -- 10 uint64 per CTA for
  * the first max_ctas CTAs (SM clock at entry / set-up / first TMA / first operands / last MMA / accumulator ready /
- * epilogue done / exit, then globaltimer at entry and exit).  NULL disables. */
+ * epilogue done / exit, then globaltimer at entry and exit).  NULL disables.  max_launches < 0: the buffer (32 x 8
+ * uint64) instead receives the accumulated per-phase SM clocks of the cluster LSTM kernels (csrc/lstm_cluster.cu). */
 void radmmm_debug_trace(void* device_buf, int max_ctas, int max_launches);
 /* Number of kernels this library has launched in the process so far (every launch site counts itself; memsets and
  * library calls are not included).  bench.py reports the difference over its timed region as "gpu_launches". */

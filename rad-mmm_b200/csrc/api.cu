@@ -32,7 +32,7 @@ int launch_gemm(const GemmArgs& args, int mode, cudaStream_t stream) {
     if (g_prof_on && g_prof_n < kProfMax) {
         slot = &g_prof[g_prof_n++];
         if (!slot->e0) { cudaEventCreate(&slot->e0); cudaEventCreate(&slot->e1); }
-        slot->tag = args.wgrad ? 16 + args.n_seg : args.epi.kind;
+        slot->tag = args.wgrad == 3 ? 24 + args.n_seg : args.wgrad ? 16 + args.n_seg : args.epi.kind;
         double k = 0;
         for (int s = 0; s < args.n_seg; ++s) k += args.seg[s].K;
         slot->flops = args.wgrad ? 2.0 * args.epi.M * args.epi.N * (double)args.R * args.n_seg
@@ -44,6 +44,7 @@ int launch_gemm(const GemmArgs& args, int mode, cudaStream_t stream) {
     return rc;
 }
 
+void lstm_cluster_set_trace(void* buf);      // lstm_cluster.cu (diagnostic phase timers)
 // wn.cu
 int flow_prepare(const radmmm_flow_desc* f, cudaStream_t st);
 int flow_forward(const radmmm_flow_desc* f, const float* z_in, float* z_mid, float* params, float* z_out, float* log_s,
@@ -86,7 +87,10 @@ extern "C" {
 int radmmm_abi_version(void) { return RADMMM_ABI_VERSION; }
 long long radmmm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-void radmmm_debug_trace(void* device_buf, int max_ctas, int max_launches) { gemm_tc_set_trace(device_buf, max_ctas, max_launches); }
+void radmmm_debug_trace(void* device_buf, int max_ctas, int max_launches) {
+    if (max_launches < 0) lstm_cluster_set_trace(device_buf);      // max_launches < 0: the buffer goes to the cluster LSTM kernels
+    else gemm_tc_set_trace(device_buf, max_ctas, max_launches);
+}
 void radmmm_profile_enable(int on) { g_prof_on = on != 0; if (on) g_prof_n = 0; }
 int radmmm_profile_collect(int max_tags, int* counts, double* ms, double* flops) {
     cudaDeviceSynchronize();

@@ -56,6 +56,7 @@ struct EpiParams {
     float* cf_out;               // channels-first (B, cf_C, Tp) fp32
     int cf_C, cf_c0;
     int atomic;                  // weight-grad split-K: atomicAdd instead of store
+    float* group_out[4];         // grouped weight-grad (GemmArgs::wgrad == 3): output of group g (else null: f32_out + tap stride)
 };
 
 struct GemmArgs {
@@ -65,6 +66,8 @@ struct GemmArgs {
     int n_tiles_n;  // informational
     int wgrad;      // 0 row GEMM; 1 weight-grad GEMM, one output tile set per segment (= conv tap);
                     // 2 weight-grad GEMM, all segments (same dY, different X) accumulate into ONE output
+                    // 3 GROUPED weight-grad GEMMs: segment g is an independent problem dY_g^T X_g -> epi.group_out[g] (same M, N,
+                    //   R for all groups): one launch instead of n_seg small ones, full-K tiles, no split-K / atomics / memset
     int split_k;    // weight-grad only
     int zero_output;  // weight-grad: the launcher zeroes `f32_out` itself if (and only if) its split-K reduces with atomics,
                       // and stores plainly otherwise (epi.atomic is then decided by the launcher)
@@ -425,7 +428,8 @@ __device__ __forceinline__ void epi_dh_with_h(const EpiParams& p, const Stager& 
 template <int NV>
 __device__ __forceinline__ void epi_wgrad(const EpiParams& p, int tap, int m, int n0, const float* acc) {
     if (m >= p.M) return;
-    float* o = p.f32_out + (long long)tap * p.f32_tap_stride + (long long)m * p.f32_ld + n0;
+    float* o = (p.group_out[tap & 3] != nullptr ? p.group_out[tap & 3] : p.f32_out + (long long)tap * p.f32_tap_stride) +
+               (long long)m * p.f32_ld + n0;
     if (n0 + NV <= p.N && (p.f32_ld & 3) == 0) {       // whole vector in range: 16-byte vector reductions / stores
 #pragma unroll
         for (int i = 0; i < NV / 4; ++i) {

@@ -342,8 +342,8 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
                             const int ra = kb * BK, rb = kb * BK + sg.b_row_off;
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i) {
-                                tma_load<CL>(sa_hi + i * (BK * 128), &P.a_hi[0], fb, m_blk * BM + i * 64, ra);
-                                if (C::planes == 2) tma_load<CL>(sa_lo + i * (BK * 128), &P.a_lo[0], fb, m_blk * BM + i * 64, ra);
+                                tma_load<CL>(sa_hi + i * (BK * 128), &P.a_hi[sg.a_map], fb, m_blk * BM + i * 64, ra);
+                                if (C::planes == 2) tma_load<CL>(sa_lo + i * (BK * 128), &P.a_lo[sg.a_map], fb, m_blk * BM + i * 64, ra);
                             }
 #pragma unroll
                             for (int i = 0; i < C::b_rows / 64; ++i) {
@@ -740,6 +740,8 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         RADMMM_REQUIRE(g0.a.ptr && g0.w.ptr, "gemm_tc: null weight-grad operand");
         RADMMM_REQUIRE(g0.a.ld % 64 == 0 && g0.w.ld % 64 == 0, "gemm_tc: weight-grad operands need ld %% 64 == 0");
         const int M = args.epi.M;
+        const bool grouped = args.wgrad == 3;
+        RADMMM_REQUIRE(!grouped || args.n_seg <= 4, "gemm_tc: at most 4 grouped weight-grad problems per launch");
         P.m_tiles = cdiv(M, BM);
         P.acc_segs = args.wgrad == 2;
         P.taps = P.acc_segs ? 1 : args.n_seg;
@@ -771,16 +773,31 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // slices of wider matrices never read past their rows
         const long long a_in = round_up(M, 64) < g0.a.ld ? round_up(M, 64) : g0.a.ld;
         const long long b_in = round_up(N, 64) < g0.w.ld ? round_up(N, 64) : g0.w.ld;
-        RADMMM_TRY(make_map(&P.a_hi[0], g0.a.ptr, a_in, args.R, g0.a.ld, 64));
-        if (x3) RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.a.ptr + g0.a.plane_stride, a_in, args.R, g0.a.ld, 64));
-        n_a = 1;
+        if (!grouped) {
+            RADMMM_TRY(make_map(&P.a_hi[0], g0.a.ptr, a_in, args.R, g0.a.ld, 64));
+            if (x3) RADMMM_TRY(make_map(&P.a_lo[0], (const __nv_bfloat16*)g0.a.ptr + g0.a.plane_stride, a_in, args.R, g0.a.ld, 64));
+            n_a = 1;
+        }
         for (int s = 0; s < args.n_seg; ++s) {
             const GemmSeg& g = args.seg[s];
-            RADMMM_REQUIRE(g.a.ptr == g0.a.ptr, "gemm_tc: weight-grad segments must share dY");
-            RADMMM_REQUIRE(P.acc_segs || g.w.ptr == g0.w.ptr, "gemm_tc: weight-grad taps must share X");
+            int ai = 0;
+            if (grouped) {                       // every group brings its own dY (and X)
+                RADMMM_REQUIRE(g.a.ptr && g.w.ptr && g.a.ld == g0.a.ld && g.w.ld == g0.w.ld, "gemm_tc: grouped weight-grad operands must share their row pitch");
+                ai = find_or_add(a_keys, n_a, g.a.ptr, g.a.ld, g.a.plane_stride);
+                RADMMM_REQUIRE(ai >= 0, "gemm_tc: too many distinct dY operands");
+            } else {
+                RADMMM_REQUIRE(g.a.ptr == g0.a.ptr, "gemm_tc: weight-grad segments must share dY");
+                RADMMM_REQUIRE(P.acc_segs || g.w.ptr == g0.w.ptr, "gemm_tc: weight-grad taps must share X");
+            }
             int bi = find_or_add(b_keys, n_b, g.w.ptr, g.w.ld, g.w.plane_stride);
             RADMMM_REQUIRE(bi >= 0, "gemm_tc: too many distinct X operands");
-            P.seg[s] = TcSeg{0, bi, 0, g.shift, P.k_blocks_total};
+            P.seg[s] = TcSeg{ai, bi, 0, g.shift, P.k_blocks_total};
+        }
+        if (grouped) {
+            for (int i = 0; i < n_a; ++i) {
+                RADMMM_TRY(make_map(&P.a_hi[i], a_keys[i].ptr, a_in, args.R, a_keys[i].ld, 64));
+                if (x3) RADMMM_TRY(make_map(&P.a_lo[i], (const __nv_bfloat16*)a_keys[i].ptr + a_keys[i].plane, a_in, args.R, a_keys[i].ld, 64));
+            }
         }
         for (int i = 0; i < n_b; ++i) {
             RADMMM_TRY(make_map(&P.b_hi[i], b_keys[i].ptr, b_in, args.R, b_keys[i].ld, 64));

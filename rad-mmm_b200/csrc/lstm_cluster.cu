@@ -51,6 +51,7 @@ struct ClParams {
     const float* dout;        // backward: (B, Tp, 2H)
     float* dgates;            // backward: [R][8H] pre-activation gate gradients
     int B, NB, Tp, H, pitch;
+    unsigned long long* trace;   // diagnostic (radmmm_debug_trace): per CTA 8 accumulated SM-clock counters, see kernels
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +145,7 @@ __device__ __forceinline__ float whh_at(const float* __restrict__ Whh, int H, in
 // =========================================================================================================== forward
 // shared memory: [2 mbarriers | lens[32] | hs[2][NB][544][8] bf16 | part[2][144][8 NB] fp32 | hstage[NB][34][8] bf16 |
 //                 cst[33 * 8 NB] fp32 | xps[2][4][33 * 8 NB] fp32]
+template <bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int H = p.H, NB = p.NB, NBN = 8 * NB, NIT = UPC * NBN;
@@ -203,10 +205,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     };
     fetch_xp(0);
     const uint32_t tx_bytes = (uint32_t)(CL * UPC * NB * 16);
+    // diagnostic phase timers of thread 0: [0] wait for h, [1] mat-vec, [2] cp.async wait + barrier, [3] gates, [4] barrier, [5] push
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+    auto lap = [&](int i) { if (TRACE && tid == 0) { const long long now = clock64(); tacc[i] += now - tlast; tlast = now; } };
 
     for (int s = 0; s < tmax; ++s) {
         const int cur = s & 1, prev = cur ^ 1;
+        lap(5);
         if (s > 0) mbar_wait(&bars[prev], ((s - 1) >> 1) & 1);         // the 16 slices of h_{s-1} have landed in hs[prev]
+        lap(0);
         // ---- recurrent mat-vec on the tensor cores: part[kh][row][n] = sum_{k in half kh} W[row][k] h_{s-1}[k][n]
         if (mma_warp) {
             for (int nb = 0; nb < NB; ++nb) {
@@ -229,8 +236,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
                 *reinterpret_cast<float2*>(o + 8 * NBN) = make_float2(acc0[2] + acc1[2], acc0[3] + acc1[3]);
             }
         }
+        lap(1);
         cp_async_wait_all();                   // this thread's input projections of step s are in xps[cur]
         __syncthreads();
+        lap(2);
         // ---- gates, cell / hidden state of this CTA's units
         for (int it = tid; it < NIT; it += NT) {
             const int j = it / NBN, n = it - j * NBN, len = slen[n], unit = rank * UPC + j;
@@ -257,7 +266,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
         }
         if (s + 1 == tmax) break;
         fetch_xp(s + 1);                       // in flight across the exchange
+        lap(3);
         __syncthreads();
+        lap(4);
         // ---- push this CTA's h slice into every CTA of the cluster (own copy included), 16 bytes per (unit, tile, peer)
         if (tid == 0) mbar_expect_tx(&bars[cur], tx_bytes);
         for (int i = tid; i < UPC * NB * CL; i += NT) {
@@ -269,6 +280,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     }
     cp_async_wait_all();
     cluster_sync_all();                       // no CTA leaves while a peer could still push into its shared memory
+    if (TRACE && p.trace != nullptr && tid == 0)
+        for (int i = 0; i < 6; ++i) p.trace[blockIdx.x * 8 + i] = (unsigned long long)tacc[i];
 }
 
 // =========================================================================================================== backward
@@ -279,6 +292,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
 // owner of those units; the owner adds the 16 partial slices.
 // shared memory: [2 mbarriers | lens[32] | recv[2][CL][NB][SLOT][8] fp32 | dgs[NB][144][8] bf16 | dcn[33 * 8 NB] fp32 |
 //                 sv[2][7][33 * 8 NB] fp32]
+template <bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int H = p.H, NB = p.NB, NBN = 8 * NB, NIT = UPC * NBN;
@@ -346,11 +360,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     };
     load_saved(tmax - 1);
     const uint32_t tx_bytes = (uint32_t)(CL * NB * SLOT * 8 * 4);          // 16 sources x (34 slots x 8 sequences) fp32 per tile
+    // diagnostic phase timers of thread 0: [0] wait for dh, [1] cp.async wait, [2] gate gradients, [3] barrier, [4] mat-vec + push
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+    auto lap = [&](int i) { if (TRACE && tid == 0) { const long long now = clock64(); tacc[i] += now - tlast; tlast = now; } };
 
     for (int s = tmax - 1, step = 0; s >= 0; --s, ++step) {
         const int cur = step & 1, prev = cur ^ 1;
+        lap(4);
         if (step > 0) mbar_wait(&bars[prev], ((step - 1) >> 1) & 1);      // the 16 partial slices of dh_rec have landed
+        lap(0);
         cp_async_wait_all();
+        lap(1);
         // ---- gate gradients of this CTA's units
         for (int it = tid; it < NIT; it += NT) {
             const int j = it / NBN, n = it - j * NBN, len = slen[n], unit = rank * UPC + j;
@@ -383,7 +403,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
         }
         if (s == 0) break;
         load_saved(s - 1);                     // in flight across the mat-vec and the exchange
+        lap(2);
         __syncthreads();
+        lap(3);
         // ---- partial dh_rec for all unit slots, pushed to the owners
         if (tid == 0) mbar_expect_tx(&bars[cur], tx_bytes);
         if (mma_warp) {
@@ -426,9 +448,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     }
     cp_async_wait_all();
     cluster_sync_all();
+    if (TRACE && p.trace != nullptr && tid == 0)
+        for (int i = 0; i < 6; ++i) p.trace[blockIdx.x * 8 + i] = (unsigned long long)tacc[i];
 }
 
 }  // namespace
+
+
+
+static unsigned long long* g_lstm_trace = nullptr;
+void lstm_cluster_set_trace(void* buf) { g_lstm_trace = reinterpret_cast<unsigned long long*>(buf); }
 
 bool lstm_cluster_supported(int B, int H) { return H >= 1 && H <= HMAX && B >= 1 && B <= 32; }
 
@@ -441,13 +470,13 @@ static size_t bwd_smem(int NB) {
     return 256 + (size_t)2 * CL * NB * SLOT * 8 * 4 + (size_t)NB * ROWS * 16 + nit * 4 + 2 * 7 * nit * 4;
 }
 
-template <bool FWD>
-static int launch_cluster(const ClParams& p, size_t smem, cudaStream_t st) {
+template <bool FWD, bool TRACE>
+static int launch_cluster_t(const ClParams& p, size_t smem, cudaStream_t st) {
     static size_t smem_set[64] = {};          // function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    auto kern = FWD ? lstm_cl_fwd_kernel : lstm_cl_bwd_kernel;
+    auto kern = FWD ? lstm_cl_fwd_kernel<TRACE> : lstm_cl_bwd_kernel<TRACE>;
     if (smem > smem_set[dev]) {
         RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -458,10 +487,16 @@ static int launch_cluster(const ClParams& p, size_t smem, cudaStream_t st) {
     return RADMMM_OK;
 }
 
+template <bool FWD>
+static int launch_cluster(const ClParams& p, size_t smem, cudaStream_t st) {
+    return p.trace != nullptr ? launch_cluster_t<FWD, true>(p, smem, st) : launch_cluster_t<FWD, false>(p, smem, st);
+}
+
 static int fill(ClParams& p, const int* lens, int B, int Tp, int H) {
     RADMMM_REQUIRE(lstm_cluster_supported(B, H), "lstm_cluster: B=%d (<= 32) / H=%d (<= %d) out of range", B, H, HMAX);
     memset(&p, 0, sizeof(p));
     p.lens = lens; p.B = B; p.NB = (B + 7) / 8; p.Tp = Tp; p.H = H; p.pitch = Tp + 16;
+    p.trace = g_lstm_trace;
     return RADMMM_OK;
 }
 

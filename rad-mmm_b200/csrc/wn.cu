@@ -405,12 +405,26 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         RADMMM_CUDA(cudaMemsetAsync(gr->end_w, 0, sizeof(float) * (size_t)d.C * H, sd));
         RADMMM_TRY(launch_gemm(wa, d.mode, sd));
     }
-    for (int i = L - 1; i >= 0; --i) {       // res-skip conv i (needs DQ_i only): lanes 0 and 1
-        cudaStream_t sd = lane(i & 1);
-        RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], sd));
-        RADMMM_TRY(wgrad(d, f->lens, s.DQ[i], w.Hs[i + 1], H, H, 1, 1, s.dW_rs[i], H, 0, sd));
-        RADMMM_TRY(wn_bwd(s.dW_rs[i], H, 0, H, nullptr, 0, 0, f->rs_v[i], f->rs_g[i], p.norm_rs + (size_t)i * H, H, H, 1,
-                          gr->rs_v[i], gr->rs_g[i], sd));
+    {   // res-skip convs (need only DQ_i and the saved h_{i+1}): ONE grouped weight-grad launch for all L layers -- L x 32
+        // full-K tiles fill the machine once; one by one each problem is 32 tiles and had to be split-K'ed six ways with fp32
+        // atomics into a zeroed buffer (99 TFLOP/s).  Bias column sums run beside it on the other lane.
+        cudaStream_t sd = lane(0), sb = lane(1);
+        GemmArgs wa;
+        init_args(wa, d, f->lens, EPI_WGRAD, H);
+        wa.wgrad = 3;
+        for (int i = 0; i < L; ++i) {
+            GemmSeg& sg = wa.seg[wa.n_seg++];
+            sg.a = s.DQ[i]; sg.w = w.Hs[i + 1]; sg.K = d.R; sg.shift = 0;
+            wa.epi.group_out[i] = s.dW_rs[i];
+        }
+        wa.epi.M = H; wa.epi.f32_out = s.dW_rs[0]; wa.epi.f32_ld = H; wa.epi.f32_tap_stride = 0;
+        wa.split_k = 1; wa.epi.atomic = 0; wa.zero_output = 0;
+        RADMMM_TRY(launch_gemm(wa, d.mode, sd));
+        for (int i = L - 1; i >= 0; --i) {
+            RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], sb));
+            RADMMM_TRY(wn_bwd(s.dW_rs[i], H, 0, H, nullptr, 0, 0, f->rs_v[i], f->rs_g[i], p.norm_rs + (size_t)i * H, H, H, 1,
+                              gr->rs_v[i], gr->rs_g[i], sd));
+        }
     }
     // 3. layers, last to first
     for (int i = L - 1; i >= 0; --i) {

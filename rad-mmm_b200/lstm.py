@@ -155,6 +155,35 @@ def context_lstm(lstm: torch.nn.LSTM, x_btd: torch.Tensor, lens_g: torch.Tensor,
     lens = lens_g.to(device=x_btd.device, dtype=torch.int32).contiguous()
     p = (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
          lstm.weight_ih_l0_reverse, lstm.weight_hh_l0_reverse, lstm.bias_ih_l0_reverse, lstm.bias_hh_l0_reverse)
+    hid = lstm.hidden_size
+    hp = N.round_up(hid, 16)
+    if hp != hid:
+        # the kernels want a hidden size that is a multiple of 16 (8H a multiple of 128): run a zero-padded LSTM -- a padded
+        # unit has zero weights and biases, so its gates are (1/2, 1/2, 0, 1/2), its cell and output stay exactly 0 and
+        # nothing depends on it -- and slice its outputs away (RADTTS variant: hidden 524, configs/RADTTS_model_config.yaml)
+        p = _pad_hidden(p, hid, hp)
+        y = _run_chunks(lstm, mode, x_btd, lens, p)
+        return torch.cat((y[..., :hid], y[..., hp:hp + hid]), dim=-1)
+    return _run_chunks(lstm, mode, x_btd, lens, p)
+
+
+def _pad_hidden(p, hid: int, hp: int):
+    """Zero-pad every gate block of (W_ih, W_hh, b_ih, b_hh) x 2 directions from ``hid`` to ``hp`` units (differentiable)."""
+    F = torch.nn.functional
+    out = []
+    for i, t in enumerate(p):
+        kind = i % 4
+        if kind == 0:                                   # W_ih (4H, In)
+            t = F.pad(t.reshape(4, hid, -1), (0, 0, 0, hp - hid)).reshape(4 * hp, -1)
+        elif kind == 1:                                 # W_hh (4H, H)
+            t = F.pad(t.reshape(4, hid, hid), (0, hp - hid, 0, hp - hid)).reshape(4 * hp, hp)
+        else:                                           # biases (4H)
+            t = F.pad(t.reshape(4, hid), (0, hp - hid)).reshape(4 * hp)
+        out.append(t.contiguous())
+    return tuple(out)
+
+
+def _run_chunks(lstm, mode, x_btd, lens, p):
     outs = []
     chunk = 32 if mode == N.MODE_BF16 else 64      # sequences per launch of the recurrence kernels (csrc/lstm_cluster.cu / lstm.cu)
     for s in range(0, x_btd.shape[0], chunk):

@@ -103,7 +103,8 @@ def test_decoder_vs_reference_fixture(fname, n_flows, batch, frames, precision):
     for i, ls in enumerate(out["log_s_list"]):
         close(ls.cpu().double() * m, gd[f"log_s_{i}"].double() * m, tol, what=f"log_s[{i}]")
     close(torch.stack(out["log_det_W_list"]), gd["log_det"], 1e-5, what="log_det_W")
-    close(out["context_w_spkvec"][:, ::33], gd["context"], 1e-5, what="context_w_spkvec")
+    # "bf16": the context LSTM runs its recurrence with bf16 W_hh / h on the tensor cores (csrc/lstm_cluster.cu)
+    close(out["context_w_spkvec"][:, ::33], gd["context"], 5e-3 if precision == "bf16" else 1e-5, what="context_w_spkvec")
     loss, prior = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g.to(DEV),
                              n_elements=L.n_elements_like_reference(bt["out_lens"], 2))
     rel = {"fp32": 1e-5, "bf16x3": 5e-5, "bf16": 5e-3}[precision]          # north-star bar: 1e-4 relative

@@ -87,7 +87,8 @@ def test_decoder_bench_shape_vs_oracle(precision):
     lens_g = (bt["out_lens"] // 2)
     m = of.length_mask(lens_g.cpu(), T // 2)[:, None].double()
     tol = Z_TOL[precision]
-    close(out["context_w_spkvec"].cpu().double() * m, ref["ctx"].double() * m, 2e-4, what="context_w_spkvec")
+    close(out["context_w_spkvec"].cpu().double() * m, ref["ctx"].double() * m, 1e-2 if precision == "bf16" else 2e-4,
+          what="context_w_spkvec")
     close(out["z_mel"].cpu().double() * m, ref["z"].double() * m, tol, what="z_mel @ B=8,T=800")
     for i, ls in enumerate(out["log_s_list"]):
         close(ls.cpu().double() * m, ref["log_s"][i].double() * m, tol, what=f"log_s[{i}] @ B=8,T=800")

@@ -36,7 +36,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layouts(lib):
     from radmmm_b200 import _native
-    assert lib.radmmm_abi_version() == 1
+    assert lib.radmmm_abi_version() == _native.ABI_VERSION
     assert lib.radmmm_sizeof_flow_desc() == ctypes.sizeof(_native.FlowDesc)
     assert lib.radmmm_sizeof_flow_grads() == ctypes.sizeof(_native.FlowGrads)
 
