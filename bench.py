@@ -346,6 +346,49 @@ def precision_errors(dev, precisions):
     return res
 
 
+def optimizer_bench(dev, pk, build, resident, host, valid_frames, timed, args):
+    """fused multi-tensor RAdam + global-norm clip (radmmm_b200.radam.RAdam, configs: lr 1e-3, weight decay 1e-6,
+    gradient_clip_val 1.0).  optimizer_ms: the three launches alone on the decoder's 219 M parameters (CUDA events);
+    full_step: decoder train step + clip + optimizer captured in ONE CUDA graph, the reference loop's whole per-step device work
+    for this path."""
+    from radmmm_b200.graphs import GraphedTrainStep
+    from radmmm_b200.radam import RAdam
+    dec = build("bf16")
+    opt = RAdam(dec.parameters(), lr=1e-3, weight_decay=1e-6, max_grad_norm=1.0)
+    g = GraphedTrainStep(dec, resident)                       # gradients live in the decoder's arena from here on
+    g(resident)
+    opt.step()                                                # builds the device tables
+    torch.cuda.synchronize()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        opt.step()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    opt_ms = sorted(ts)[len(ts) // 2]
+    nbytes = opt.bytes_per_step()
+    del g
+    gfull = GraphedTrainStep(dec, resident, after_backward=opt.step)
+    for _ in range(3):
+        gfull(resident)
+    ms_full = timed(lambda: gfull(resident), max(5, args.steps // 2))
+    ms_full_e2e = timed(lambda: float(gfull(host).cpu()), max(3, args.steps // 4))
+    out = {"optimizer_ms": opt_ms, "algorithmic_bytes": nbytes, "achieved": nbytes / (opt_ms * 1e-3) / 1e9, "unit": "GB/s",
+           "peak": pk["hbm_gbs"], "frac": nbytes / (opt_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+           "full_step": {"ms_per_step": ms_full, "value": valid_frames / (ms_full * 1e-3), "e2e_ms_per_step": ms_full_e2e,
+                         "e2e_value": valid_frames / (ms_full_e2e * 1e-3), "unit": UNIT,
+                         "note": "train step + gradient-norm clip + RAdam update of all 219M parameters in one CUDA graph"},
+           "note": "radmmm_b200.radam.RAdam: 3 launches (gradient sum of squares, scalar hyper step, fused update); 32 B per "
+                   "parameter; L2 flushed before every timed call"}
+    del gfull, dec, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     from radmmm_b200 import _native as N
@@ -591,6 +634,10 @@ def run_ours(args):
             torch.cuda.empty_cache()
         except Exception as exc:
             extras["parity_mode"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            extras["optimizer"] = optimizer_bench(dev, pk, build, resident, host, valid_frames, timed, args)
+        except Exception as exc:
+            extras["optimizer"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         try:
             extras["roofline_hbm"] = hbm_rooflines(dev, pk, batch, frames)
         except Exception as exc:

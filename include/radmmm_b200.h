@@ -161,6 +161,20 @@ int radmmm_lstm_backward(int mode, const float* dout, const float* gates, const 
                          const float* whh_r, const int32_t* lens, int B, int Tp, int H, float* dgates, void* workspace,
                          void* stream);
 
+/* Fused multi-tensor RAdam + global-norm gradient clipping.  Replaces radam.RAdam.step (radam.py:63-142, a Python loop over
+ * every parameter tensor) and Lightning's `gradient_clip_val` (configs/RADMMM_train_config.yaml:7-8 ->
+ * torch.nn.utils.clip_grad_norm_) with three launches for ALL parameters, no host synchronisation (CUDA-graph capturable).
+ *   recs:          device array of n_tensors records {float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+ *                  long long numel} (40 bytes each);
+ *   chunk_tensor / chunk_off: device tables, chunk c covers elements [chunk_off[c], + radmmm_radam_chunk_elems()) of tensor
+ *                  chunk_tensor[c];
+ *   state:         6 device doubles, zero-initialised once: [0] scratch (sum of squares), [1] step count (incremented by the
+ *                  call), [2] step size, [3] variance-rectified branch taken, [4] clip coefficient, [5] gradient norm;
+ *   cfg:           6 device doubles: lr, beta1, beta2, eps, weight_decay, max_grad_norm (<= 0: no clipping). */
+int radmmm_radam_chunk_elems(void);
+int radmmm_radam_step(const void* recs, const int32_t* chunk_tensor, const long long* chunk_off, int n_chunks, double* state,
+                      const double* cfg, void* stream);
+
 /* Stand-alone ops (also used by the tests) ------------------------------------------------------------- */
 
 /* Invertible 1x1 conv: out[b,co,t] = sum_ci W[co,ci]*(in[b,ci,t]-pre[ci]) + post[co]   (common.py:540-548,605-617) */

@@ -362,3 +362,38 @@ def flow_loss(z: Tensor, log_det_list: Sequence[Tensor], log_s_list: Sequence[Te
     prior = torch.sum((z * mask) ** 2) / (2 * sigma * sigma)
     denom = n * z.shape[1]
     return (prior - log_s_total - log_det_total) / denom, prior / denom
+
+
+# --------------------------------------------------------------------------- optimizer (next-row 8f-1)
+def clip_grad_norm(grads: Sequence[Tensor], max_norm: float) -> Tensor:
+    """torch.nn.utils.clip_grad_norm_ (what Lightning's ``gradient_clip_val`` / ``gradient_clip_algorithm: norm`` calls,
+    configs/RADMMM_train_config.yaml:7-8): scales ``grads`` IN PLACE, returns the total norm."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in grads]))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads:
+        g.mul_(coef)
+    return total
+
+
+def radam_step(params: Sequence[Tensor], grads: Sequence[Tensor], exp_avg: Sequence[Tensor], exp_avg_sq: Sequence[Tensor],
+               step: int, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+    """One ``RAdam.step`` (radam.py:63-142) on explicit state, in place; ``step`` is the count AFTER this update
+    (``state['step'] += 1`` happens before it is used, radam.py:103)."""
+    beta1, beta2 = betas
+    beta2_t = beta2 ** step
+    n_sma_max = 2 / (1 - beta2) - 1
+    n_sma = n_sma_max - 2 * step * beta2_t / (1 - beta2_t)
+    if n_sma >= 5:                                                              # radam.py:116-124
+        step_size = lr * math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_sma_max - 4) * (n_sma - 2) / n_sma *
+                                   n_sma_max / (n_sma_max - 2)) / (1 - beta1 ** step)
+    else:
+        step_size = lr / (1 - beta1 ** step)                                    # radam.py:125-126
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)                           # radam.py:98
+        m.mul_(beta1).add_(g, alpha=1 - beta1)                                  # radam.py:100
+        if weight_decay != 0:
+            p.add_(p, alpha=-weight_decay * lr)                                 # radam.py:129-132
+        if n_sma >= 5:
+            p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)                 # radam.py:135-137
+        else:
+            p.add_(m, alpha=-step_size)                                         # radam.py:138-139

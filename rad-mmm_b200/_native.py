@@ -84,6 +84,8 @@ SIGNATURES = {
     "radmmm_masked_sum_backward": (_i, [_fp, _fp, _i, _i, _i, _i, _fp, _f, _fp, _fp]),
     "radmmm_conv_rows": (_i, [_i, _fp, _ll, _ll, _fp, _ll, _ll, _ll, _fp, _fp, _ll, _i, _i, _i, _i, _i, _fp]),
     "radmmm_wgrad_rows": (_i, [_i, _fp, _ll, _ll, _fp, _ll, _ll, _fp, _ll, _ll, _i, _i, _i, _i, _i, _i, _fp]),
+    "radmmm_radam_chunk_elems": (_i, []),
+    "radmmm_radam_step": (_i, [_fp, _fp, _fp, _i, _fp, _fp, _fp]),
     "radmmm_lstm_workspace_bytes": (_sz, [_i, _i]),
     "radmmm_lstm_forward": (_i, [_i, _fp, _fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp]),
     "radmmm_lstm_backward": (_i, [_i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp]),

@@ -144,6 +144,12 @@ int radmmm_flow_backward(const radmmm_flow_desc* d, const float* z_in, const flo
                          ST(stream));
 }
 
+int radmmm_radam_chunk_elems(void) { return radam_chunk_elems(); }
+int radmmm_radam_step(const void* recs, const int32_t* chunk_tensor, const long long* chunk_off, int n_chunks, double* state,
+                      const double* cfg, void* stream) {
+    return radam_step(recs, chunk_tensor, chunk_off, n_chunks, state, cfg, ST(stream));
+}
+
 size_t radmmm_lstm_workspace_bytes(int B, int H) { return lstm_workspace_bytes(B, H); }
 int radmmm_lstm_forward(int mode, const float* xproj, const float* whh_f, const float* whh_r, const int32_t* lens, int B, int Tp,
                         int H, float* out, float* gates, float* cstate, void* workspace, void* stream) {

@@ -50,7 +50,9 @@ struct ClParams {
     float* cstate;            // [R][2H] cell state (saved for backward)
     const float* dout;        // backward: (B, Tp, 2H)
     float* dgates;            // backward: [R][8H] pre-activation gate gradients
-    int B, NB, Tp, H, pitch;
+    int B, NB, Tp, H, pitch, n_chunks;     // NB x 8 sequences per cluster, n_chunks clusters per direction
+    int bulk;                    // 1: exchange with one bulk DSMEM copy per peer (cp.async.bulk shared::cta -> shared::cluster);
+                                 // 0: one 16-byte st.async per (unit, peer)  (RADMMM_B200_LSTM_BULK=0, A/B measurements)
     unsigned long long* trace;   // diagnostic (radmmm_debug_trace): per CTA 8 accumulated SM-clock counters, see kernels
 };
 
@@ -102,6 +104,13 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remot
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar) : "memory");
 }
+// bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into another CTA's; completes on that CTA's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (the bulk-copy engine) after the next barrier
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -144,7 +153,7 @@ __device__ __forceinline__ float whh_at(const float* __restrict__ Whh, int H, in
 
 // =========================================================================================================== forward
 // shared memory: [2 mbarriers | lens[32] | hs[2][NB][544][8] bf16 | part[2][144][8 NB] fp32 | hstage[NB][34][8] bf16 |
-//                 cst[33 * 8 NB] fp32 | xps[2][4][33 * 8 NB] fp32]
+//                 (x2) | cst[33 * 8 NB] fp32 | xps[2][4][33 * 8 NB] fp32 | itab[33 * 8 NB] int4]
 template <bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -153,10 +162,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     int* slen = reinterpret_cast<int*>(smem + 128);                                          // [32]
     __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem + 256);                       // [2][NB][KP][8]
     float* part = reinterpret_cast<float*>(smem + 256 + (size_t)2 * NB * KP * 16);           // [2][ROWS][NBN]
-    __nv_bfloat16* hstage = reinterpret_cast<__nv_bfloat16*>(part + (size_t)2 * ROWS * NBN);  // [NB][SLOT][8]
-    float* cst = reinterpret_cast<float*>(hstage + (size_t)NB * SLOT * 8);                   // [NIT]
+    // hstage is double-buffered: the bulk copies of step s may still be reading it while step s+1 writes (they are known to
+    // be complete once h_{s+1} of every peer has arrived, i.e. before step s+2 writes the same half again)
+    __nv_bfloat16* hstage2 = reinterpret_cast<__nv_bfloat16*>(part + (size_t)2 * ROWS * NBN); // [2][NB][SLOT][8]
+    float* cst = reinterpret_cast<float*>(hstage2 + (size_t)2 * NB * SLOT * 8);              // [NIT]
     float* xps = cst + NIT;                                                                   // [2][4][NIT]
-    const int rank = (int)cluster_rank(), dir = (int)cluster_id_x();
+    int4* itab = reinterpret_cast<int4*>(xps + (size_t)2 * 4 * NIT);                          // [NIT]
+    const int rank = (int)cluster_rank(), dir = (int)(cluster_id_x() & 1), n0 = (int)(cluster_id_x() >> 1) * 8;     // cluster = (8-sequence chunk, direction)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool mma_warp = warp < 2 * MT;      // 18 of the 20 warps
     const int mt = warp >> 1, kh = warp & 1;
@@ -167,9 +179,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 32) slen[tid] = tid < p.B ? min(p.lens[tid], p.Tp) : 0;
+    if (tid < 32) slen[tid] = (tid < 8 * NB && n0 + tid < p.B) ? min(p.lens[n0 + tid], p.Tp) : 0;
     for (int i = tid; i < 2 * NB * KP; i += NT) reinterpret_cast<uint4*>(hs)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0, zero slots
     for (int i = tid; i < NIT; i += NT) cst[i] = 0.0f;
+    // per-item constants (item it = j * NBN + n: unit j of this CTA, sequence n), so that the per-step gate code does no index
+    // arithmetic: .x = length (0: nothing to do), .y = offset of (row of frame 0, this direction, this unit) in xproj / gates
+    // ([R][8H]), .z = the same in cstate ([R][2H]), .w = offset of (frame 0) in out ((B, Tp, 2H))
+    for (int it = tid; it < NIT; it += NT) {
+        const int j = it / NBN, n = it - j * NBN, unit = rank * UPC + j;
+        int4 e;
+        const int ng = n0 + n;                       // sequence index in the batch
+        e.x = (ng < p.B && unit < H) ? min(p.lens[ng], p.Tp) : 0;
+        e.y = ng * p.pitch * 8 * H + dir * 4 * H + unit;
+        e.z = ng * p.pitch * 2 * H + dir * H + unit;
+        e.w = ng * p.Tp * 2 * H + dir * H + unit;
+        itab[it] = e;
+    }
     // W_hh slice -> A fragments (rows = local gate rows of m-tile `mt`, k = slots of this warp's K half)
     uint32_t wf[TPW][4];
     if (mma_warp) {
@@ -183,8 +208,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
             wf[i][3] = pack_bf16(whh_at(Whh, H, rank, r1, c0 + 8), whh_at(Whh, H, rank, r1, c0 + 9));
         }
     }
-    int tmax = 0;
-    for (int b = 0; b < p.B; ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
+    int tmax = 0;                                  // this chunk's longest sequence
+    for (int b = n0; b < min(p.B, n0 + 8 * NB); ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
     __syncthreads();
     cluster_sync_all();                       // every CTA's barriers and zeroed h tiles exist before the first push
 
@@ -192,10 +217,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     // the input projections of step s are fetched into xps[s & 1] with cp.async during step s - 1
     auto fetch_xp = [&](int s) {
         for (int it = tid; it < NIT; it += NT) {
-            const int j = it / NBN, n = it - j * NBN, len = slen[n], unit = rank * UPC + j;
-            if (s < len && unit < H) {
-                const int t = dir ? len - 1 - s : s;
-                const float* x = p.xproj + ((size_t)n * p.pitch + t) * 8 * H + (size_t)dir * 4 * H + unit;
+            const int4 e = itab[it];
+            if (s < e.x) {
+                const int t = dir ? e.x - 1 - s : s;
+                const float* x = p.xproj + (size_t)e.y + (size_t)t * 8 * H;
                 float* d = xps + (size_t)(s & 1) * 4 * NIT + it;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) cp_async4(d + (size_t)g * NIT, x + (size_t)g * H);
@@ -211,6 +236,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
 
     for (int s = 0; s < tmax; ++s) {
         const int cur = s & 1, prev = cur ^ 1;
+        __nv_bfloat16* hstage = hstage2 + (size_t)cur * NB * SLOT * 8;
         lap(5);
         if (s > 0) mbar_wait(&bars[prev], ((s - 1) >> 1) & 1);         // the 16 slices of h_{s-1} have landed in hs[prev]
         lap(0);
@@ -242,9 +268,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
         lap(2);
         // ---- gates, cell / hidden state of this CTA's units
         for (int it = tid; it < NIT; it += NT) {
-            const int j = it / NBN, n = it - j * NBN, len = slen[n], unit = rank * UPC + j;
+            const int4 e = itab[it];
+            const int j = it / NBN, n = it - j * NBN;
             float h = 0.0f;
-            if (s < len && unit < H) {
+            if (s < e.x) {
                 const float* pa = part + (size_t)(4 * j) * NBN + n;
                 const float* pb = pa + (size_t)ROWS * NBN;
                 const float* xp = xps + (size_t)cur * 4 * NIT + it;
@@ -255,32 +282,40 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
                 const float c = gf * cst[it] + gi * gg;
                 h = go * tanhf_(c);
                 cst[it] = c;
-                const int t = dir ? len - 1 - s : s;
-                const size_t r = (size_t)n * p.pitch + t;
-                float* gp = p.gates + r * 8 * H + (size_t)dir * 4 * H + unit;
+                const int t = dir ? e.x - 1 - s : s;
+                float* gp = p.gates + (size_t)e.y + (size_t)t * 8 * H;
                 gp[0] = gi; gp[H] = gf; gp[2 * (size_t)H] = gg; gp[3 * (size_t)H] = go;
-                p.cstate[r * 2 * H + (size_t)dir * H + unit] = c;
-                p.out[((size_t)n * p.Tp + t) * 2 * H + (size_t)dir * H + unit] = h;
+                p.cstate[(size_t)e.z + (size_t)t * 2 * H] = c;
+                p.out[(size_t)e.w + (size_t)t * 2 * H] = h;
             }
             hstage[((size_t)(n >> 3) * SLOT + j) * 8 + (n & 7)] = __float2bfloat16_rn(h);
         }
         if (s + 1 == tmax) break;
         fetch_xp(s + 1);                       // in flight across the exchange
         lap(3);
+        if (p.bulk) fence_proxy_async();       // hstage was written through the generic proxy, the copy engine reads it
         __syncthreads();
         lap(4);
-        // ---- push this CTA's h slice into every CTA of the cluster (own copy included), 16 bytes per (unit, tile, peer)
+        // ---- push this CTA's h slice into every CTA of the cluster (own copy included)
         if (tid == 0) mbar_expect_tx(&bars[cur], tx_bytes);
-        for (int i = tid; i < UPC * NB * CL; i += NT) {
-            const int peer = i % CL, rest = i / CL, j = rest % UPC, nb = rest / UPC;
-            const uint4 v = *reinterpret_cast<const uint4*>(hstage + ((size_t)nb * SLOT + j) * 8);
-            const uint32_t dst = smem_u32(hs + ((size_t)(cur * NB + nb) * KP + rank * SLOT + j) * 8);
-            st_async_v4(mapa(dst, peer), mapa(smem_u32(&bars[cur]), peer), v);
+        if (p.bulk) {                          // ONE bulk copy of 33 units x 16 bytes per (tile, peer)
+            if (tid < CL * NB) {
+                const int peer = tid % CL, nb = tid / CL;
+                const uint32_t dst = smem_u32(hs + ((size_t)(cur * NB + nb) * KP + rank * SLOT) * 8);
+                bulk_copy_to_peer(mapa(dst, peer), smem_u32(hstage + (size_t)nb * SLOT * 8), UPC * 16, mapa(smem_u32(&bars[cur]), peer));
+            }
+        } else {                               // 16 bytes per (unit, tile, peer)
+            for (int i = tid; i < UPC * NB * CL; i += NT) {
+                const int peer = i % CL, rest = i / CL, j = rest % UPC, nb = rest / UPC;
+                const uint4 v = *reinterpret_cast<const uint4*>(hstage + ((size_t)nb * SLOT + j) * 8);
+                const uint32_t dst = smem_u32(hs + ((size_t)(cur * NB + nb) * KP + rank * SLOT + j) * 8);
+                st_async_v4(mapa(dst, peer), mapa(smem_u32(&bars[cur]), peer), v);
+            }
         }
     }
     cp_async_wait_all();
     cluster_sync_all();                       // no CTA leaves while a peer could still push into its shared memory
-    if (TRACE && p.trace != nullptr && tid == 0)
+    if (TRACE && p.trace != nullptr && tid == 0 && blockIdx.x < 2 * CL)          // the trace buffer holds the first two clusters
         for (int i = 0; i < 6; ++i) p.trace[blockIdx.x * 8 + i] = (unsigned long long)tacc[i];
 }
 
@@ -291,7 +326,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
 // k-tiles: warp w < 17 holds m-tiles 2w and 2w+1 with the full K), and pushes each 16-unit x 8-sequence fp32 tile to the
 // owner of those units; the owner adds the 16 partial slices.
 // shared memory: [2 mbarriers | lens[32] | recv[2][CL][NB][SLOT][8] fp32 | dgs[NB][144][8] bf16 | dcn[33 * 8 NB] fp32 |
-//                 sv[2][7][33 * 8 NB] fp32]
+//                 sv[2][7][33 * 8 NB] fp32 | itab[33 * 8 NB] int4 | pstage[2][NB][544][8] fp32 (bulk exchange only)]
 template <bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -302,7 +337,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(recv + (size_t)2 * CL * NB * SLOT * 8);   // [NB][ROWS][8]
     float* dcn = reinterpret_cast<float*>(dgs + (size_t)NB * ROWS * 8);                      // [NIT]
     float* sv = dcn + NIT;                                                                    // [2][7][NIT]
-    const int rank = (int)cluster_rank(), dir = (int)cluster_id_x();
+    int4* itab = reinterpret_cast<int4*>(sv + (size_t)2 * 7 * NIT);                           // [NIT]
+    float* pstage2 = reinterpret_cast<float*>(itab + NIT);                                    // [2][NB][KP][8]
+    const int rank = (int)cluster_rank(), dir = (int)(cluster_id_x() & 1), n0 = (int)(cluster_id_x() >> 1) * 8;     // cluster = (8-sequence chunk, direction)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* Whh = p.whh[dir];
     constexpr int MTW = 2;                    // m-tiles (of 16 unit slots) per warp
@@ -313,9 +350,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 32) slen[tid] = tid < p.B ? min(p.lens[tid], p.Tp) : 0;
+    if (tid < 32) slen[tid] = (tid < 8 * NB && n0 + tid < p.B) ? min(p.lens[n0 + tid], p.Tp) : 0;
     for (int i = tid; i < NB * ROWS; i += NT) reinterpret_cast<uint4*>(dgs)[i] = make_uint4(0, 0, 0, 0);   // padding rows stay zero
     for (int i = tid; i < NIT; i += NT) dcn[i] = 0.0f;
+    for (int it = tid; it < NIT; it += NT) {      // per-item constants, as in the forward kernel (.y also addresses dgates)
+        const int j = it / NBN, n = it - j * NBN, unit = rank * UPC + j;
+        int4 e;
+        const int ng = n0 + n;                       // sequence index in the batch
+        e.x = (ng < p.B && unit < H) ? min(p.lens[ng], p.Tp) : 0;
+        e.y = ng * p.pitch * 8 * H + dir * 4 * H + unit;
+        e.z = ng * p.pitch * 2 * H + dir * H + unit;
+        e.w = ng * p.Tp * 2 * H + dir * H + unit;
+        itab[it] = e;
+    }
     // A fragments of the transposed slice: A[m = unit slot][k = local gate row] = W_hh[row(k)][unit(m)]
     uint32_t wf[MTW][MT][4];
     if (mma_warp) {
@@ -332,28 +379,25 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
             }
         }
     }
-    int tmax = 0;
-    for (int b = 0; b < p.B; ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
+    int tmax = 0;                                  // this chunk's longest sequence
+    for (int b = n0; b < min(p.B, n0 + 8 * NB); ++b) tmax = max(tmax, min(p.lens[b], p.Tp));
     __syncthreads();
     cluster_sync_all();
 
     // saved forward values of (unit, sequence) for time step s: gates i f g o, c, c_prev, dout -> sv[s & 1], one step ahead
     auto load_saved = [&](int s) {
         for (int it = tid; it < NIT; it += NT) {
-            const int j = it / NBN, n = it - j * NBN, len = slen[n], unit = rank * UPC + j;
-            if (s >= 0 && s < len && unit < H) {
-                const int t = dir ? len - 1 - s : s;
-                const size_t r = (size_t)n * p.pitch + t;
-                const float* gp = p.gates + r * 8 * H + (size_t)dir * 4 * H + unit;
+            const int4 e = itab[it];
+            if (s >= 0 && s < e.x) {
+                const int t = dir ? e.x - 1 - s : s;
+                const float* gp = p.gates + (size_t)e.y + (size_t)t * 8 * H;
+                const float* cp = p.cstate + (size_t)e.z + (size_t)t * 2 * H;
                 float* d = sv + (size_t)(s & 1) * 7 * NIT + it;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) cp_async4(d + (size_t)g * NIT, gp + (size_t)g * H);
-                cp_async4(d + (size_t)4 * NIT, p.cstate + r * 2 * H + (size_t)dir * H + unit);
-                if (s > 0) {
-                    const size_t rp = dir ? r + 1 : r - 1;
-                    cp_async4(d + (size_t)5 * NIT, p.cstate + rp * 2 * H + (size_t)dir * H + unit);
-                }
-                cp_async4(d + (size_t)6 * NIT, p.dout + ((size_t)n * p.Tp + t) * 2 * H + (size_t)dir * H + unit);
+                cp_async4(d + (size_t)4 * NIT, cp);
+                if (s > 0) cp_async4(d + (size_t)5 * NIT, dir ? cp + 2 * (size_t)H : cp - 2 * (size_t)H);     // c of the previous step
+                cp_async4(d + (size_t)6 * NIT, p.dout + (size_t)e.w + (size_t)t * 2 * H);
             }
         }
         cp_async_commit();
@@ -373,9 +417,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
         lap(1);
         // ---- gate gradients of this CTA's units
         for (int it = tid; it < NIT; it += NT) {
-            const int j = it / NBN, n = it - j * NBN, len = slen[n], unit = rank * UPC + j;
+            const int4 e = itab[it];
+            const int j = it / NBN, n = it - j * NBN;
             float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, dc_keep = 0.0f;
-            if (s < len && unit < H) {
+            if (s < e.x) {
                 const float* v = sv + (size_t)(s & 1) * 7 * NIT + it;
                 float dh = v[6 * NIT];
                 if (step > 0) {
@@ -392,8 +437,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                 d_g = dc * gi * (1.0f - gg * gg);
                 d_f = dc * c_prev * gf * (1.0f - gf);
                 dc_keep = dc * gf;
-                const int t = dir ? len - 1 - s : s;
-                float* dg = p.dgates + ((size_t)n * p.pitch + t) * 8 * H + (size_t)dir * 4 * H + unit;
+                const int t = dir ? e.x - 1 - s : s;
+                float* dg = p.dgates + (size_t)e.y + (size_t)t * 8 * H;
                 dg[0] = d_i; dg[H] = d_f; dg[2 * (size_t)H] = d_g; dg[3 * (size_t)H] = d_o;
             }
             dcn[it] = dc_keep;
@@ -427,28 +472,49 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
 #pragma unroll
                     for (int a = 0; a < MTW; ++a) mma_bf16(acc[a], wf[a][MT - 1], b0, b1);
                 }
-                // C fragment: rows lane/4 (+8), sequences 2 (lane%4) + {0,1}.  Lane pairs (xor 1) trade halves so that the even
-                // lane owns 4 consecutive sequences of row lane/4 and the odd lane those of row lane/4 + 8: one 16-byte push each.
+                if (p.bulk) {
+                    // C fragment (rows lane/4 and +8, sequences 2 (lane%4) + {0,1}) -> local staging tile [slot][8] fp32
+                    float* ps = pstage2 + ((size_t)(cur * NB + nb) * KP) * 8;
 #pragma unroll
-                for (int a = 0; a < MTW; ++a) {
-                    const bool odd = lane & 1;
-                    const float s0 = odd ? acc[a][0] : acc[a][2], s1 = odd ? acc[a][1] : acc[a][3];
-                    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-                    float4 v;
-                    if (!odd) v = make_float4(acc[a][0], acc[a][1], r0, r1);        // row lane/4
-                    else v = make_float4(r0, r1, acc[a][2], acc[a][3]);             // row lane/4 + 8
-                    const int slot = (warp * MTW + a) * 16 + (lane >> 2) + (odd ? 8 : 0);
-                    const int n0 = 4 * ((lane & 3) >> 1);                            // lanes 0,1 -> sequences 0..3; lanes 2,3 -> 4..7
-                    const int owner = slot / SLOT, js = slot % SLOT;
-                    const uint32_t dst = smem_u32(recv + ((((size_t)cur * CL + rank) * NB + nb) * SLOT + js) * 8 + n0);
-                    st_async_v4(mapa(dst, owner), mapa(smem_u32(&bars[cur]), owner), *reinterpret_cast<uint4*>(&v));
+                    for (int a = 0; a < MTW; ++a) {
+                        float* o = ps + (size_t)((warp * MTW + a) * 16 + (lane >> 2)) * 8 + 2 * (lane & 3);
+                        *reinterpret_cast<float2*>(o) = make_float2(acc[a][0], acc[a][1]);
+                        *reinterpret_cast<float2*>(o + 64) = make_float2(acc[a][2], acc[a][3]);
+                    }
+                } else {
+                    // Lane pairs (xor 1) trade halves so that the even lane owns 4 consecutive sequences of row lane/4 and the odd
+                    // lane those of row lane/4 + 8: one 16-byte push each.
+#pragma unroll
+                    for (int a = 0; a < MTW; ++a) {
+                        const bool odd = lane & 1;
+                        const float s0 = odd ? acc[a][0] : acc[a][2], s1 = odd ? acc[a][1] : acc[a][3];
+                        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                        float4 v;
+                        if (!odd) v = make_float4(acc[a][0], acc[a][1], r0, r1);        // row lane/4
+                        else v = make_float4(r0, r1, acc[a][2], acc[a][3]);             // row lane/4 + 8
+                        const int slot = (warp * MTW + a) * 16 + (lane >> 2) + (odd ? 8 : 0);
+                        const int n0 = 4 * ((lane & 3) >> 1);                            // lanes 0,1 -> sequences 0..3; lanes 2,3 -> 4..7
+                        const int owner = slot / SLOT, js = slot % SLOT;
+                        const uint32_t dst = smem_u32(recv + ((((size_t)cur * CL + rank) * NB + nb) * SLOT + js) * 8 + n0);
+                        st_async_v4(mapa(dst, owner), mapa(smem_u32(&bars[cur]), owner), *reinterpret_cast<uint4*>(&v));
+                    }
                 }
+            }
+        }
+        if (p.bulk) {       // the staged partial sums go to their owners: ONE bulk copy of 34 slots x 32 bytes per (tile, owner)
+            fence_proxy_async();
+            __syncthreads();
+            if (tid < CL * NB) {
+                const int owner = tid % CL, nb = tid / CL;
+                const uint32_t src = smem_u32(pstage2 + ((size_t)(cur * NB + nb) * KP + owner * SLOT) * 8);
+                const uint32_t dst = smem_u32(recv + (((size_t)cur * CL + rank) * NB + nb) * SLOT * 8);
+                bulk_copy_to_peer(mapa(dst, owner), src, SLOT * 32, mapa(smem_u32(&bars[cur]), owner));
             }
         }
     }
     cp_async_wait_all();
     cluster_sync_all();
-    if (TRACE && p.trace != nullptr && tid == 0)
+    if (TRACE && p.trace != nullptr && tid == 0 && blockIdx.x < 2 * CL)          // the trace buffer holds the first two clusters
         for (int i = 0; i < 6; ++i) p.trace[blockIdx.x * 8 + i] = (unsigned long long)tacc[i];
 }
 
@@ -459,15 +525,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
 static unsigned long long* g_lstm_trace = nullptr;
 void lstm_cluster_set_trace(void* buf) { g_lstm_trace = reinterpret_cast<unsigned long long*>(buf); }
 
-bool lstm_cluster_supported(int B, int H) { return H >= 1 && H <= HMAX && B >= 1 && B <= 32; }
+bool lstm_cluster_supported(int B, int H) { return H >= 1 && H <= HMAX && B >= 1 && B <= 256; }
 
 static size_t fwd_smem(int NB) {
     const size_t nit = (size_t)UPC * 8 * NB;
-    return 256 + (size_t)2 * NB * KP * 16 + (size_t)2 * ROWS * 8 * NB * 4 + (size_t)NB * SLOT * 16 + nit * 4 + 2 * 4 * nit * 4;
+    return 256 + (size_t)2 * NB * KP * 16 + (size_t)2 * ROWS * 8 * NB * 4 + (size_t)2 * NB * SLOT * 16 + nit * 4 + 2 * 4 * nit * 4 + nit * 16;
 }
 static size_t bwd_smem(int NB) {
     const size_t nit = (size_t)UPC * 8 * NB;
-    return 256 + (size_t)2 * CL * NB * SLOT * 8 * 4 + (size_t)NB * ROWS * 16 + nit * 4 + 2 * 7 * nit * 4;
+    return 256 + (size_t)2 * CL * NB * SLOT * 8 * 4 + (size_t)NB * ROWS * 16 + nit * 4 + 2 * 7 * nit * 4 + nit * 16 +
+           (size_t)2 * NB * KP * 8 * 4;
 }
 
 template <bool FWD, bool TRACE>
@@ -482,7 +549,7 @@ static int launch_cluster_t(const ClParams& p, size_t smem, cudaStream_t st) {
         RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[dev] = smem;
     }
-    kern<<<2 * CL, NT, smem, st>>>(p);
+    kern<<<2 * CL * p.n_chunks, NT, smem, st>>>(p);       // clusters of 16: (chunk, direction); independent of each other
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }
@@ -493,10 +560,14 @@ static int launch_cluster(const ClParams& p, size_t smem, cudaStream_t st) {
 }
 
 static int fill(ClParams& p, const int* lens, int B, int Tp, int H) {
-    RADMMM_REQUIRE(lstm_cluster_supported(B, H), "lstm_cluster: B=%d (<= 32) / H=%d (<= %d) out of range", B, H, HMAX);
+    RADMMM_REQUIRE(lstm_cluster_supported(B, H), "lstm_cluster: B=%d (<= 256) / H=%d (<= %d) out of range", B, H, HMAX);
     memset(&p, 0, sizeof(p));
-    p.lens = lens; p.B = B; p.NB = (B + 7) / 8; p.Tp = Tp; p.H = H; p.pitch = Tp + 16;
+    // one cluster per (8 sequences, direction): a step costs the same for every batch size as long as the clusters are
+    // co-resident (148 SMs hold 9 clusters of 16 CTAs, i.e. 32 sequences run in one wave, 64 in two)
+    p.lens = lens; p.B = B; p.NB = 1; p.n_chunks = (B + 7) / 8; p.Tp = Tp; p.H = H; p.pitch = Tp + 16;
     p.trace = g_lstm_trace;
+    static const bool bulk = []() { const char* e = getenv("RADMMM_B200_LSTM_BULK"); return !(e && e[0] == '0'); }();
+    p.bulk = bulk ? 1 : 0;                      // (the backward kernel's staging tile limits the bulk exchange to NB <= 2)
     return RADMMM_OK;
 }
 

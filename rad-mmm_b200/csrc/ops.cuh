@@ -32,6 +32,10 @@ int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const fl
 int colsum(int mode, ActMat x, const RowGeom& g, int n_cols, int dilation, int unratio, float* out, cudaStream_t st);
 int cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, cudaStream_t st);
 
+int radam_chunk_elems();
+int radam_step(const void* recs, const int* chunk_tensor, const long long* chunk_off, int n_chunks, double* state, const double* cfg,
+               cudaStream_t st);
+
 size_t lstm_workspace_bytes(int B, int H);
 int lstm_forward(int mode, const float* xproj, const float* whh_f, const float* whh_r, const int* lens, int B, int Tp, int H,
                  float* out, float* gates, float* cstate, void* workspace, cudaStream_t st);

@@ -185,7 +185,7 @@ def _pad_hidden(p, hid: int, hp: int):
 
 def _run_chunks(lstm, mode, x_btd, lens, p):
     outs = []
-    chunk = 32 if mode == N.MODE_BF16 else 64      # sequences per launch of the recurrence kernels (csrc/lstm_cluster.cu / lstm.cu)
+    chunk = 64      # sequences per launch of the recurrence kernels (csrc/lstm_cluster.cu / lstm.cu)
     for s in range(0, x_btd.shape[0], chunk):
         outs.append(ContextLSTMFunction.apply(lstm, mode, x_btd[s:s + chunk], lens[s:s + chunk].contiguous(), *p))
     return outs[0] if len(outs) == 1 else torch.cat(outs, 0)

@@ -279,9 +279,29 @@ def frontend_case():
         npz(f"frontend_{tag}.npz", mag=mag[:, ::8], mel=mel, meta=np.asarray([sr, n]))
 
 
+def radam_case():
+    """Reference radam.RAdam (radam.py:45-142) for 9 steps -- across the N_sma >= 5 switch -- with the gradient clipping
+    Lightning applies before every step (configs/RADMMM_train_config.yaml:7-8: clip_grad_norm_(params, 1.0)) and the shipped
+    weight decay (configs/RADMMM_model_config.yaml:64)."""
+    from radam import RAdam
+    shapes = {"a": (37, 19), "b": (1024,), "c": (5, 7, 3), "d": (1,)}
+    params = [torch.nn.Parameter(syn.hash_uniform("radam.p." + k, s, -1, 1)) for k, s in shapes.items()]
+    opt = RAdam(params, lr=1e-3, weight_decay=1e-6)
+    traj, norms = [], []
+    for step in range(9):
+        for (k, s), p in zip(shapes.items(), params):
+            p.grad = syn.hash_uniform(f"radam.g{step}." + k, s, -1, 1) * (3.0 if step % 2 == 0 else 0.01)
+        norms.append(torch.nn.utils.clip_grad_norm_(params, 1.0).item())
+        opt.step()
+        traj.append(torch.cat([p.detach().flatten() for p in params]).clone())
+    st = opt.state[params[0]]
+    npz("radam.npz", traj=torch.stack(traj), norms=np.asarray(norms), exp_avg_a=st["exp_avg"], exp_avg_sq_a=st["exp_avg_sq"],
+        step=np.asarray(st["step"]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["keys", "ops", "spline", "frontend", "small", "full"]
+    which = sys.argv[1:] or ["keys", "ops", "spline", "frontend", "small", "full", "radam"]
     if "keys" in which:
         state_dict_keys()
     if "ops" in which:
@@ -294,3 +314,5 @@ if __name__ == "__main__":
         decoder_case("decoder_small.npz", n_flows=2, batch=2, frames=128)
     if "full" in which:
         decoder_case("decoder_full.npz", n_flows=8, batch=2, frames=96)
+    if "radam" in which:
+        radam_case()

@@ -438,3 +438,74 @@ def test_training_step_standin():
     assert losses_e[0] != losses_e[1] != losses_e[2]
     for a, b in zip(losses_e, losses_g):
         assert abs(a - b) <= 2e-5 * abs(a) + 1e-6, (losses_e, losses_g)
+
+
+# ------------------------------------------------------------------------------------------------ fused RAdam (8f-1)
+def test_fused_radam_vs_reference_trajectory():
+    """radmmm_b200.radam.RAdam (three launches for all tensors, clipping folded in) against the reference radam.RAdam
+    trajectory fixture (9 steps across the N_sma >= 5 switch, clip_grad_norm_(1.0) before every step, weight decay 1e-6),
+    and against the oracle restatement on a larger, ragged set of tensors."""
+    from radmmm_b200.radam import RAdam
+    gd = gold("radam.npz")
+    shapes = {"a": (37, 19), "b": (1024,), "c": (5, 7, 3), "d": (1,)}
+    params = [torch.nn.Parameter(syn.hash_uniform("radam.p." + k, s, -1, 1).to(DEV)) for k, s in shapes.items()]
+    opt = RAdam(params, lr=1e-3, weight_decay=1e-6, max_grad_norm=1.0)
+    for step in range(9):
+        for (k, s), p in zip(shapes.items(), params):
+            p.grad = (syn.hash_uniform(f"radam.g{step}." + k, s, -1, 1) * (3.0 if step % 2 == 0 else 0.01)).to(DEV)
+        opt.step()
+        close(torch.cat([p.detach().flatten() for p in params]), gd["traj"][step], 2e-7, what=f"radam step {step + 1}")
+        close(opt.last_grad_norm(), gd["norms"][step], 1e-5 * float(gd["norms"][step]), what="grad norm")
+    st = opt.state[params[0]]
+    close(st["exp_avg"], gd["exp_avg_a"], 1e-8, what="exp_avg")
+    close(st["exp_avg_sq"], gd["exp_avg_sq_a"], 1e-9, what="exp_avg_sq")
+    assert st["step"] == 9
+    # larger / ragged tensors (several chunks per tensor, unaligned sizes), no clipping, vs the oracle
+    sizes = [(3, 16384 + 5), (70001,), (129, 513), (7,)]
+    ps = [torch.nn.Parameter(syn.hash_uniform(f"radam2.p{i}", s, -1, 1).to(DEV)) for i, s in enumerate(sizes)]
+    ref_p = [p.detach().cpu().clone() for p in ps]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    opt2 = RAdam(ps, lr=3e-3, betas=(0.8, 0.99), weight_decay=0)
+    for step in range(7):
+        gs = [syn.hash_uniform(f"radam2.g{step}.{i}", s, -1, 1) for i, s in enumerate(sizes)]
+        for p, g in zip(ps, gs):
+            p.grad = g.to(DEV)
+        opt2.step()
+        of.radam_step(ref_p, gs, ref_m, ref_v, step + 1, lr=3e-3, betas=(0.8, 0.99))
+    for p, r in zip(ps, ref_p):
+        close(p.detach(), r, 5e-7, what="radam vs oracle (ragged tensors)")
+
+
+def test_fused_radam_inside_the_graphed_step():
+    """The optimizer captured in the step graph (GraphedTrainStep(after_backward=optimizer.step)): three replays equal three
+    eager steps (decoder forward + loss + backward + clip + RAdam) on a twin decoder."""
+    from radmmm_b200.graphs import GraphedTrainStep
+    from radmmm_b200.radam import RAdam
+    T = 64
+    bt = {k: v.to(DEV) for k, v in syn.synthetic_batch(2, T, tag="radam.graph").items()}
+    eager, graphed = _decoder(2, "fp32"), _decoder(2, "fp32")
+    opt_e = RAdam(eager.parameters(), lr=1e-3, weight_decay=1e-6, max_grad_norm=1.0)
+    opt_g = RAdam(graphed.parameters(), lr=1e-3, weight_decay=1e-6, max_grad_norm=1.0)
+    # one eager step on both: builds the optimizer's device tables (needs gradients) before the capture
+    for dec, opt in ((eager, opt_e), (graphed, opt_g)):
+        _eager_grads(dec, bt, T)
+        opt.step()
+    step = GraphedTrainStep(graphed, bt, after_backward=opt_g.step)
+    # the capture's warm-up steps already advanced `graphed`; bring the twin to the same point, then compare replays
+    eager.load_state_dict(graphed.state_dict())
+    opt_e.load_state_dict(opt_g.state_dict())
+    opt_g.sync_step_counts()
+    opt_e.load_state_dict(opt_g.state_dict())
+    losses_g, losses_e = [], []
+    for _ in range(3):
+        losses_g.append(float(step(bt)))
+        le, _ = _eager_grads(eager, bt, T)
+        opt_e.step()
+        losses_e.append(float(le))
+    torch.cuda.synchronize()
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= 2e-5 * abs(a) + 1e-6, (losses_e, losses_g)
+    assert losses_e[0] != losses_e[2]
+    for (n, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
+        close(q.detach(), p.detach(), 2e-5 * max(1.0, p.detach().abs().max().item()), what="parameter after 3 steps " + n)

@@ -265,3 +265,29 @@ def test_decoder_forward_loss_grads_inverse(fname, n_flows, batch, frames):
     with torch.no_grad():
         mel = of.decoder_inverse(sd, cfg, residual, out["context_w_spkvec"].detach(), lens_g)
     close(mel, gd["mel_inv"], 2e-4, 1e-5)
+
+
+def _radam_inputs():
+    shapes = {"a": (37, 19), "b": (1024,), "c": (5, 7, 3), "d": (1,)}
+    params = [syn.hash_uniform("radam.p." + k, s, -1, 1) for k, s in shapes.items()]
+    grads = [[syn.hash_uniform(f"radam.g{step}." + k, s, -1, 1) * (3.0 if step % 2 == 0 else 0.01) for k, s in shapes.items()]
+             for step in range(9)]
+    return shapes, params, grads
+
+
+def test_radam_trajectory():
+    """oracle.flow.radam_step + clip_grad_norm against 9 steps of the reference radam.RAdam under Lightning-style clipping
+    (radam.py:63-142; the trajectory crosses the N_sma >= 5 switch between steps 5 and 6)."""
+    gd = g("radam.npz")
+    _, params, grads = _radam_inputs()
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    for step in range(9):
+        gs = [x.clone() for x in grads[step]]
+        total = of.clip_grad_norm(gs, 1.0)
+        assert abs(float(total) - float(gd["norms"][step])) <= 1e-5 * float(gd["norms"][step])
+        of.radam_step(params, gs, m, v, step + 1, lr=1e-3, weight_decay=1e-6)
+        close(torch.cat([p.flatten() for p in params]), gd["traj"][step], 1e-7)
+    close(m[0], gd["exp_avg_a"], 1e-8)
+    close(v[0], gd["exp_avg_sq_a"], 1e-9)
+    assert int(gd["step"]) == 9

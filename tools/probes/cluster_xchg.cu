@@ -59,7 +59,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) xchg_kernel(
                              ::"r"(dst), "r"(v), "r"(v), "r"(v), "r"(v), "r"(rbar) : "memory");
             }
             mbar_wait(&bars[par], (s >> 1) & 1);
-        } else {
+        } else if (MODE == 1) {
             for (int i = tid; i < total_vec; i += NT) {
                 const int peer = i / vec_per_pair, slot = i % vec_per_pair;
                 const uint32_t dst = mapa(smem_u32(&buf[(par * CL + rank) * vec_per_pair + slot]), peer);
@@ -67,6 +67,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) xchg_kernel(
                 asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v), "r"(v), "r"(v), "r"(v) : "memory");
             }
             asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        } else {
+            // mode 2: the slice is first written to a local staging tile, then ONE bulk copy per peer (the copy engine moves
+            // vec_per_pair * 16 bytes and completes them on the peer's mbarrier)
+            uint4* stage = buf + 2 * total_vec;                          // [vec_per_pair]
+            for (int i = tid; i < vec_per_pair; i += NT) stage[i] = make_uint4(s, rank, s, rank);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[par])), "r"(total_vec * 16) : "memory");
+            if (tid < CL) {
+                const uint32_t dst = mapa(smem_u32(&buf[(par * CL + rank) * vec_per_pair]), tid);
+                const uint32_t rbar = mapa(smem_u32(&bars[par]), tid);
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "r"(smem_u32(stage)), "r"(vec_per_pair * 16), "r"(rbar) : "memory");
+            }
+            mbar_wait(&bars[par], (s >> 1) & 1);
         }
         // consume: every thread reads one received vector (as the mat-vec would) -- keeps the loads from being elided
         const uint4 r = buf[par * total_vec + (tid % total_vec)];
@@ -80,7 +95,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) xchg_kernel(
 template <int MODE>
 static void run(int n_clusters, int steps, int vec_per_pair, float* out) {
     auto kern = xchg_kernel<MODE>;
-    const size_t smem = 64 + 2 * CL * (size_t)vec_per_pair * 16;
+    const size_t smem = 64 + 2 * CL * (size_t)vec_per_pair * 16 + (size_t)vec_per_pair * 16;
     cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
@@ -95,7 +110,7 @@ static void run(int n_clusters, int steps, int vec_per_pair, float* out) {
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep == 2)
             printf("mode %d (%s) clusters=%d bytes/pair=%5d: %8.1f us total, %6.3f us/step\n", MODE,
-                   MODE == 0 ? "st.async+mbarrier" : "st.cluster+barrier.cluster", n_clusters, vec_per_pair * 16, ms * 1e3, ms * 1e3 / steps);
+                   MODE == 0 ? "st.async+mbarrier" : MODE == 1 ? "st.cluster+barrier.cluster" : "bulk copy per peer+mbarrier", n_clusters, vec_per_pair * 16, ms * 1e3, ms * 1e3 / steps);
     }
 }
 
@@ -105,7 +120,7 @@ int main() {
     int max_clusters = 0;
     {
         cudaLaunchConfig_t q = {};
-        q.gridDim = dim3(2 * CL); q.blockDim = dim3(NT); q.dynamicSmemBytes = 64 + 2 * CL * 132 * 16;
+        q.gridDim = dim3(2 * CL); q.blockDim = dim3(NT); q.dynamicSmemBytes = 64 + 2 * CL * 132 * 16 + 132 * 16;
         cudaLaunchAttribute qa[1];
         qa[0].id = cudaLaunchAttributeClusterDimension;
         qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
@@ -119,6 +134,7 @@ int main() {
     for (int vec : {33, 66, 132, 264}) {           // 528 B (h hi, B=8), 1056 B (hi+lo / fp32 partials), 2112, 4224
         run<0>(2, steps, vec, out);
         run<1>(2, steps, vec, out);
+        run<2>(2, steps, vec, out);
     }
     run<0>(1, steps, 33, out);
     cudaFree(out);
