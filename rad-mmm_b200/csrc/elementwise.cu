@@ -1,6 +1,7 @@
 // HBM-bound kernels of the flow step: layout packing, affine coupling (fwd / inverse / bwd), invertible 1x1
 // convolution, flow-NLL reduction, weight-norm preparation and its backward, bias-gradient column sums.
 // All are sized so that a warp touches consecutive addresses along the contiguous (time or channel) axis.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -741,11 +742,92 @@ __global__ void __launch_bounds__(256) wn_bwd_staged_kernel(const float* __restr
     }
 }
 
+// The same computation fed by the bulk-copy engine: the v row (contiguous) and the ksize dW rows of the output channel are
+// brought into shared memory by cp.async.bulk (one elected thread, one mbarrier) -- no register staging, all of a CTA's
+// bytes in flight at once, several CTAs per SM overlapping their load / compute / store phases.  dW stays in its
+// [tap][ci] layout; the dot product and dv read it transposed out of shared memory (stride ksize: conflict-free for 5).
+// Needs 16-byte aligned rows (ci_total % 4 == 0 and a single source block); other shapes use the staged kernel above.
+__global__ void __launch_bounds__(256) wn_bwd_bulk_kernel(const float* __restrict__ src, long long ld, long long tap_stride,
+                                                          const float* __restrict__ v, const float* __restrict__ g,
+                                                          const float* __restrict__ norm, int ci_total, int ksize,
+                                                          float* __restrict__ dv, float* __restrict__ dg) {
+    extern __shared__ __align__(128) float wsm[];
+    const int co = blockIdx.x;
+    const int per_co = ci_total * ksize;
+    float* sv = wsm;                 // [ci][k]  (the layout of v)
+    float* sd = wsm + per_co;        // [k][ci]  (the layout of dW)
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes_v = (unsigned)per_co * 4u, bytes_row = (unsigned)ci_total * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes_v + bytes_row * ksize) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(sv)), "l"(v + (long long)co * per_co), "r"(bytes_v), "r"(bar_addr) : "memory");
+        for (int k = 0; k < ksize; ++k)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((unsigned)__cvta_generic_to_shared(sd + k * ci_total)), "l"(src + k * tap_stride + (long long)co * ld),
+                           "r"(bytes_row), "r"(bar_addr) : "memory");
+    }
+    __syncthreads();                                   // the barrier is initialised before anyone polls it
+    {
+        unsigned done = 0;
+        long long spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar_addr) : "memory");
+            if (++spins > (1ll << 22)) { printf("radmmm wn_bwd_bulk: copy timed out (block %d)\n", blockIdx.x); __trap(); }
+        }
+    }
+    double dot = 0.0;
+    {
+        float part = 0.0f;               // <= 8 products per fp32 partial, then fp64
+        int n = 0;
+        for (int i = threadIdx.x; i < per_co; i += 256) {
+            const int ci = i / ksize, k = i - ci * ksize;
+            part = fmaf(sd[k * ci_total + ci], sv[i], part);
+            if (++n == 8) { dot += (double)part; part = 0.0f; n = 0; }
+        }
+        dot += (double)part;
+    }
+    __shared__ double red[8];
+    __shared__ float sdot;
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0;
+        for (int i = 0; i < 8; ++i) a += red[i];
+        sdot = (float)a;
+    }
+    __syncthreads();
+    const float nrm = norm[co], gg = g[co];
+    const float d = sdot;
+    if (threadIdx.x == 0) dg[co] = d / nrm;
+    const float sc = gg / nrm, coef = d / (nrm * nrm);
+    float4* o = reinterpret_cast<float4*>(dv + (long long)co * per_co);
+    for (int i4 = threadIdx.x; i4 < (per_co >> 2); i4 += 256) {
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = 4 * i4 + e, ci = i / ksize, k = i - ci * ksize;
+            r[e] = sc * (sd[k * ci_total + ci] - sv[i] * coef);
+        }
+        o[i4] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
 int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const float* src1, long long ld1,
            long long tap1, const float* v, const float* g, const float* norm, int n_co, int ci_total, int ksize,
            float* dv, float* dg, cudaStream_t st) {
     const size_t smem = sizeof(float) * 2 * (size_t)ci_total * ksize;
-    if (smem <= 48 * 1024) {
+    static const bool bulk_on = []() { const char* e = getenv("RADMMM_B200_WNBWD_BULK"); return !(e && e[0] == '0'); }();
+    const bool aligned = src1 == nullptr && n_ci0 == ci_total && (ci_total & 3) == 0 && (ld0 & 3) == 0 && (tap0 & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(src0) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0;
+    if (bulk_on && aligned && smem <= 48 * 1024) {
+        wn_bwd_bulk_kernel<<<n_co, 256, smem, st>>>(src0, ld0, tap0, v, g, norm, ci_total, ksize, dv, dg);
+    } else if (smem <= 48 * 1024) {
         wn_bwd_staged_kernel<<<n_co, 256, smem, st>>>(src0, ld0, tap0, n_ci0, src1, ld1, tap1, v, g, norm, ci_total, ksize, dv, dg);
     } else {
         wn_bwd_kernel<<<n_co, 256, 0, st>>>(src0, ld0, tap0, n_ci0, src1, ld1, tap1, v, g, norm, ci_total, ksize, dv, dg);
@@ -804,6 +886,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(ActMat x, RowGeom g, int n_
     for (int i = 0; i < 8; ++i) tot += red[i][tid];
     const int c = blockIdx.x * 256 + tid;
     if (c < n_cols && tot != 0.0f) atomicAdd(out + c, tot);
+}
+
+__global__ void zero_list_kernel(ZeroList z) {
+    float* p = z.ptr[blockIdx.x];
+    for (int i = threadIdx.x; i < z.count[blockIdx.x]; i += blockDim.x) p[i] = 0.0f;
+}
+int zero_list(const ZeroList& z, cudaStream_t st) {
+    if (z.n <= 0) return RADMMM_OK;
+    zero_list_kernel<<<z.n, 256, 0, st>>>(z);
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
 }
 
 int colsum(int mode, ActMat x, const RowGeom& g, int n_cols, int dilation, int unratio, float* out, cudaStream_t st) {

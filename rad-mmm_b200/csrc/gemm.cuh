@@ -57,6 +57,11 @@ struct EpiParams {
     int cf_C, cf_c0;
     int atomic;                  // weight-grad split-K: atomicAdd instead of store
     float* group_out[4];         // grouped weight-grad (GemmArgs::wgrad == 3): output of group g (else null: f32_out + tap stride)
+    // Bias gradients fused into the gradient epilogues of the tensor-core path (null: not wanted / computed by colsum()):
+    // colsum[l][n] += sum over valid rows of what the epilogue produces for layer l BEFORE the partial-conv ratio
+    // (EPI_DOUT: dq_l -> res-skip bias l; EPI_DH: acc * softplus' -> dilated-conv bias; EPI_DH0: dh0 -> start bias).
+    // The buffers must be zero when the kernel starts.
+    float* colsum[kMaxLayers];
 };
 
 struct GemmArgs {
@@ -209,6 +214,26 @@ __device__ __forceinline__ void staged_store32_f32(const Stager& st, float* out,
     }
 }
 
+// Column sums of a warp's 32 x 32 tile (lane = row, v[32] = this row's values): halving butterfly, 31 shuffles; lane c
+// ends up with the sum of column c.  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+__device__ __forceinline__ void colsum_add(float* dst, int n0, int N, int lane, float* v) {
+    const float sum = warp_colsum32(v, lane);
+    if (n0 + lane < N) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n0 + lane), "f"(sum) : "memory");
+}
+
 template <int MODE, int NV>
 __device__ __forceinline__ void store_row_vec(const Stager& st, const ActMat& m, int r, int n0, const float* v) {
     if (m.ptr == nullptr) return;
@@ -358,6 +383,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
                                 out[i] = valid ? y : 0.0f;
                             }
                             store_row_vec<MODE, NV>(st, p.dq[l0 + j], r, n0, out);
+                            if (p.colsum[l0 + j] != nullptr) colsum_add(p.colsum[l0 + j], n0, p.N, st.lane, out);
                         }
                     }
                 }
@@ -388,6 +414,9 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const Stager& st, 
 #pragma unroll
         for (int i = 0; i < NV; ++i) out[i] = valid ? acc[i] : 0.0f;
         store_row_vec<MODE, NV>(st, p.out0, r, n0, out);
+        if constexpr (MODE != MODE_F32 && NV == 32) {
+            if (st.buf != nullptr && p.colsum[0] != nullptr) colsum_add(p.colsum[0], n0, p.N, st.lane, out);
+        }
     } else if constexpr (KIND == EPI_DCTX || KIND == EPI_F32) {
         if constexpr (NV == 32) {
             if (st.buf != nullptr && !p.accumulate && n0 + NV <= p.N && (p.f32_ld & 3) == 0) {
@@ -415,13 +444,15 @@ __device__ __forceinline__ void epi_dh_with_h(const EpiParams& p, const Stager& 
     row_decode(p.geom, r, b, t, len);
     const bool valid = t < len;
     const float ratio = valid ? pconv_ratio(t, len, p.dilation) : 0.0f;
-    float out[32];
+    float out[32], pre[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const float y = acc[i] * sigmoid_from_softplus<true>(hv[i]) * ratio;
-        out[i] = valid ? y : 0.0f;
+        const float y = acc[i] * sigmoid_from_softplus<true>(hv[i]);       // gradient at the conv's bias (before the ratio)
+        pre[i] = valid ? y : 0.0f;
+        out[i] = pre[i] * ratio;
     }
     store_row_vec<MODE, 32>(st, p.out0, r, n0, out);
+    if (p.colsum[0] != nullptr) colsum_add(p.colsum[0], n0, p.N, st.lane, pre);
 }
 
 // weight-grad tile element (m, n0..n0+NV) of tap `tap`

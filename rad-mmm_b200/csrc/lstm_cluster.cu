@@ -51,6 +51,8 @@ struct ClParams {
     const float* dout;        // backward: (B, Tp, 2H)
     float* dgates;            // backward: [R][8H] pre-activation gate gradients
     int B, NB, Tp, H, pitch, n_chunks;     // NB x 8 sequences per cluster, n_chunks clusters per direction
+    int probe;                   // tools/lstm_cluster_probe.py (RADMMM_B200_LSTM_PROBE): 1 skip the saved-state stores, 2 skip the gate
+                                 // transcendentals, 4 skip the cp.async prefetch
     int bulk;                    // 1: exchange with one bulk DSMEM copy per peer (cp.async.bulk shared::cta -> shared::cluster);
                                  // 0: one 16-byte st.async per (unit, peer)  (RADMMM_B200_LSTM_BULK=0, A/B measurements)
     unsigned long long* trace;   // diagnostic (radmmm_debug_trace): per CTA 8 accumulated SM-clock counters, see kernels
@@ -275,23 +277,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
                 const float* pa = part + (size_t)(4 * j) * NBN + n;
                 const float* pb = pa + (size_t)ROWS * NBN;
                 const float* xp = xps + (size_t)cur * 4 * NIT + it;
-                const float gi = sigmoidf_(pa[0] + pb[0] + xp[0]);
-                const float gf = sigmoidf_(pa[NBN] + pb[NBN] + xp[NIT]);
-                const float gg = tanhf_(pa[2 * NBN] + pb[2 * NBN] + xp[2 * NIT]);
-                const float go = sigmoidf_(pa[3 * NBN] + pb[3 * NBN] + xp[3 * NIT]);
+                float gi = pa[0] + pb[0] + xp[0], gf = pa[NBN] + pb[NBN] + xp[NIT];
+                float gg = pa[2 * NBN] + pb[2 * NBN] + xp[2 * NIT], go = pa[3 * NBN] + pb[3 * NBN] + xp[3 * NIT];
+                if (!(p.probe & 2)) { gi = sigmoidf_(gi); gf = sigmoidf_(gf); gg = tanhf_(gg); go = sigmoidf_(go); }
                 const float c = gf * cst[it] + gi * gg;
-                h = go * tanhf_(c);
+                h = go * ((p.probe & 2) ? c : tanhf_(c));
                 cst[it] = c;
-                const int t = dir ? e.x - 1 - s : s;
-                float* gp = p.gates + (size_t)e.y + (size_t)t * 8 * H;
-                gp[0] = gi; gp[H] = gf; gp[2 * (size_t)H] = gg; gp[3 * (size_t)H] = go;
-                p.cstate[(size_t)e.z + (size_t)t * 2 * H] = c;
-                p.out[(size_t)e.w + (size_t)t * 2 * H] = h;
+                if (!(p.probe & 1)) {
+                    const int t = dir ? e.x - 1 - s : s;
+                    float* gp = p.gates + (size_t)e.y + (size_t)t * 8 * H;
+                    gp[0] = gi; gp[H] = gf; gp[2 * (size_t)H] = gg; gp[3 * (size_t)H] = go;
+                    p.cstate[(size_t)e.z + (size_t)t * 2 * H] = c;
+                    p.out[(size_t)e.w + (size_t)t * 2 * H] = h;
+                }
             }
             hstage[((size_t)(n >> 3) * SLOT + j) * 8 + (n & 7)] = __float2bfloat16_rn(h);
         }
         if (s + 1 == tmax) break;
-        fetch_xp(s + 1);                       // in flight across the exchange
+        if (!(p.probe & 4)) fetch_xp(s + 1);   // in flight across the exchange
         lap(3);
         if (p.bulk) fence_proxy_async();       // hstage was written through the generic proxy, the copy engine reads it
         __syncthreads();
@@ -430,16 +433,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                 }
                 const float gi = v[0], gf = v[NIT], gg = v[2 * NIT], go = v[3 * NIT];
                 const float c_prev = s > 0 ? v[5 * NIT] : 0.0f;
-                const float tc = tanhf_(v[4 * NIT]);
+                const float tc = (p.probe & 2) ? v[4 * NIT] : tanhf_(v[4 * NIT]);
                 const float dc = dh * go * (1.0f - tc * tc) + dcn[it];
                 d_o = dh * tc * go * (1.0f - go);
                 d_i = dc * gg * gi * (1.0f - gi);
                 d_g = dc * gi * (1.0f - gg * gg);
                 d_f = dc * c_prev * gf * (1.0f - gf);
                 dc_keep = dc * gf;
-                const int t = dir ? e.x - 1 - s : s;
-                float* dg = p.dgates + (size_t)e.y + (size_t)t * 8 * H;
-                dg[0] = d_i; dg[H] = d_f; dg[2 * (size_t)H] = d_g; dg[3 * (size_t)H] = d_o;
+                if (!(p.probe & 1)) {
+                    const int t = dir ? e.x - 1 - s : s;
+                    float* dg = p.dgates + (size_t)e.y + (size_t)t * 8 * H;
+                    dg[0] = d_i; dg[H] = d_f; dg[2 * (size_t)H] = d_g; dg[3 * (size_t)H] = d_o;
+                }
             }
             dcn[it] = dc_keep;
             __nv_bfloat16* o = dgs + ((size_t)(n >> 3) * ROWS + 4 * j) * 8 + (n & 7);
@@ -447,7 +452,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
             o[16] = __float2bfloat16_rn(d_g); o[24] = __float2bfloat16_rn(d_o);
         }
         if (s == 0) break;
-        load_saved(s - 1);                     // in flight across the mat-vec and the exchange
+        if (!(p.probe & 4)) load_saved(s - 1); // in flight across the mat-vec and the exchange
         lap(2);
         __syncthreads();
         lap(3);
@@ -555,7 +560,13 @@ static int launch_cluster_t(const ClParams& p, size_t smem, cudaStream_t st) {
 }
 
 template <bool FWD>
-static int launch_cluster(const ClParams& p, size_t smem, cudaStream_t st) {
+static int launch_cluster(const ClParams& p_in, size_t smem, cudaStream_t st) {
+    // exchange flavour (measured on B200 at B=8, T'=400, profiles/): forward 2.50 us/step with one bulk DSMEM copy per peer
+    // vs 2.84 with 16-byte st.async pushes; backward 2.94 vs 2.63 (its payload comes straight from the accumulator registers,
+    // the bulk copy needs a staging round trip through shared memory).  RADMMM_B200_LSTM_BULK=0/1 forces one for both.
+    static const int forced = []() { const char* e = getenv("RADMMM_B200_LSTM_BULK"); return e ? (e[0] != '0' ? 1 : 0) : -1; }();
+    ClParams p = p_in;
+    p.bulk = forced >= 0 ? forced : (FWD ? 1 : 0);
     return p.trace != nullptr ? launch_cluster_t<FWD, true>(p, smem, st) : launch_cluster_t<FWD, false>(p, smem, st);
 }
 
@@ -566,8 +577,8 @@ static int fill(ClParams& p, const int* lens, int B, int Tp, int H) {
     // co-resident (148 SMs hold 9 clusters of 16 CTAs, i.e. 32 sequences run in one wave, 64 in two)
     p.lens = lens; p.B = B; p.NB = 1; p.n_chunks = (B + 7) / 8; p.Tp = Tp; p.H = H; p.pitch = Tp + 16;
     p.trace = g_lstm_trace;
-    static const bool bulk = []() { const char* e = getenv("RADMMM_B200_LSTM_BULK"); return !(e && e[0] == '0'); }();
-    p.bulk = bulk ? 1 : 0;                      // (the backward kernel's staging tile limits the bulk exchange to NB <= 2)
+    p.bulk = -1;                                // decided per kernel in launch_cluster
+    { const char* e = getenv("RADMMM_B200_LSTM_PROBE"); p.probe = e ? atoi(e) : 0; }
     return RADMMM_OK;
 }
 

@@ -31,6 +31,9 @@ int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const fl
            float* dv, float* dg, cudaStream_t st);
 int colsum(int mode, ActMat x, const RowGeom& g, int n_cols, int dilation, int unratio, float* out, cudaStream_t st);
 int cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, cudaStream_t st);
+// zero up to 16 small fp32 buffers with one launch
+struct ZeroList { float* ptr[16]; int count[16]; int n; };
+int zero_list(const ZeroList& z, cudaStream_t st);
 
 int radam_chunk_elems();
 int radam_step(const void* recs, const int* chunk_tensor, const long long* chunk_off, int n_chunks, double* state, const double* cfg,

@@ -382,13 +382,23 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         return RADMMM_OK;
     };
 
+    // Bias gradients of the WN convs: on the tensor-core path the gradient epilogues accumulate them (column sums with
+    // red.global.add), so the 2L + 1 buffers are zeroed here by one small launch; the fp32 path uses colsum() kernels.
+    const bool fuse_bias = d.mode != MODE_F32;
+    if (fuse_bias) {
+        ZeroList z;
+        z.n = 0;
+        for (int i = 0; i < L; ++i) { z.ptr[z.n] = gr->rs_b[i]; z.count[z.n++] = H; z.ptr[z.n] = gr->in_b[i]; z.count[z.n++] = H; }
+        z.ptr[z.n] = gr->start_b; z.count[z.n++] = H;
+        RADMMM_TRY(zero_list(z, mc));
+    }
     // 1. coupling tail
     RADMMM_TRY(coupling_bwd(dz_out, dlog_s, z_mid, params, f->lens, dz_mid, dparams, d.B, d.C, d.Tp, f->scaling_fn, mc));
     RADMMM_TRY(rows_from_cf(d.mode, dparams, (long long)d.C * d.Tp, d.C, g, s.DP, d.Cp, 1, mc));
     // 2. end conv: input gradient on the chain ...
     init_args(a, d, f->lens, EPI_DOUT, H);
     add_seg(a, s.DP, p.WendT, d.Cp, 0);
-    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.S[i]; a.epi.dq[i] = s.DQ[i]; }
+    for (int i = 0; i < L; ++i) { a.epi.sig[i] = w.S[i]; a.epi.dq[i] = s.DQ[i]; if (fuse_bias) a.epi.colsum[i] = gr->rs_b[i]; }
     RADMMM_TRY(launch_gemm(a, d.mode, mc));
     //    ... DP and every DQ_i are ready: the end conv and all L res-skip convs can take their weight gradients now
     for (int l = 0; l < (forked ? kLanes : 0); ++l) RADMMM_TRY(ready(lane_stream(l)));
@@ -421,9 +431,9 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         wa.split_k = 1; wa.epi.atomic = 0; wa.zero_output = 0;
         RADMMM_TRY(launch_gemm(wa, d.mode, sd));
         for (int i = L - 1; i >= 0; --i) {
-            RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], sb));
+            if (!fuse_bias) RADMMM_TRY(colsum(d.mode, s.DQ[i], g, H, 1, 0, gr->rs_b[i], sb));
             RADMMM_TRY(wn_bwd(s.dW_rs[i], H, 0, H, nullptr, 0, 0, f->rs_v[i], f->rs_g[i], p.norm_rs + (size_t)i * H, H, H, 1,
-                              gr->rs_v[i], gr->rs_g[i], sd));
+                              gr->rs_v[i], gr->rs_g[i], sd));        // same lane as the grouped launch that produced dW_rs
         }
     }
     // 3. layers, last to first
@@ -438,11 +448,12 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
         a.epi.h = w.Hs[i + 1];
         a.epi.dilation = dil;
         a.epi.out0 = s.DACC[i];
+        if (fuse_bias) a.epi.colsum[0] = gr->in_b[i];
         RADMMM_TRY(launch_gemm(a, d.mode, mc));
         // dilated conv i: bias (un-ratio'd) and weights on lanes 2 and 3
         cudaStream_t sd = lane(2 + (i & 1));
         RADMMM_TRY(ready(sd));                // dacc_i ready
-        RADMMM_TRY(colsum(d.mode, s.DACC[i], g, H, dil, 1, gr->in_b[i], sd));
+        if (!fuse_bias) RADMMM_TRY(colsum(d.mode, s.DACC[i], g, H, dil, 1, gr->in_b[i], sd));
         RADMMM_TRY(wgrad(d, f->lens, s.DACC[i], w.Hs[i], H, H, 5, dil, s.dW_in[i], H, p.HH, sd));
         RADMMM_TRY(wn_bwd(s.dW_in[i], H, p.HH, H, nullptr, 0, 0, f->in_v[i], f->in_g[i], p.norm_in + (size_t)i * H, H, H, 5,
                           gr->in_v[i], gr->in_g[i], sd));
@@ -451,13 +462,14 @@ int flow_backward(const radmmm_flow_desc* f, const float* z_in, const float* z_m
     init_args(a, d, f->lens, EPI_DH0, H);
     for (int j = 0; j < 5; ++j) add_seg(a, s.DACC[0], sub_mode(p.WinT, (long long)j * p.HH, d.es), H, -(j - 2));
     a.epi.out0 = s.DACC[L];
+    if (fuse_bias) a.epi.colsum[0] = gr->start_b;
     RADMMM_TRY(launch_gemm(a, d.mode, mc));
     const ActMat& DH0 = s.DACC[L];
     // 5. start conv: weight / bias gradients on lane 0, input gradients on the chain
     {
         cudaStream_t sd = lane(0);
         RADMMM_TRY(ready(sd));                // dh0 ready
-        RADMMM_TRY(colsum(d.mode, DH0, g, H, 1, 0, gr->start_b, sd));
+        if (!fuse_bias) RADMMM_TRY(colsum(d.mode, DH0, g, H, 1, 0, gr->start_b, sd));
         float* dWz = s.dW_start;
         float* dWc = s.dW_start + (size_t)H * d.Kz;
         RADMMM_TRY(wgrad(d, f->lens, DH0, w.Z0, H, d.Kz, 1, 1, dWz, d.Kz, 0, sd));

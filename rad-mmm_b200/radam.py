@@ -121,6 +121,12 @@ class RAdam(Optimizer):
                     self.state[p]["step"] = self.state[p].get("step", 0) + 1
         return loss
 
+    def load_state_dict(self, state_dict):
+        """The loaded state tensors are new objects: forget the device tables (rebuilt, with the loaded step count, at the next
+        ``step``)."""
+        super().load_state_dict(state_dict)
+        self._tables = {}
+
     def sync_step_counts(self):
         """After CUDA-graph replays (which advance the device counter only): copy it into the per-parameter ``step`` entries
         so that ``state_dict()`` is exact.  One device-to-host read."""

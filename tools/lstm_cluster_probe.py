@@ -66,6 +66,12 @@ def main():
         for tag, rows in (("mean", t.mean(0)), ("min ", t.min(0).values), ("max ", t.max(0).values)):
             print(f"{tag}" + " ".join(f"{float(v):13.3f}" for v in rows[:6]) + f"   {float(rows[:6].sum()):8.3f}")
     lib.radmmm_debug_trace(None, 0, -1)
+    # what a step's pointwise phase is made of: parts disabled one at a time (results are wrong, timings are what matters)
+    for bits, what in ((1, "no saved-state stores"), (2, "no transcendentals"), (4, "no cp.async prefetch"), (7, "none of the three")):
+        os.environ["RADMMM_B200_LSTM_PROBE"] = str(bits)
+        tf, tb = timeit(lambda: fwd(N.MODE_BF16)), timeit(lambda: bwd(N.MODE_BF16))
+        print(f"probe {bits} ({what:24s}): forward {tf / T:5.2f} us/step   backward {tb / T:5.2f} us/step")
+    os.environ["RADMMM_B200_LSTM_PROBE"] = "0"
 
 
 if __name__ == "__main__":
