@@ -278,6 +278,11 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) RADMMM_TRACE(1);
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) touches no memory
+    // the previous kernel of the stream produces, so with the launch attribute set it overlaps that kernel's tail; from here on
+    // this grid reads its operands.  Without the attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // Tile walk.  A "walk" position is one 128 x BN tile (CL == 1) or one 256 x BN pair tile (CL == 2, CTA `crank` takes
     // row tile 2*pm + crank).  Weight-grad: the (tap, split-K range) pair is the slowest index.
@@ -581,22 +586,33 @@ static int launch_inst(const TcParams& P, int n_tiles_total, cudaStream_t st) {
         }
         configured = true;
     }
+    // RADMMM_B200_PDL=1: programmatic stream serialization (see the kernel) for every contraction launch
+    static const bool pdl = []() { const char* e = getenv("RADMMM_B200_PDL"); return e && e[0] == '1'; }();
+    int grid;
     if (CL == 1) {
-        int grid = n_tiles_total < sm_count() ? n_tiles_total : sm_count();
+        grid = n_tiles_total < sm_count() ? n_tiles_total : sm_count();
         if (grid < 1) grid = 1;
-        kern<<<grid, kThreads, C::smem_bytes, st>>>(P);
-        RADMMM_LAUNCH_CHECK();
-        return RADMMM_OK;
+    } else {
+        int clusters = n_tiles_total / CL;
+        if (clusters > max_clusters) clusters = max_clusters;
+        if (clusters < 1) clusters = 1;
+        grid = clusters * CL;
     }
-    int clusters = n_tiles_total / CL;
-    if (clusters > max_clusters) clusters = max_clusters;
-    if (clusters < 1) clusters = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::smem_bytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (CL > 1) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = CL; attr[n_attr].val.clusterDim.y = 1; attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
+    }
+    if (pdl) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n_attr;
     RADMMM_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     count_launch();
     return RADMMM_OK;
@@ -662,15 +678,23 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     const int n_pad = (int)round_up(N, 128);
     int BN = (!x3 && n_pad % 256 == 0) ? 256 : 128;
     if (args.wgrad && BN == 256 && args.split_k < 1) {
-        // weight-grad tiling: if 128-wide tiles alone fill the machine ~1.5 times over (the 5-tap dilated conv: 160 pair
-        // tiles for 74 pair slots) take them and skip split-K -- plain stores, no zero-fill, no fp32 atomics; 256-wide
-        // tiles leave 80 pair tiles = two rounds for 6 pairs
+        // Weight-grad tiling.  128-wide tiles (160 pair tiles for the 5-tap dilated conv: plain stores, no split-K) looked
+        // attractive for their tile count, but a 256 x 128 pair tile streams 24 KB of MN-major operands per 64-row K block
+        // for 256 tensor cycles -- 96 B/clk per SM, ~14 KB/clk over the chip, more than twice what L2 delivers: measured
+        // 0.46 us per K block instead of 0.13 (profiles/r2_gemm_timeline.md).  256-wide tiles stream 32 KB per 512 cycles,
+        // the same 64 B/clk per SM as the forward convolutions, which run at the tensor peak; their 80 pair tiles are split
+        // in two along K below (160 work items for 74 pair slots, fp32 red.add into the zeroed output).
+        // RADMMM_B200_WGRAD_BN128=1 restores the old choice (A/B measurements).
+        static const bool bn128 = []() { const char* e = getenv("RADMMM_B200_WGRAD_BN128"); return e && e[0] == '1'; }();
         const int taps = args.wgrad == 2 ? 1 : args.n_seg;
         const long long slots = sm_count();
         const long long t256 = (long long)cdiv(args.epi.M, BM) * (n_pad / 256) * taps;
         const long long t128 = (long long)cdiv(args.epi.M, BM) * (n_pad / 128) * taps;
-        if (2 * t256 < 3 * slots && 2 * t128 >= 3 * slots) BN = 128;
+        if (bn128 && 2 * t256 < 3 * slots && 2 * t128 >= 3 * slots) BN = 128;
     }
+    // narrow outputs (the `end` conv: N = C <= 160 -> one 256-wide tile per 128 rows, 26 CTAs at B=8): 128-wide tiles double
+    // the CTA count and halve each CTA's main loop
+    if (!args.wgrad && BN == 256 && (long long)(args.R / BM) * (n_pad / 256) * 2 <= sm_count()) BN = 128;
     P.n_tiles = n_pad / BN;
     int n_tiles_total;
 

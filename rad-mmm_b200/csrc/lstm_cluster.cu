@@ -134,6 +134,7 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) {
     const float t = __expf(-2.0f * fabsf(x));
@@ -155,7 +156,7 @@ __device__ __forceinline__ float whh_at(const float* __restrict__ Whh, int H, in
 
 // =========================================================================================================== forward
 // shared memory: [2 mbarriers | lens[32] | hs[2][NB][544][8] bf16 | part[2][144][8 NB] fp32 | hstage[NB][34][8] bf16 |
-//                 (x2) | cst[33 * 8 NB] fp32 | xps[2][4][33 * 8 NB] fp32 | itab[33 * 8 NB] int4]
+//                 (x2) | cst[33 * 8 NB] fp32 | xps[3][4][33 * 8 NB] fp32 | itab[33 * 8 NB] int4 | stash[6][33 * 8 NB] fp32]
 template <bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -168,8 +169,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     // be complete once h_{s+1} of every peer has arrived, i.e. before step s+2 writes the same half again)
     __nv_bfloat16* hstage2 = reinterpret_cast<__nv_bfloat16*>(part + (size_t)2 * ROWS * NBN); // [2][NB][SLOT][8]
     float* cst = reinterpret_cast<float*>(hstage2 + (size_t)2 * NB * SLOT * 8);              // [NIT]
-    float* xps = cst + NIT;                                                                   // [2][4][NIT]
-    int4* itab = reinterpret_cast<int4*>(xps + (size_t)2 * 4 * NIT);                          // [NIT]
+    float* xps = cst + NIT;                                                                   // [3][4][NIT]
+    int4* itab = reinterpret_cast<int4*>(xps + (size_t)3 * 4 * NIT);                          // [NIT]
+    float* stash = reinterpret_cast<float*>(itab + NIT);                                      // [6][NIT] values saved for backward
     const int rank = (int)cluster_rank(), dir = (int)(cluster_id_x() & 1), n0 = (int)(cluster_id_x() >> 1) * 8;     // cluster = (8-sequence chunk, direction)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool mma_warp = warp < 2 * MT;      // 18 of the 20 warps
@@ -216,14 +218,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     cluster_sync_all();                       // every CTA's barriers and zeroed h tiles exist before the first push
 
     // pointwise work items: it = j * NBN + n (unit j of this CTA, sequence n), thread tid handles it = tid, tid + NT, ...
-    // the input projections of step s are fetched into xps[s & 1] with cp.async during step s - 1
+    // the input projections of step s are fetched into xps[s % 3] with cp.async TWO steps ahead (issued after the push of
+    // step s - 2, so neither their issue nor their latency sits on a step's critical path)
     auto fetch_xp = [&](int s) {
         for (int it = tid; it < NIT; it += NT) {
             const int4 e = itab[it];
             if (s < e.x) {
                 const int t = dir ? e.x - 1 - s : s;
                 const float* x = p.xproj + (size_t)e.y + (size_t)t * 8 * H;
-                float* d = xps + (size_t)(s & 1) * 4 * NIT + it;
+                float* d = xps + (size_t)(s % 3) * 4 * NIT + it;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) cp_async4(d + (size_t)g * NIT, x + (size_t)g * H);
             }
@@ -231,6 +234,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
         cp_async_commit();
     };
     fetch_xp(0);
+    fetch_xp(1);
     const uint32_t tx_bytes = (uint32_t)(CL * UPC * NB * 16);
     // diagnostic phase timers of thread 0: [0] wait for h, [1] mat-vec, [2] cp.async wait + barrier, [3] gates, [4] barrier, [5] push
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
@@ -265,10 +269,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
             }
         }
         lap(1);
-        cp_async_wait_all();                   // this thread's input projections of step s are in xps[cur]
+        cp_async_wait_but_one();               // this thread's input projections of step s are in xps[s % 3]
         __syncthreads();
         lap(2);
-        // ---- gates, cell / hidden state of this CTA's units
+        // ---- gates, cell / hidden state of this CTA's units.  What the backward pass needs (gates, c, h: six scattered global
+        // stores per item) is only parked in shared memory here and written out AFTER the push, while the exchange is in
+        // flight -- off the step's critical path; so is the prefetch of the next step's input projections.
         for (int it = tid; it < NIT; it += NT) {
             const int4 e = itab[it];
             const int j = it / NBN, n = it - j * NBN;
@@ -276,25 +282,33 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
             if (s < e.x) {
                 const float* pa = part + (size_t)(4 * j) * NBN + n;
                 const float* pb = pa + (size_t)ROWS * NBN;
-                const float* xp = xps + (size_t)cur * 4 * NIT + it;
+                const float* xp = xps + (size_t)(s % 3) * 4 * NIT + it;
                 float gi = pa[0] + pb[0] + xp[0], gf = pa[NBN] + pb[NBN] + xp[NIT];
                 float gg = pa[2 * NBN] + pb[2 * NBN] + xp[2 * NIT], go = pa[3 * NBN] + pb[3 * NBN] + xp[3 * NIT];
                 if (!(p.probe & 2)) { gi = sigmoidf_(gi); gf = sigmoidf_(gf); gg = tanhf_(gg); go = sigmoidf_(go); }
                 const float c = gf * cst[it] + gi * gg;
                 h = go * ((p.probe & 2) ? c : tanhf_(c));
                 cst[it] = c;
-                if (!(p.probe & 1)) {
-                    const int t = dir ? e.x - 1 - s : s;
-                    float* gp = p.gates + (size_t)e.y + (size_t)t * 8 * H;
-                    gp[0] = gi; gp[H] = gf; gp[2 * (size_t)H] = gg; gp[3 * (size_t)H] = go;
-                    p.cstate[(size_t)e.z + (size_t)t * 2 * H] = c;
-                    p.out[(size_t)e.w + (size_t)t * 2 * H] = h;
-                }
+                float* sp = stash + it;
+                sp[0] = gi; sp[NIT] = gf; sp[2 * NIT] = gg; sp[3 * NIT] = go; sp[4 * NIT] = c; sp[5 * NIT] = h;
             }
             hstage[((size_t)(n >> 3) * SLOT + j) * 8 + (n & 7)] = __float2bfloat16_rn(h);
         }
-        if (s + 1 == tmax) break;
-        if (!(p.probe & 4)) fetch_xp(s + 1);   // in flight across the exchange
+        auto write_saved = [&]() {             // each thread writes what it parked itself: no barrier needed
+            if (p.probe & 1) return;
+            for (int it = tid; it < NIT; it += NT) {
+                const int4 e = itab[it];
+                if (s < e.x) {
+                    const int t = dir ? e.x - 1 - s : s;
+                    const float* sp = stash + it;
+                    float* gp = p.gates + (size_t)e.y + (size_t)t * 8 * H;
+                    gp[0] = sp[0]; gp[H] = sp[NIT]; gp[2 * (size_t)H] = sp[2 * NIT]; gp[3 * (size_t)H] = sp[3 * NIT];
+                    p.cstate[(size_t)e.z + (size_t)t * 2 * H] = sp[4 * NIT];
+                    p.out[(size_t)e.w + (size_t)t * 2 * H] = sp[5 * NIT];
+                }
+            }
+        };
+        if (s + 1 == tmax) { write_saved(); break; }
         lap(3);
         if (p.bulk) fence_proxy_async();       // hstage was written through the generic proxy, the copy engine reads it
         __syncthreads();
@@ -315,6 +329,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
                 st_async_v4(mapa(dst, peer), mapa(smem_u32(&bars[cur]), peer), v);
             }
         }
+        write_saved();
+        if (!(p.probe & 4)) fetch_xp(s + 2);   // issued while this CTA waits for the other 15 slices, needed two steps from now
+        else cp_async_commit();
     }
     cp_async_wait_all();
     cluster_sync_all();                       // no CTA leaves while a peer could still push into its shared memory
@@ -329,7 +346,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
 // k-tiles: warp w < 17 holds m-tiles 2w and 2w+1 with the full K), and pushes each 16-unit x 8-sequence fp32 tile to the
 // owner of those units; the owner adds the 16 partial slices.
 // shared memory: [2 mbarriers | lens[32] | recv[2][CL][NB][SLOT][8] fp32 | dgs[NB][144][8] bf16 | dcn[33 * 8 NB] fp32 |
-//                 sv[2][7][33 * 8 NB] fp32 | itab[33 * 8 NB] int4 | pstage[2][NB][544][8] fp32 (bulk exchange only)]
+//                 sv[3][7][33 * 8 NB] fp32 | itab[33 * 8 NB] int4 | stash[4][33 * 8 NB] fp32 |
+//                 pstage[2][NB][544][8] fp32 (bulk exchange only)]
 template <bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -339,9 +357,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     float* recv = reinterpret_cast<float*>(smem + 256);                                      // [2][CL][NB][SLOT][8]
     __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(recv + (size_t)2 * CL * NB * SLOT * 8);   // [NB][ROWS][8]
     float* dcn = reinterpret_cast<float*>(dgs + (size_t)NB * ROWS * 8);                      // [NIT]
-    float* sv = dcn + NIT;                                                                    // [2][7][NIT]
-    int4* itab = reinterpret_cast<int4*>(sv + (size_t)2 * 7 * NIT);                           // [NIT]
-    float* pstage2 = reinterpret_cast<float*>(itab + NIT);                                    // [2][NB][KP][8]
+    float* sv = dcn + NIT;                                                                    // [3][7][NIT]
+    int4* itab = reinterpret_cast<int4*>(sv + (size_t)3 * 7 * NIT);                           // [NIT]
+    float* stash = reinterpret_cast<float*>(itab + NIT);                                      // [4][NIT] gate gradients for dgates
+    float* pstage2 = stash + (size_t)4 * NIT;                                                 // [2][NB][KP][8]
     const int rank = (int)cluster_rank(), dir = (int)(cluster_id_x() & 1), n0 = (int)(cluster_id_x() >> 1) * 8;     // cluster = (8-sequence chunk, direction)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* Whh = p.whh[dir];
@@ -387,7 +406,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     __syncthreads();
     cluster_sync_all();
 
-    // saved forward values of (unit, sequence) for time step s: gates i f g o, c, c_prev, dout -> sv[s & 1], one step ahead
+    // saved forward values of (unit, sequence) for time step s: gates i f g o, c, c_prev, dout -> sv[s % 3], two steps ahead
     auto load_saved = [&](int s) {
         for (int it = tid; it < NIT; it += NT) {
             const int4 e = itab[it];
@@ -395,7 +414,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                 const int t = dir ? e.x - 1 - s : s;
                 const float* gp = p.gates + (size_t)e.y + (size_t)t * 8 * H;
                 const float* cp = p.cstate + (size_t)e.z + (size_t)t * 2 * H;
-                float* d = sv + (size_t)(s & 1) * 7 * NIT + it;
+                float* d = sv + (size_t)(s % 3) * 7 * NIT + it;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) cp_async4(d + (size_t)g * NIT, gp + (size_t)g * H);
                 cp_async4(d + (size_t)4 * NIT, cp);
@@ -406,6 +425,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
         cp_async_commit();
     };
     load_saved(tmax - 1);
+    load_saved(tmax - 2);
     const uint32_t tx_bytes = (uint32_t)(CL * NB * SLOT * 8 * 4);          // 16 sources x (34 slots x 8 sequences) fp32 per tile
     // diagnostic phase timers of thread 0: [0] wait for dh, [1] cp.async wait, [2] gate gradients, [3] barrier, [4] mat-vec + push
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
@@ -416,7 +436,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
         lap(4);
         if (step > 0) mbar_wait(&bars[prev], ((step - 1) >> 1) & 1);      // the 16 partial slices of dh_rec have landed
         lap(0);
-        cp_async_wait_all();
+        cp_async_wait_but_one();
         lap(1);
         // ---- gate gradients of this CTA's units
         for (int it = tid; it < NIT; it += NT) {
@@ -424,7 +444,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
             const int j = it / NBN, n = it - j * NBN;
             float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, dc_keep = 0.0f;
             if (s < e.x) {
-                const float* v = sv + (size_t)(s & 1) * 7 * NIT + it;
+                const float* v = sv + (size_t)(s % 3) * 7 * NIT + it;
                 float dh = v[6 * NIT];
                 if (step > 0) {
                     const float* rc = recv + (((size_t)prev * CL * NB + (n >> 3)) * SLOT + j) * 8 + (n & 7);
@@ -440,19 +460,27 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                 d_g = dc * gi * (1.0f - gg * gg);
                 d_f = dc * c_prev * gf * (1.0f - gf);
                 dc_keep = dc * gf;
-                if (!(p.probe & 1)) {
-                    const int t = dir ? e.x - 1 - s : s;
-                    float* dg = p.dgates + (size_t)e.y + (size_t)t * 8 * H;
-                    dg[0] = d_i; dg[H] = d_f; dg[2 * (size_t)H] = d_g; dg[3 * (size_t)H] = d_o;
-                }
+                float* sp = stash + it;        // written to dgates after the exchange has been started (see write_saved)
+                sp[0] = d_i; sp[NIT] = d_f; sp[2 * NIT] = d_g; sp[3 * NIT] = d_o;
             }
             dcn[it] = dc_keep;
             __nv_bfloat16* o = dgs + ((size_t)(n >> 3) * ROWS + 4 * j) * 8 + (n & 7);
             o[0] = __float2bfloat16_rn(d_i); o[8] = __float2bfloat16_rn(d_f);
             o[16] = __float2bfloat16_rn(d_g); o[24] = __float2bfloat16_rn(d_o);
         }
-        if (s == 0) break;
-        if (!(p.probe & 4)) load_saved(s - 1); // in flight across the mat-vec and the exchange
+        auto write_saved = [&]() {             // each thread writes what it parked itself: no barrier needed
+            if (p.probe & 1) return;
+            for (int it = tid; it < NIT; it += NT) {
+                const int4 e = itab[it];
+                if (s < e.x) {
+                    const int t = dir ? e.x - 1 - s : s;
+                    const float* sp = stash + it;
+                    float* dg = p.dgates + (size_t)e.y + (size_t)t * 8 * H;
+                    dg[0] = sp[0]; dg[H] = sp[NIT]; dg[2 * (size_t)H] = sp[2 * NIT]; dg[3 * (size_t)H] = sp[3 * NIT];
+                }
+            }
+        };
+        if (s == 0) { write_saved(); break; }
         lap(2);
         __syncthreads();
         lap(3);
@@ -516,6 +544,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                 bulk_copy_to_peer(mapa(dst, owner), src, SLOT * 32, mapa(smem_u32(&bars[cur]), owner));
             }
         }
+        write_saved();
+        if (!(p.probe & 4)) load_saved(s - 2); // issued while this CTA waits for the other partial sums, needed two steps from now
+        else cp_async_commit();
     }
     cp_async_wait_all();
     cluster_sync_all();
@@ -534,11 +565,11 @@ bool lstm_cluster_supported(int B, int H) { return H >= 1 && H <= HMAX && B >= 1
 
 static size_t fwd_smem(int NB) {
     const size_t nit = (size_t)UPC * 8 * NB;
-    return 256 + (size_t)2 * NB * KP * 16 + (size_t)2 * ROWS * 8 * NB * 4 + (size_t)2 * NB * SLOT * 16 + nit * 4 + 2 * 4 * nit * 4 + nit * 16;
+    return 256 + (size_t)2 * NB * KP * 16 + (size_t)2 * ROWS * 8 * NB * 4 + (size_t)2 * NB * SLOT * 16 + nit * 4 + 3 * 4 * nit * 4 + nit * 16 + 6 * nit * 4;
 }
 static size_t bwd_smem(int NB) {
     const size_t nit = (size_t)UPC * 8 * NB;
-    return 256 + (size_t)2 * CL * NB * SLOT * 8 * 4 + (size_t)NB * ROWS * 16 + nit * 4 + 2 * 7 * nit * 4 + nit * 16 +
+    return 256 + (size_t)2 * CL * NB * SLOT * 8 * 4 + (size_t)NB * ROWS * 16 + nit * 4 + 3 * 7 * nit * 4 + nit * 16 + 4 * nit * 4 +
            (size_t)2 * NB * KP * 8 * 4;
 }
 

@@ -497,15 +497,16 @@ def test_fused_radam_inside_the_graphed_step():
     opt_e.load_state_dict(opt_g.state_dict())
     opt_g.sync_step_counts()
     opt_e.load_state_dict(opt_g.state_dict())
-    losses_g, losses_e = [], []
+    losses_g, losses_e, dbg = [], [], []
     for _ in range(3):
         losses_g.append(float(step(bt)))
         le, _ = _eager_grads(eager, bt, T)
         opt_e.step()
         losses_e.append(float(le))
+        dbg.append((opt_g._tables[0]["dstate"][1:6].tolist(), opt_e._tables[0]["dstate"][1:6].tolist()))
     torch.cuda.synchronize()
     for a, b in zip(losses_e, losses_g):
-        assert abs(a - b) <= 2e-5 * abs(a) + 1e-6, (losses_e, losses_g)
+        assert abs(a - b) <= 2e-5 * abs(a) + 1e-6, (losses_e, losses_g, dbg)
     assert losses_e[0] != losses_e[2]
     for (n, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
         close(q.detach(), p.detach(), 2e-5 * max(1.0, p.detach().abs().max().item()), what="parameter after 3 steps " + n)
