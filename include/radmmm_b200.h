@@ -215,6 +215,16 @@ int radmmm_spline_backward(const float* z1, const float* q, const int32_t* lens,
                            const float* dlog_s, float* dz1, float* dq, int B, int Ch, int Tp, int n_bins, float lo,
                            float hi, void* stream);
 
+/* Piecewise-linear spline coupling (splines.py:57-142 forward, 145-238 inverse; the use_quadratic=False branch of
+ * SplineTransformationLayer, common.py:1019-1020,1069-1075).  q (B, Ch*n_bins, Tp): n_bins un-normalised bin heights per
+ * (channel, frame), n_bins in {8, 16, 32}; z1 is normalised with (z1 - lo) / (hi - lo) and de-normalised on the way out;
+ * elements outside [lo, hi] pass through.  log_s (B,1,Tp) (may be NULL): sum over channels of log slope (inverse: minus). */
+int radmmm_spline_linear_forward(const float* z1, const float* q, const int32_t* lens, float* z1_out, float* log_s, int B,
+                                 int Ch, int Tp, int n_bins, float lo, float hi, int inverse, void* stream);
+int radmmm_spline_linear_backward(const float* z1, const float* q, const int32_t* lens, const float* dz1_out,
+                                  const float* dlog_s, float* dz1, float* dq, int B, int Ch, int Tp, int n_bins, float lo,
+                                  float hi, void* stream);
+
 /* STFT + mel filterbank + log (audio_processing.py:137-154, 227-255): audio (B,S) in [-1,1] -> mel (B,n_mel,S/hop+1).
  * mel_basis (n_mel, n_fft/2+1) fp32 as registered by TacotronSTFT.__init__ (audio_processing.py:124-127). */
 int radmmm_stft_mel(const float* audio, const float* mel_basis, float* mel, float* magnitude_or_null, int B, int S,

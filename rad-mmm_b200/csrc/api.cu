@@ -255,6 +255,15 @@ int radmmm_spline_backward(const float* z1, const float* q, const int32_t* lens,
                            float hi, void* stream) {
     return spline_bwd(z1, q, lens, dz1_out, dlog_s, dz1, dq, B, Ch, Tp, n_bins, lo, hi, ST(stream));
 }
+int radmmm_spline_linear_forward(const float* z1, const float* q, const int32_t* lens, float* z1_out, float* log_s, int B,
+                                 int Ch, int Tp, int n_bins, float lo, float hi, int inverse, void* stream) {
+    return spline_linear(z1, q, lens, z1_out, log_s, B, Ch, Tp, n_bins, lo, hi, inverse, ST(stream));
+}
+int radmmm_spline_linear_backward(const float* z1, const float* q, const int32_t* lens, const float* dz1_out,
+                                  const float* dlog_s, float* dz1, float* dq, int B, int Ch, int Tp, int n_bins, float lo,
+                                  float hi, void* stream) {
+    return spline_linear_bwd(z1, q, lens, dz1_out, dlog_s, dz1, dq, B, Ch, Tp, n_bins, lo, hi, ST(stream));
+}
 int radmmm_stft_mel(const float* audio, const float* mel_basis, float* mel, float* magnitude_or_null, int B, int S,
                     int n_fft, int hop, int n_mel, float clip, void* stream) {
     return stft_mel(audio, mel_basis, mel, magnitude_or_null, B, S, n_fft, hop, n_mel, clip, ST(stream));

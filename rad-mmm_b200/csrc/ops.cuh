@@ -49,6 +49,10 @@ int spline_fwd(const float* z1, const float* q, const int* lens, float* z1_out, 
                int n_bins, float lo, float hi, int inverse, cudaStream_t st);
 int spline_bwd(const float* z1, const float* q, const int* lens, const float* dz1_out, const float* dlog_s, float* dz1,
                float* dq, int B, int Ch, int Tp, int n_bins, float lo, float hi, cudaStream_t st);
+int spline_linear(const float* z1, const float* q, const int* lens, float* z1_out, float* log_s, int B, int Ch, int Tp, int n_bins,
+                  float lo, float hi, int inverse, cudaStream_t st);
+int spline_linear_bwd(const float* z1, const float* q, const int* lens, const float* dz1_out, const float* dlog_s, float* dz1, float* dq,
+                      int B, int Ch, int Tp, int n_bins, float lo, float hi, cudaStream_t st);
 int stft_mel(const float* audio, const float* mel_basis, float* mel, float* mag, int B, int S, int n_fft, int hop,
              int n_mel, float clip, cudaStream_t st);
 int soft_attention(const float* q, const float* k, const float* prior, const int* in_lens, float* attn,

@@ -196,7 +196,160 @@ __global__ void __launch_bounds__(128) spline_bwd_kernel(const float* __restrict
     for (int k = 0; k <= K; ++k) dqp[(long long)(K + k) * Tp] = dv[k] - ((k == s.vmax_idx) ? dmax : 0.0f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Piecewise-LINEAR transform (splines.py:57-142 forward, 145-238 inverse; SplineTransformationLayer(use_quadratic=False),
+// common.py:1019-1020,1069-1075).  NBL un-normalised bin heights per element; q = NBL * softmax(q~) are the slopes.
+// forward:  y = (x - m/NBL) q_m + sum_{k<m} q_k / NBL,  m = clamp(floor(NBL x)),  log J = log q_m
+// inverse:  m = last bin whose left integral is <= y,  x = (y - left_m) / q_m + m / NBL
+// Elements outside [0, 1] pass through (slope 1).  One thread per element, parameters in registers, lanes along time.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NBL>
+__device__ __forceinline__ void linear_setup(const float* __restrict__ q, long long stride, float* p) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NBL; ++k) { p[k] = q[k * stride]; m = fmaxf(m, p[k]); }
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NBL; ++k) { p[k] = expf(p[k] - m); sum += p[k]; }
+#pragma unroll
+    for (int k = 0; k < NBL; ++k) p[k] = p[k] / sum;            // softmax; slope q_k = NBL * p_k
+}
+
+// grid (ceil(Tp/32), B), block (32, 8)
+template <int NBL>
+__global__ void __launch_bounds__(256) spline_linear_kernel(const float* __restrict__ z1, const float* __restrict__ q,
+                                                            float* __restrict__ z1_out, float* __restrict__ log_s, int Ch,
+                                                            int Tp, float lo, float hi, int inverse) {
+    __shared__ float red[8][33];
+    const int t = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
+    const float range = hi - lo, w = 1.0f / NBL;
+    float lj_sum = 0.0f;
+    if (t < Tp) {
+        for (int c = threadIdx.y; c < Ch; c += 8) {
+            const long long zi = ((long long)b * Ch + c) * Tp + t;
+            const float x = (z1[zi] - lo) / range;
+            float y = x, slope = 1.0f;
+            if (x >= 0.0f && x <= 1.0f) {
+                float p[NBL];
+                linear_setup<NBL>(q + ((long long)b * Ch + c) * NBL * Tp + t, Tp, p);
+                if (!inverse) {
+                    const int m = min(max((int)floorf(NBL * x), 0), NBL - 1);
+                    float left = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < NBL; ++k) left += (k < m) ? p[k] : 0.0f;       // sum_{k<m} q_k w = sum p_k
+                    slope = NBL * pick(p, NBL, m);
+                    y = (x - m * w) * slope + left;
+                } else {
+                    // argmin over bins of (y - left_k) among the non-negative ones = the last bin with left_k <= y
+                    float left = 0.0f, left_m = 0.0f;
+                    int m = 0;
+#pragma unroll
+                    for (int k = 0; k < NBL; ++k) {
+                        if (x - left >= 0.0f) { m = k; left_m = left; }
+                        left += p[k];
+                    }
+                    slope = NBL * pick(p, NBL, m);
+                    y = (x - left_m) / slope + m * w;
+                }
+                y = fminf(fmaxf(y, EPS), 1.0f - EPS);
+            }
+            z1_out[zi] = y * range + lo;
+            lj_sum += logf(slope);
+        }
+    }
+    if (log_s == nullptr) return;
+    red[threadIdx.y][threadIdx.x] = lj_sum;
+    __syncthreads();
+    if (threadIdx.y == 0 && t < Tp) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+        log_s[(long long)b * Tp + t] = inverse ? -tot : tot;
+    }
+}
+
+// backward of the forward linear transform: grid (ceil(Tp/128), Ch, B)
+template <int NBL>
+__global__ void __launch_bounds__(128) spline_linear_bwd_kernel(const float* __restrict__ z1, const float* __restrict__ q,
+                                                                const int* __restrict__ lens, const float* __restrict__ dz1_out,
+                                                                const float* __restrict__ dlog_s, float* __restrict__ dz1,
+                                                                float* __restrict__ dq, int Ch, int Tp, float lo, float hi) {
+    const int t = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
+    if (t >= Tp) return;
+    const float range = hi - lo, w = 1.0f / NBL;
+    const long long zi = ((long long)b * Ch + c) * Tp + t;
+    float* dqp = dq + ((long long)b * Ch + c) * NBL * Tp + t;
+    const bool valid = t < lens[b];
+    const float gz = valid ? dz1_out[zi] : 0.0f;
+    const float gj = (valid && dlog_s) ? dlog_s[(long long)b * Tp + t] : 0.0f;
+    const float x = (z1[zi] - lo) / range;
+    if (!(x >= 0.0f && x <= 1.0f) || !valid) {
+        dz1[zi] = gz;
+#pragma unroll 1
+        for (int k = 0; k < NBL; ++k) dqp[(long long)k * Tp] = 0.0f;
+        return;
+    }
+    float p[NBL];
+    linear_setup<NBL>(q + ((long long)b * Ch + c) * NBL * Tp + t, Tp, p);
+    const int m = min(max((int)floorf(NBL * x), 0), NBL - 1);
+    float left = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NBL; ++k) left += (k < m) ? p[k] : 0.0f;
+    const float pm = pick(p, NBL, m), slope = NBL * pm, alpha = x - m * w;
+    const float y = alpha * slope + left;
+    const float gy = (y >= EPS && y <= 1.0f - EPS) ? gz * range : 0.0f;         // the clamp passes gradient only inside
+    dz1[zi] = gy * slope / range;
+    // dL/dp_k: y = NBL alpha p_m + sum_{k<m} p_k ; log J = log(NBL p_m)
+    float dp[NBL], dot = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NBL; ++k) {
+        dp[k] = (k < m) ? gy : ((k == m) ? gy * NBL * alpha + gj / pm : 0.0f);
+        dot += dp[k] * p[k];
+    }
+#pragma unroll
+    for (int k = 0; k < NBL; ++k) dqp[(long long)k * Tp] = p[k] * (dp[k] - dot);     // softmax Jacobian
+}
+
 }  // namespace
+
+template <int NBL>
+static void launch_linear(const float* z1, const float* q, float* z1_out, float* log_s, int B, int Ch, int Tp, float lo, float hi,
+                          int inverse, cudaStream_t st) {
+    dim3 grid(cdiv(Tp, 32), B), block(32, 8);
+    spline_linear_kernel<NBL><<<grid, block, 0, st>>>(z1, q, z1_out, log_s, Ch, Tp, lo, hi, inverse);
+}
+template <int NBL>
+static void launch_linear_bwd(const float* z1, const float* q, const int* lens, const float* dz1_out, const float* dlog_s, float* dz1,
+                              float* dq, int B, int Ch, int Tp, float lo, float hi, cudaStream_t st) {
+    dim3 grid(cdiv(Tp, 128), Ch, B);
+    spline_linear_bwd_kernel<NBL><<<grid, 128, 0, st>>>(z1, q, lens, dz1_out, dlog_s, dz1, dq, Ch, Tp, lo, hi);
+}
+
+int spline_linear(const float* z1, const float* q, const int* lens, float* z1_out, float* log_s, int B, int Ch, int Tp, int n_bins,
+                  float lo, float hi, int inverse, cudaStream_t st) {
+    (void)lens;
+    RADMMM_REQUIRE(hi > lo, "spline_linear: bad bounds");
+    switch (n_bins) {
+        case 8: launch_linear<8>(z1, q, z1_out, log_s, B, Ch, Tp, lo, hi, inverse, st); break;
+        case 16: launch_linear<16>(z1, q, z1_out, log_s, B, Ch, Tp, lo, hi, inverse, st); break;
+        case 32: launch_linear<32>(z1, q, z1_out, log_s, B, Ch, Tp, lo, hi, inverse, st); break;
+        default: RADMMM_REQUIRE(false, "spline_linear: n_bins=%d (8, 16 or 32)", n_bins);
+    }
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
+
+int spline_linear_bwd(const float* z1, const float* q, const int* lens, const float* dz1_out, const float* dlog_s, float* dz1, float* dq,
+                      int B, int Ch, int Tp, int n_bins, float lo, float hi, cudaStream_t st) {
+    switch (n_bins) {
+        case 8: launch_linear_bwd<8>(z1, q, lens, dz1_out, dlog_s, dz1, dq, B, Ch, Tp, lo, hi, st); break;
+        case 16: launch_linear_bwd<16>(z1, q, lens, dz1_out, dlog_s, dz1, dq, B, Ch, Tp, lo, hi, st); break;
+        case 32: launch_linear_bwd<32>(z1, q, lens, dz1_out, dlog_s, dz1, dq, B, Ch, Tp, lo, hi, st); break;
+        default: RADMMM_REQUIRE(false, "spline_linear_bwd: n_bins=%d (8, 16 or 32)", n_bins);
+    }
+    RADMMM_LAUNCH_CHECK();
+    return RADMMM_OK;
+}
 
 int spline_fwd(const float* z1, const float* q, const int* lens, float* z1_out, float* log_s, int B, int Ch, int Tp,
                int n_bins, float lo, float hi, int inverse, cudaStream_t st) {

@@ -255,23 +255,55 @@ class _QuadraticSpline(torch.autograd.Function):
         return dz, dq, None, None, None, None
 
 
+class _LinearSpline(torch.autograd.Function):
+    """z1 (B, Ch, T), q (B, Ch*n_bins, T) -> (z1', log_s (B,1,T));  splines.py:57-142 with bounds [lo, hi]."""
+
+    @staticmethod
+    def forward(ctx, z1, q, lens, lo: float, hi: float, n_bins: int):
+        lib = N.lib()
+        z1, q = z1.contiguous().float(), q.contiguous().float()
+        b, ch, t = z1.shape
+        out = torch.empty_like(z1)
+        log_s = torch.empty(b, 1, t, device=z1.device)
+        N.check(lib.radmmm_spline_linear_forward(N.fptr(z1), N.fptr(q), N.ptr(lens), N.fptr(out), N.fptr(log_s), b, ch, t, n_bins,
+                                                 lo, hi, 0, N.stream()))
+        ctx.save_for_backward(z1, q, lens)
+        ctx.cfg = (lo, hi, n_bins)
+        return out, log_s
+
+    @staticmethod
+    def backward(ctx, dz_out, dlog_s):
+        lib = N.lib()
+        z1, q, lens = ctx.saved_tensors
+        lo, hi, n_bins = ctx.cfg
+        b, ch, t = z1.shape
+        dz_out = dz_out.contiguous() if dz_out is not None else torch.zeros_like(z1)
+        dls = dlog_s.contiguous() if dlog_s is not None else None
+        dz, dq = torch.empty_like(z1), torch.empty_like(q)
+        N.check(lib.radmmm_spline_linear_backward(N.fptr(z1), N.fptr(q), N.ptr(lens), N.fptr(dz_out), N.fptr(dls), N.fptr(dz),
+                                                  N.fptr(dq), b, ch, t, n_bins, lo, hi, N.stream()))
+        return dz, dq, None, None, None, None
+
+
 class SplineTransformationLayer(nn.Module):
-    """common.py:1006-1090 for ``use_quadratic=True`` (what FlowStep builds, decoders.py:51-61)."""
+    """common.py:1006-1090: piecewise-quadratic (``use_quadratic=True``, what FlowStep builds, decoders.py:51-61) or
+    piecewise-linear (``use_quadratic=False``, the class default) spline coupling on a FiLM parameter network."""
 
     def __init__(self, n_mel_channels, n_context_dim, n_layers, with_dilation=True, kernel_size=5, scaling_fn="exp",
                  affine_activation="softplus", n_bins=8, left=-4, right=4, bottom=-4, top=4, use_quadratic=False,
                  use_bn=True):
         super().__init__()
-        if not use_quadratic:
-            raise NotImplementedError("radmmm_b200 builds the piecewise-quadratic spline step (use_quadratic=True), the only "
-                                      "one RADMMMFlow instantiates")
+        if not use_quadratic and n_bins not in (8, 16, 32):
+            raise NotImplementedError("piecewise-linear spline: n_bins must be 8, 16 or 32")
+        if use_quadratic and n_bins != 32:
+            raise NotImplementedError("piecewise-quadratic spline: n_bins must be 32 (decoders.py:56)")
         if (left, right) != (bottom, top):
             raise NotImplementedError("equal input / output bounds only (as in decoders.py:52-55)")
         self.n_mel_channels = n_mel_channels
         self.half_mel_channels = int(n_mel_channels / 2)
         self.left, self.right, self.bottom, self.top = left, right, bottom, top
         self.use_quadratic = use_quadratic
-        self.n_bins = 2 * n_bins + 1
+        self.n_bins = 2 * n_bins + 1 if use_quadratic else n_bins
         self.param_predictor = FiLMStack(self.half_mel_channels, n_context_dim, 512, self.half_mel_channels * self.n_bins,
                                          n_layers, use_dilation=with_dilation, kernel_size=kernel_size, use_bn=use_bn)
         self.precision = _DEFAULT_PRECISION
@@ -295,9 +327,16 @@ class SplineTransformationLayer(nn.Module):
             with torch.no_grad():
                 z1c, qc = z1.contiguous().float(), q.contiguous()
                 out = torch.empty_like(z1c)
-                N.check(lib.radmmm_spline_forward(N.fptr(z1c), N.fptr(qc), N.ptr(lens), N.fptr(out), None, b, n_half, t,
-                                                  (self.n_bins - 1) // 2, lo, hi, 1, N.stream()))
+                if self.use_quadratic:
+                    N.check(lib.radmmm_spline_forward(N.fptr(z1c), N.fptr(qc), N.ptr(lens), N.fptr(out), None, b, n_half, t,
+                                                      (self.n_bins - 1) // 2, lo, hi, 1, N.stream()))
+                else:
+                    N.check(lib.radmmm_spline_linear_forward(N.fptr(z1c), N.fptr(qc), N.ptr(lens), N.fptr(out), None, b, n_half, t,
+                                                             self.n_bins, lo, hi, 1, N.stream()))
             return torch.cat((z0, out), dim=1)
-        z1o, log_s = _QuadraticSpline.apply(z1, q, lens, lo, hi, (self.n_bins - 1) // 2)
+        if self.use_quadratic:
+            z1o, log_s = _QuadraticSpline.apply(z1, q, lens, lo, hi, (self.n_bins - 1) // 2)
+        else:
+            z1o, log_s = _LinearSpline.apply(z1, q, lens, lo, hi, self.n_bins)
         log_s = log_s + n_half * (np.log(self.top - self.bottom) - np.log(self.right - self.left))
         return torch.cat((z0, z1o), dim=1), log_s

@@ -229,6 +229,81 @@ def test_spline_kernels():
 
 
 # ------------------------------------------------------------------------------------------------ front end
+def test_linear_spline_kernels():
+    """Piecewise-linear transform (splines.py:57-238): forward / inverse against the REFERENCE fixtures (ops.npz: spl_yl,
+    spl_ljl, spl_xli, spl_ljli were produced by the unmodified splines.py), gradients against oracle autograd, pass-through of
+    elements outside [lo, hi], 8- and 32-bin variants."""
+    lib = N.lib()
+    gd = gold("ops.npz")
+    # the fixture's layout: x (50, 7) in [0, 1], q~ (50, 7, 32)  ->  kernel layout (B=1, Ch=7, T=50), q (1, 7*32, 50)
+    x = syn.hash_uniform("spl.x", (50, 7), -0.2, 1.2).clamp(0, 1)
+    wt = syn.hash_uniform("spl.w", (50, 7, 32), -2, 2)
+    z1 = x.t().reshape(1, 7, 50).contiguous().to(DEV)
+    q = wt.permute(1, 2, 0).reshape(1, 7 * 32, 50).contiguous().to(DEV)
+    lens = torch.tensor([50], dtype=torch.int32, device=DEV)
+    out, ls = torch.empty_like(z1), torch.empty(1, 1, 50, device=DEV)
+    N.check(lib.radmmm_spline_linear_forward(N.fptr(z1), N.fptr(q), N.ptr(lens), N.fptr(out), N.fptr(ls), 1, 7, 50, 32, 0.0, 1.0, 0,
+                                             N.stream()))
+    close(out[0].t(), gd["spl_yl"], 2e-6, what="linear spline fwd vs reference")
+    close(ls[0, 0], gd["spl_ljl"], 2e-5, what="linear spline log J vs reference")
+    back, lsi = torch.empty_like(z1), torch.empty(1, 1, 50, device=DEV)
+    yl = gd["spl_yl"].t().reshape(1, 7, 50).contiguous().to(DEV)
+    N.check(lib.radmmm_spline_linear_forward(N.fptr(yl), N.fptr(q), N.ptr(lens), N.fptr(back), N.fptr(lsi), 1, 7, 50, 32, 0.0, 1.0, 1,
+                                             N.stream()))
+    close(back[0].t(), gd["spl_xli"], 2e-5, what="linear spline inverse vs reference")
+    close(lsi[0, 0], gd["spl_ljli"], 2e-4, what="linear spline inverse log J vs reference")
+    # gradients + out-of-range pass-through at other shapes / bin counts, vs oracle autograd (fp64)
+    for nb in (8, 32):
+        B, Ch, T = 2, 5, 41
+        z = syn.hash_uniform(f"spll.z{nb}", (B, Ch, T), -3.6, 3.6)
+        qq = syn.hash_uniform(f"spll.q{nb}", (B, Ch * nb, T), -2, 2)
+        ln = torch.tensor([41, 23], dtype=torch.int32)
+        zd, qd, lnd = z.to(DEV), qq.to(DEV), ln.to(DEV)
+        o, l = torch.empty_like(zd), torch.empty(B, 1, T, device=DEV)
+        N.check(lib.radmmm_spline_linear_forward(N.fptr(zd), N.fptr(qd), N.ptr(lnd), N.fptr(o), N.fptr(l), B, Ch, T, nb, -3.0, 3.0, 0,
+                                                 N.stream()))
+        zc, qc = z.double().requires_grad_(True), qq.double().requires_grad_(True)
+        y, lj = osp.linear_spline((zc.permute(0, 2, 1) + 3) / 6, qc.permute(0, 2, 1).reshape(B, T, Ch, nb))
+        y_ref, l_ref = (y * 6 - 3).permute(0, 2, 1), lj.unsqueeze(1)
+        close(o, y_ref.detach(), 2e-5, what=f"linear spline fwd ({nb} bins)")
+        close(l, l_ref.detach(), 2e-4, what=f"linear spline log J ({nb} bins)")
+        outside = (z < -3) | (z > 3)
+        assert torch.equal(o.cpu()[outside], z[outside])
+        mask = of.length_mask(ln.long(), T)[:, None].double()
+        g1, g2 = syn.hash_uniform("spll.g1", (B, Ch, T)).double(), syn.hash_uniform("spll.g2", (B, 1, T)).double()
+        ((y_ref * g1 * mask).sum() + (l_ref * g2 * mask).sum()).backward()
+        dz, dq = torch.empty_like(zd), torch.empty_like(qd)
+        g1d, g2d = g1.float().to(DEV), g2.float().to(DEV)
+        N.check(lib.radmmm_spline_linear_backward(N.fptr(zd), N.fptr(qd), N.ptr(lnd), N.fptr(g1d), N.fptr(g2d), N.fptr(dz), N.fptr(dq),
+                                                  B, Ch, T, nb, -3.0, 3.0, N.stream()))
+        close(dz, zc.grad, 2e-4 * max(1.0, zc.grad.abs().max().item()), what=f"linear spline dz ({nb} bins)")
+        close(dq, qc.grad, 2e-4 * max(1.0, qc.grad.abs().max().item()), what=f"linear spline dq ({nb} bins)")
+
+
+def test_linear_spline_layer():
+    """SplineTransformationLayer(use_quadratic=False) (the reference class default, common.py:1010-1020): forward, inverse
+    round trip and gradients flow through the FiLM parameter net."""
+    from radmmm_b200.common import SequenceLength
+    from radmmm_b200.splines import SplineTransformationLayer
+    layer = SplineTransformationLayer(8, 10, 2, n_bins=8, left=-3, right=3, bottom=-3, top=3, use_quadratic=False, use_bn=False)
+    for n, p in layer.named_parameters():
+        p.data.copy_(syn.hash_uniform("spllayer." + n, tuple(p.shape), -0.3, 0.3))
+    layer.precision = "fp32"
+    layer = layer.to(DEV)
+    lens = torch.tensor([21, 9], device=DEV)
+    z = syn.hash_uniform("spllayer.z", (2, 8, 21), -3.5, 3.5).to(DEV).requires_grad_(True)
+    ctx = syn.hash_uniform("spllayer.ctx", (2, 10, 21), -1, 1).to(DEV)
+    seq = SequenceLength(lens, 21)
+    zo, ls = layer(z, ctx, seq_lens=seq)
+    assert zo.shape == z.shape and ls.shape == (2, 1, 21) and torch.isfinite(zo).all() and torch.isfinite(ls).all()
+    with torch.no_grad():
+        zi = layer(zo, ctx, inverse=True, seq_lens=seq)
+    m = of.length_mask(lens.cpu(), 21)[:, None].double()
+    close(zi.cpu().double() * m, z.detach().cpu().double() * m, 5e-4, what="linear spline layer round trip")
+    (zo.sum() + ls.sum()).backward()
+    assert z.grad is not None and all(p.grad is not None and torch.isfinite(p.grad).all() for p in layer.parameters())
+
+
 @pytest.mark.parametrize("tag,sr", [("22k", 22050), ("16k", 16000)])
 def test_stft_mel(tag, sr):
     from radmmm_b200 import audio_processing as ap
