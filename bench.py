@@ -193,7 +193,8 @@ def cpu_baseline_sample(batch, frames, timeout_s=420.0):
 # ------------------------------------------------------------------------------------------------------- HBM-bound kernels
 def hbm_rooflines(dev, pk, batch, frames):
     """Every HBM-bound kernel of the path timed ALONE through the C ABI at the benchmark's shapes: CUDA events around one
-    launch, L2 flushed (a 512 MB memset) before every timed launch, median of 7.  achieved = algorithmic bytes / time."""
+    launch, L2 flushed (a 512 MB memset) before every timed launch and the launch queued behind a device-side spin (a
+    ~10 us kernel timed on an idle stream measures the host's launch latency instead), median of 7.  achieved = algorithmic bytes / time."""
     from radmmm_b200 import _native as N
     from radmmm_b200 import synthetic as syn
     lib = N.lib()
@@ -208,7 +209,8 @@ def hbm_rooflines(dev, pk, batch, frames):
     def timed(name, nbytes, fn, note=""):
         ts = []
         for _ in range(7):
-            flush.zero_()
+            torch.cuda._sleep(400_000)      # ~0.2 ms of device spin: the host queues the launch below while the GPU is
+            flush.zero_()                   # still busy, so the events bracket the kernel and not the host's launch path
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()

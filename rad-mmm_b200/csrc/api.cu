@@ -238,8 +238,8 @@ int radmmm_wgrad_rows(int mode, const void* dy, long long dy_ld, long long dy_pl
         s.w.ptr = const_cast<void*>(x); s.w.ld = x_ld; s.w.plane_stride = x_plane;
         s.K = R;
         s.shift = (j - taps / 2) * dilation + shift_offset;
-        RADMMM_CUDA(cudaMemset2DAsync(out + j * out_tap_stride, sizeof(float) * out_ld, 0, sizeof(float) * N, M, ST(stream)));
     }
+    a.zero_output = 1;          // the launcher zero-fills `out` itself when its tiling reduces with red.add (same as the train step)
     return launch_gemm(a, mode, ST(stream));
 }
 int radmmm_cast_rows(int mode, const float* src, long long n, void* dst, long long plane_stride, void* stream) {

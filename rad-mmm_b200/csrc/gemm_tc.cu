@@ -43,6 +43,7 @@ struct TcParams {
     int n_seg, n_a_maps, n_b_maps;
     int m_tiles, n_tiles, taps, split_k, k_blocks_total;   // weight-grad: k_blocks_total = R/64
     int acc_segs;                                          // weight-grad: all segments accumulate into one output
+    int balanced;                                          // weight-grad: K blocks of all tiles cut into equal runs per CTA (pair)
     int debug;                                             // probe bits (tools/gemm_probe.py): 1 no epilogue, 2 no MMA, 4 no TMA
     unsigned long long* trace;                             // tools/gemm_probe.py: [CTA][kTraceSlots] SM-clock / globaltimer stamps
     int trace_ctas;
@@ -304,20 +305,54 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
         kb1 = min(P.k_blocks_total, kb0 + per);
     };
     const bool all_segs = !WGRAD || P.acc_segs;     // segments accumulate into one tile (row GEMM / accumulating weight-grad)
+    // Balanced weight-grad walk (P.balanced): the job is walk_mn * taps tiles of k_blocks_total K blocks each; the K blocks of
+    // all tiles are laid end to end and cut into gridDim.x / CL equal contiguous runs, one per CTA (pair).  A run crosses
+    // tile boundaries, so a CTA works on up to ceil(run / k_blocks_total) + 1 partial tiles and every tile is reduced
+    // with red.add into a zero-filled output -- no worker idles for the quantisation tail a whole-tile walk leaves
+    // (5 taps x 32 pair tiles on 74 pairs: 3 rounds where 2.16 would do).
+    const bool balanced = WGRAD && P.balanced != 0;
+    int u_begin = 0, u_end = 0;
+    if (balanced) {
+        const long long units = (long long)walk_mn * P.taps * P.k_blocks_total;
+        u_begin = (int)(units * walk_begin / walk_step);
+        u_end = (int)(units * (walk_begin + 1) / walk_step);
+    }
+    // One "item" = one accumulator tile's worth of work for this CTA: (tile, tap, K-block range).  All three roles walk the
+    // same item sequence.
+    auto item_first = [&]() -> int { return balanced ? u_begin : walk_begin; };
+    auto item_valid = [&](int pos) -> bool { return balanced ? pos < u_end : pos < walk_end; };
+    auto item_decode = [&](int pos, int& m_blk, int& n_blk, int& tap, int& kb0, int& kb1) {
+        if (balanced) {
+            const int tile = pos / P.k_blocks_total;
+            kb0 = pos - tile * P.k_blocks_total;
+            kb1 = min(P.k_blocks_total, kb0 + (u_end - pos));
+            const int mn = tile % walk_mn;
+            tap = tile / walk_mn;
+            m_blk = (mn / P.n_tiles) * CL + (int)crank;
+            n_blk = mn % P.n_tiles;
+        } else {
+            int split;
+            decode(pos, m_blk, n_blk, tap, split);
+            kb0 = 0;
+            kb1 = 0;
+            if (WGRAD) k_range(split, kb0, kb1);
+        }
+    };
+    auto item_next = [&](int pos, int kb0, int kb1) -> int { return balanced ? pos + (kb1 - kb0) : pos + walk_step; };
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA producer
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int walk = walk_begin; walk < walk_end; walk += walk_step) {
-                int m_blk, n_blk, tap, split;
-                decode(walk, m_blk, n_blk, tap, split);
+            bool first_load = true;
+            int m_blk, n_blk, tap, ikb0 = 0, ikb1 = 0;
+            for (int pos = item_first(); item_valid(pos); pos = item_next(pos, ikb0, ikb1)) {
+                item_decode(pos, m_blk, n_blk, tap, ikb0, ikb1);
                 const int seg_begin = all_segs ? 0 : tap, seg_end = all_segs ? P.n_seg : tap + 1;
                 for (int s = seg_begin; s < seg_end; ++s) {
                     const TcSeg sg = P.seg[s];
-                    int kb0 = 0, kb1 = sg.k_blocks;
-                    if (WGRAD) k_range(split, kb0, kb1);
+                    const int kb0 = WGRAD ? ikb0 : 0, kb1 = WGRAD ? ikb1 : sg.k_blocks;
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* st = smem + stage * C::stage_bytes;
@@ -363,7 +398,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
                             if (leader) mbar_expect_tx(fb, 2 * C::stage_bytes);
                             else mbar_arrive_remote(fb, 0);
                         }
-                        if (walk == walk_begin && s == seg_begin && kb == kb0) RADMMM_TRACE(2);
+                        if (first_load) { RADMMM_TRACE(2); first_load = false; }
                         if (++stage == C::stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -376,16 +411,14 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int walk = walk_begin; walk < walk_end; walk += walk_step, ++it) {
-                int m_blk, n_blk, tap, split;
-                decode(walk, m_blk, n_blk, tap, split);
+            int m_blk, n_blk, tap, ikb0 = 0, ikb1 = 0;
+            for (int pos = item_first(); item_valid(pos); pos = item_next(pos, ikb0, ikb1), ++it) {
+                item_decode(pos, m_blk, n_blk, tap, ikb0, ikb1);
                 int total_kb = 0;
                 if (!WGRAD) {
                     for (int s = 0; s < P.n_seg; ++s) total_kb += P.seg[s].k_blocks;
                 } else {
-                    int kb0, kb1;
-                    k_range(split, kb0, kb1);
-                    total_kb = (kb1 - kb0) * (P.acc_segs ? P.n_seg : 1);
+                    total_kb = (ikb1 - ikb0) * (P.acc_segs ? P.n_seg : 1);
                 }
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -442,9 +475,9 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
         constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
         const Stager stager{stage_tiles + (warp - 4) * (32 * kStageLd), lane};
         int it = 0;
-        for (int walk = walk_begin; walk < walk_end; walk += walk_step, ++it) {
-            int m_blk, n_blk, tap, split;
-            decode(walk, m_blk, n_blk, tap, split);
+        int m_blk, n_blk, tap, ikb0 = 0, ikb1 = 0;
+        for (int pos = item_first(); item_valid(pos); pos = item_next(pos, ikb0, ikb1), ++it) {
+            item_decode(pos, m_blk, n_blk, tap, ikb0, ikb1);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int row = m_blk * BM + q * 32 + lane;
@@ -475,8 +508,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             if (warp == 4 && lane == 0) RADMMM_TRACE(5);
-            bool has_acc = true;
-            if (WGRAD) { int kb0, kb1; k_range(split, kb0, kb1); has_acc = kb1 > kb0; }
+            const bool has_acc = !WGRAD || ikb1 > ikb0;
 #pragma unroll 1
             for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
                 if (P.debug & 1) break;                           // probe: no epilogue
@@ -785,14 +817,28 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
             const int per = cdiv(P.k_blocks_total, split);
             split = cdiv(P.k_blocks_total, per);
         }
+        use_cl = (P.m_tiles % 2 == 0) && pair_mode_enabled();
+        // Whole tiles or equal K-block runs?  Whole tiles cost `rounds * K blocks per item`; the balanced walk costs
+        // `units / workers` plus roughly one more epilogue (counted as 4 K blocks).  Take the balanced walk when it wins by
+        // more than 10 % (the 5-tap dilated conv: 80 pair tiles on 74 pairs -- 78 K-block times split in two, 56 balanced).
+        // RADMMM_B200_WGRAD_BALANCED=0 keeps whole tiles (A/B measurements).
+        static const bool allow_balanced = []() { const char* e = getenv("RADMMM_B200_WGRAD_BALANCED"); return !(e && e[0] == '0'); }();
+        if (allow_balanced && args.zero_output && !P.acc_segs && args.split_k < 1) {
+            const int cl = use_cl ? 2 : 1;
+            const long long workers = sm_count() / cl;
+            const long long items = (long long)(tiles0 / cl) * split;
+            const long long whole = cdiv(items, workers) * cdiv(P.k_blocks_total, split);
+            const long long even = cdiv((long long)(tiles0 / cl) * P.k_blocks_total, workers) + 4;
+            if (items > workers / 2 && 10 * even < 9 * whole) { P.balanced = 1; split = 1; }
+        }
         P.split_k = split;
         n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
-        use_cl = (P.m_tiles % 2 == 0) && pair_mode_enabled();
+        if (P.balanced && n_tiles_total < 2 * sm_count()) n_tiles_total = 2 * sm_count();     // grid = every CTA (pair) slot
         if (args.zero_output) {                 // the launcher owns the reduction strategy
-            P.epi.atomic = split > 1;
-            if (split > 1) RADMMM_TRY(zero_wgrad_output(args, stream));
+            P.epi.atomic = split > 1 || P.balanced;
+            if (P.epi.atomic) RADMMM_TRY(zero_wgrad_output(args, stream));
         }
-        RADMMM_REQUIRE(split == 1 || P.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
+        RADMMM_REQUIRE((split == 1 && !P.balanced) || P.epi.atomic, "gemm_tc: split-K weight-grad needs the atomic epilogue");
         // inner extents stop at the logical widths (rounded to the 64-channel box) so that operands which are column
         // slices of wider matrices never read past their rows
         const long long a_in = round_up(M, 64) < g0.a.ld ? round_up(M, 64) : g0.a.ld;

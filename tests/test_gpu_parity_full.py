@@ -11,6 +11,7 @@
 * a duck-typed ``TTSModel.training_step`` (tts_lightning_modules.py:643-686) through the eager module and the pool.
 """
 import functools
+import copy
 import os
 
 import pytest
@@ -494,9 +495,10 @@ def test_fused_radam_inside_the_graphed_step():
     step = GraphedTrainStep(graphed, bt, after_backward=opt_g.step)
     # the capture's warm-up steps already advanced `graphed`; bring the twin to the same point, then compare replays
     eager.load_state_dict(graphed.state_dict())
-    opt_e.load_state_dict(opt_g.state_dict())
     opt_g.sync_step_counts()
-    opt_e.load_state_dict(opt_g.state_dict())
+    # deep copy: Optimizer.load_state_dict keeps the SAME state tensors when dtype and device already match, and two
+    # optimizers sharing their moment buffers would each apply both updates
+    opt_e.load_state_dict(copy.deepcopy(opt_g.state_dict()))
     losses_g, losses_e, dbg = [], [], []
     for _ in range(3):
         losses_g.append(float(step(bt)))
