@@ -245,6 +245,22 @@ int radmmm_soft_attention_backward(const float* q, const float* k, const float* 
                                    const float* dcontext, float* dq, float* dk, float* dtxt, int B, int Ca, int T1, int T2,
                                    int Dt, float temperature, void* stream);
 
+/* Monotonic alignment search, width 1 (alignment.py:31-59 `mas_width1`), batched the way its caller loops
+ * (tts_lightning_modules.py:270-284 `binarize_attention`): attn (B,1,T1,T2) soft attention (probabilities; is_log != 0:
+ * already log-probabilities), in_lens / out_lens (B) text / mel lengths, out (B,1,T1,T2) receives the 0/1 map of
+ * attn[b,0,:out_len,:in_len] and zeros elsewhere.  T2 <= 4096.  radmmm_mas_workspace_bytes returns 0 when the back
+ * pointers (one bit per cell) fit in shared memory, else the size of the device workspace to pass. */
+long long radmmm_mas_workspace_bytes(int B, int T1, int T2);
+int radmmm_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, float* out, int B, int T1, int T2,
+                      int is_log, void* workspace, long long workspace_bytes, void* stream);
+
+/* AttentionCTCLoss (loss.py:112-140) forward AND gradient in one launch: attn_logprob (B,1,T1,T2), key lengths in_lens,
+ * query lengths out_lens; cost (B) receives each utterance's CTC loss (nn.CTCLoss reduction='mean' over its one target:
+ * nll / key_len; zero_infinity: 0 when infeasible) -- the module's value is mean(cost); grad (B,1,T1,T2) receives
+ * d mean(cost) / d attn_logprob.  T2 <= 1023. */
+int radmmm_attention_ctc(const float* attn_logprob, const int32_t* in_lens, const int32_t* out_lens, float* cost, float* grad,
+                         int B, int T1, int T2, float blank_logprob, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

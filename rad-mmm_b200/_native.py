@@ -97,6 +97,9 @@ SIGNATURES = {
     "radmmm_stft_mel": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
     "radmmm_soft_attention": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
     "radmmm_soft_attention_backward": (_i, [_fp] * 12 + [_i, _i, _i, _i, _i, _f, _fp]),
+    "radmmm_mas_workspace_bytes": (_ll, [_i, _i, _i]),
+    "radmmm_mas_width1": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _ll, _fp]),
+    "radmmm_attention_ctc": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp]),
 }
 
 _lib: Optional[C.CDLL] = None

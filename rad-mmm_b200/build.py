@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libradmmm_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "elementwise.cu", "gemm_ffma.cu", "gemm_tc.cu", "wn.cu", "spline.cu", "stft.cu", "attention.cu", "lstm.cu", "lstm_cluster.cu", "optim.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "gemm_ffma.cu", "gemm_tc.cu", "wn.cu", "spline.cu", "stft.cu", "attention.cu", "alignment.cu", "lstm.cu", "lstm_cluster.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

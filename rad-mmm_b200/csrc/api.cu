@@ -268,6 +268,15 @@ int radmmm_stft_mel(const float* audio, const float* mel_basis, float* mel, floa
                     int n_fft, int hop, int n_mel, float clip, void* stream) {
     return stft_mel(audio, mel_basis, mel, magnitude_or_null, B, S, n_fft, hop, n_mel, clip, ST(stream));
 }
+long long radmmm_mas_workspace_bytes(int B, int T1, int T2) { return mas_workspace_bytes(B, T1, T2); }
+int radmmm_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, float* out, int B, int T1, int T2,
+                      int is_log, void* workspace, long long workspace_bytes, void* stream) {
+    return mas_width1(attn, in_lens, out_lens, out, B, T1, T2, is_log, workspace, workspace_bytes, ST(stream));
+}
+int radmmm_attention_ctc(const float* attn_logprob, const int32_t* in_lens, const int32_t* out_lens, float* cost, float* grad,
+                         int B, int T1, int T2, float blank_logprob, void* stream) {
+    return attention_ctc(attn_logprob, in_lens, out_lens, cost, grad, B, T1, T2, blank_logprob, ST(stream));
+}
 int radmmm_soft_attention(const float* q, const float* k, const float* prior, const int32_t* in_lens, float* attn,
                           float* attn_logprob, const float* txt_enc, float* context, int B, int Ca, int T1, int T2,
                           int Dt, float temperature, void* stream) {

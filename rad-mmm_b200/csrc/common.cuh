@@ -109,6 +109,15 @@ __device__ __forceinline__ void row_decode(const RowGeom& g, int r, int& b, int&
     len = (b < g.B) ? min(g.lens[b], g.Tp) : 0;
 }
 
+// 16-byte load that stays where it is written: a batch of these followed by a barrier is in flight all at once.  (A batch of
+// __ldg / ld.global.nc loads is not: ptxas may move non-coherent loads below a bar.sync and it does, interleaving them with
+// their consumers a few at a time to save registers.)
+__device__ __forceinline__ float4 ldg_f4_issue(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // number of in-sequence taps of a k=5 conv with dilation d centred at t (partialconv1d.py:74-77 in closed form)
 __device__ __forceinline__ int tap_count(int t, int len, int d) {
     int u = 0;

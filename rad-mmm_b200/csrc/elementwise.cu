@@ -179,47 +179,47 @@ int coupling_bwd(const float* dz_out, const float* dlog_s, const float* z, const
 
 // =========================================================================================================
 // Invertible 1x1 convolution (common.py:540-548, 605-617):  out[b,co,t] = sum_ci W[co,ci]*(in[b,ci,t]-pre[ci]) + post[co]
-// A small fp32 GEMM per utterance (M = Cout <= 256, N = T', K = Cin): one CTA per 32 (co) x 64 (t) output tile, K in
-// chunks of 32 through shared memory (W tile stored k-major so a thread reads its 2 output channels side by side, x tile
-// as is); a thread owns 2 channels x 4 consecutive frames.  Every global access is a full 128-byte row segment.
-// HBM-bound: 2*C*4 bytes per grouped frame; W (100 KB) comes from L2.
+// A small fp32 GEMM per utterance (M = Cout <= 256, N = T', K = Cin), kept in fp32 FFMA because the flow's invertibility and
+// log-determinant ride on it.  HBM-bound in principle (2*C*4 bytes per grouped frame; W, 100 KB, comes from L2), latency-bound
+// in practice: the whole problem is 0.5 M outputs, so the tile shape is chosen for the number of resident warps, not for
+// register reuse.  One CTA (256 threads) per 32 (co) x 128 (t) tile, a thread owns 4 channels x 4 consecutive frames (two
+// 16-byte shared loads per 16 FMAs), K in chunks of 32 through shared memory with the next chunk prefetched into registers.
+// History (profiles/r2_ncu_inv1x1.md): a 4 x 8 micro-tile with 128-thread CTAs left ONE warp per scheduler -- 23 us per
+// call at B=8, T'=400, issue slots 25 % busy, every shared load's latency exposed (short-scoreboard 2.1 cycles per issue).
 // =========================================================================================================
 constexpr int INV_TC = 32, INV_TN = 128, INV_TK = 32;
-// One CTA (128 threads) per 32 (co) x 128 (t) output tile; a thread owns 4 channels x 8 consecutive frames, so one k step
-// is three 16-byte shared loads for 32 FMAs (the earlier 2 x 4 micro-tile was shared-memory-bandwidth bound: 28 us per call
-// at B=8, T'=400).  The next K chunk is fetched into registers while the current one is being multiplied.
-__global__ void __launch_bounds__(128) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
+__global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
                                                      const float* __restrict__ W, const float* __restrict__ pre,
                                                      const float* __restrict__ post, float* __restrict__ out,
                                                      long long out_bs, int Cin, int Cout, int Tp) {
     __shared__ __align__(16) float ws[INV_TK][INV_TC + 4];      // [k][co]
     __shared__ __align__(16) float xs[INV_TK][INV_TN];          // [k][t]
     const int t0 = blockIdx.x * INV_TN, co0 = blockIdx.y * INV_TC, b = blockIdx.z;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // 16 (t octets) x 8 (co quads)
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;      // 32 (t quads) x 8 (co quads)
     const float* inb = in + (long long)b * in_bs;
     const bool vec_ok = (Tp & 3) == 0 && (in_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-    float acc[4][8];
+    float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-    float wreg[8];
-    float4 xreg[8];
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    float wreg[4];
+    float4 xreg[4];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                              // W tile: 32 co x 32 ci, rows of 32 consecutive ci
-            const int i = j * 128 + tid, c = i >> 5, k = i & 31;
+        for (int j = 0; j < 4; ++j) {                              // W tile: 32 co x 32 ci, rows of 32 consecutive ci
+            const int i = j * 256 + tid, c = i >> 5, k = i & 31;
             wreg[j] = (co0 + c < Cout && k0 + k < Cin) ? __ldg(W + (long long)(co0 + c) * Cin + k0 + k) : 0.0f;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                              // x tile: 32 ci x 128 t, 16-byte pieces
-            const int i = j * 128 + tid, k = i >> 5, q = i & 31;
+        for (int j = 0; j < 4; ++j) {                              // x tile: 32 ci x 128 t, 16-byte pieces
+            const int i = j * 256 + tid, k = i >> 5, q = i & 31;
             const int ci = k0 + k, t = t0 + 4 * q;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ci < Cin && t < Tp) {
                 const float* src = inb + (long long)ci * Tp + t;
                 if (vec_ok && t + 3 < Tp) {
-                    v = __ldg(reinterpret_cast<const float4*>(src));
+                    v = ldg_f4_issue(reinterpret_cast<const float4*>(src));      // stays ahead of the FMAs of the current chunk
                 } else {
                     v.x = __ldg(src);
                     if (t + 1 < Tp) v.y = __ldg(src + 1);
@@ -237,38 +237,40 @@ __global__ void __launch_bounds__(128) inv1x1_kernel(const float* __restrict__ i
     fetch(0);
     for (int k0 = 0; k0 < Cin; k0 += INV_TK) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const int i = j * 128 + tid; ws[i & 31][i >> 5] = wreg[j]; }
+        for (int j = 0; j < 4; ++j) { const int i = j * 256 + tid; ws[i & 31][i >> 5] = wreg[j]; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const int i = j * 128 + tid; *reinterpret_cast<float4*>(&xs[i >> 5][4 * (i & 31)]) = xreg[j]; }
+        for (int j = 0; j < 4; ++j) { const int i = j * 256 + tid; *reinterpret_cast<float4*>(&xs[i >> 5][4 * (i & 31)]) = xreg[j]; }
         __syncthreads();
         if (k0 + INV_TK < Cin) fetch(k0 + INV_TK);
-#pragma unroll 8
+        float4 w4 = *reinterpret_cast<const float4*>(&ws[0][4 * ty]);
+        float4 x4 = *reinterpret_cast<const float4*>(&xs[0][4 * tx]);
+#pragma unroll
         for (int k = 0; k < INV_TK; ++k) {
-            const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][4 * ty]);
-            const float4 xa = *reinterpret_cast<const float4*>(&xs[k][8 * tx]);
-            const float4 xb = *reinterpret_cast<const float4*>(&xs[k][8 * tx + 4]);
             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+            if (k + 1 < INV_TK) {                                  // next step's operands are in flight during this step's FMAs
+                w4 = *reinterpret_cast<const float4*>(&ws[k + 1][4 * ty]);
+                x4 = *reinterpret_cast<const float4*>(&xs[k + 1][4 * tx]);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
         }
         __syncthreads();
     }
-    const int t = t0 + 8 * tx;
+    const int t = t0 + 4 * tx;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int co = co0 + 4 * ty + i;
         if (co < Cout && t < Tp) {
             const float pb = post ? __ldg(post + co) : 0.0f;
             float* o = out + (long long)b * out_bs + (long long)co * Tp + t;
-            if (t + 7 < Tp && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            if (t + 3 < Tp && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
                 reinterpret_cast<float4*>(o)[0] = make_float4(acc[i][0] + pb, acc[i][1] + pb, acc[i][2] + pb, acc[i][3] + pb);
-                reinterpret_cast<float4*>(o)[1] = make_float4(acc[i][4] + pb, acc[i][5] + pb, acc[i][6] + pb, acc[i][7] + pb);
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < 4; ++j)
                     if (t + j < Tp) o[j] = acc[i][j] + pb;
             }
         }
@@ -279,7 +281,7 @@ int inv1x1(const float* in, long long in_bs, const float* W, const float* pre, c
            long long out_bs, int B, int Cin, int Cout, int Tp, cudaStream_t st) {
     RADMMM_REQUIRE(Cout >= 1 && Cin >= 1, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
     dim3 grid(cdiv(Tp, INV_TN), cdiv(Cout, INV_TC), B);
-    inv1x1_kernel<<<grid, 128, 0, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
+    inv1x1_kernel<<<grid, 256, 0, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }
@@ -472,14 +474,39 @@ __global__ void __launch_bounds__(256) wn_scatter_kernel(const float* __restrict
     const int tid = threadIdx.x;
     const int ci_n = min(WS_CI, n_ci - ci0);      // valid input channels of this block
     const int run_n = ci_n * KS;
-    for (int i = tid; i < WS_CO * RUN; i += 256) {
-        const int c = i / RUN, j = i - c * RUN;
-        float val = 0.0f;
-        if (co0 + c < n_co && j < run_n) {
-            const float sc = g ? g[co0 + c] / norm[co0 + c] : 1.0f;
-            val = sc * __ldg(v + ((long long)(co0 + c) * ci_total + ci_begin + ci0) * KS + j);
+    __shared__ float sc_s[WS_CO];                 // g / ||v|| per output channel of this block
+    if (tid < WS_CO) sc_s[tid] = (co0 + tid < n_co) ? (g ? g[co0 + tid] / norm[co0 + tid] : 1.0f) : 0.0f;
+    // full tiles whose rows start on a 16-byte boundary: every thread issues ALL of its 16-byte loads before the first use,
+    // so a CTA has its whole 40 KB tile in flight at once (the scalar loop below kept ~4 loads per thread in flight and ran
+    // at 1.1 TB/s: profiles/r2_launches_bf16.md)
+    constexpr int V4 = RUN / 4, NIT = WS_CO * V4 / 256;
+    static_assert(RUN % 4 == 0 && (WS_CO * V4) % 256 == 0, "tile must split into whole float4 batches");
+    const long long row0 = ((long long)co0 * ci_total + ci_begin + ci0) * KS;
+    const bool vec = ci_n == WS_CI && co0 + WS_CO <= n_co && (row0 & 3) == 0 && (((long long)ci_total * KS) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+    if (vec) {
+        float4 buf[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = it * 256 + tid, c = i / V4, j4 = i - c * V4;
+            buf[it] = ldg_f4_issue(reinterpret_cast<const float4*>(v + row0 + (long long)c * ci_total * KS) + j4);
         }
-        tile[c * LDS_ + j] = val;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = it * 256 + tid, c = i / V4, j4 = i - c * V4;
+            const float sc = sc_s[c];
+            float* o = tile + c * LDS_ + 4 * j4;
+            o[0] = sc * buf[it].x; o[1] = sc * buf[it].y; o[2] = sc * buf[it].z; o[3] = sc * buf[it].w;
+        }
+    } else {
+        __syncthreads();
+        for (int i = tid; i < WS_CO * RUN; i += 256) {
+            const int c = i / RUN, j = i - c * RUN;
+            float val = 0.0f;
+            if (co0 + c < n_co && j < run_n) val = sc_s[c] * __ldg(v + ((long long)(co0 + c) * ci_total + ci_begin + ci0) * KS + j);
+            tile[c * LDS_ + j] = val;
+        }
     }
     __syncthreads();
     constexpr int P = (MODE == MODE_BF16X3) ? 2 : 1;

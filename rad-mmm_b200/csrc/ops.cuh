@@ -55,6 +55,11 @@ int spline_linear_bwd(const float* z1, const float* q, const int* lens, const fl
                       int B, int Ch, int Tp, int n_bins, float lo, float hi, cudaStream_t st);
 int stft_mel(const float* audio, const float* mel_basis, float* mel, float* mag, int B, int S, int n_fft, int hop,
              int n_mel, float clip, cudaStream_t st);
+long long mas_workspace_bytes(int B, int T1, int T2);
+int mas_width1(const float* attn, const int* in_lens, const int* out_lens, float* out, int B, int T1, int T2, int is_log,
+               void* workspace, long long workspace_bytes, cudaStream_t st);
+int attention_ctc(const float* logprob, const int* in_lens, const int* out_lens, float* cost, float* grad, int B, int T1, int T2,
+                  float blank_logprob, cudaStream_t st);
 int soft_attention(const float* q, const float* k, const float* prior, const int* in_lens, float* attn,
                    float* attn_logprob, const float* txt_enc, float* context, int B, int Ca, int T1, int T2, int Dt,
                    float temperature, cudaStream_t st);

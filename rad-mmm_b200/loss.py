@@ -1,5 +1,6 @@
 """Flow negative log-likelihood (reference: loss.py:85-110 ``compute_flow_loss`` and the flow part of
-``RADMMMLoss.forward``, loss.py:518-538) on masked-sum reduction kernels (fp64 accumulation, warp shuffles)."""
+``RADMMMLoss.forward``, loss.py:518-538) on masked-sum reduction kernels (fp64 accumulation, warp shuffles), and the
+alignment CTC loss (loss.py:112-140 ``AttentionCTCLoss``) as one batched kernel."""
 from __future__ import annotations
 
 import torch
@@ -78,3 +79,47 @@ class RADMMMFlowLoss(torch.nn.Module):
         loss, prior = flow_nll(model_output["z_mel"], model_output["log_det_W_list"], model_output["log_s_list"],
                                lens_g, self.sigma, n_elements=n_elements_like_reference(lengths, self.n_group_size))
         return {"loss_mel": (loss, 1.0), "loss_prior_mel": (prior, 0.0)}
+
+
+class _AttentionCTC(torch.autograd.Function):
+    """Batched forward + gradient of loss.py:112-140 in one launch (csrc/alignment.cu)."""
+
+    @staticmethod
+    def forward(ctx, attn_logprob, in_lens, out_lens, blank_logprob: float):
+        lib = N.lib()
+        x = attn_logprob.contiguous().float()
+        b, _, t1, t2 = x.shape
+        cost = torch.zeros(b, device=x.device)
+        grad = torch.empty_like(x)
+        with N.on_device_of(x):
+            N.check(lib.radmmm_attention_ctc(N.fptr(x), N.ptr(in_lens), N.ptr(out_lens), N.fptr(cost), N.fptr(grad), b, t1, t2,
+                                             float(blank_logprob), N.stream()))
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(cost)
+        return cost.mean(), cost
+
+    @staticmethod
+    def backward(ctx, g, _g_each):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None
+
+
+class AttentionCTCLoss(torch.nn.Module):
+    """Drop-in for loss.py:112-140: same constructor, same ``forward(attn_logprob, in_lens, out_lens, return_all=False)``.
+    The reference loops over the batch (log_softmax + nn.CTCLoss(zero_infinity=True) per utterance); here the whole batch
+    is one kernel that also produces the gradient w.r.t. ``attn_logprob``."""
+
+    def __init__(self, blank_logprob=-1):
+        super().__init__()
+        self.blank_logprob = blank_logprob
+
+    def forward(self, attn_logprob, in_lens, out_lens, return_all=False):
+        if not attn_logprob.is_cuda:
+            raise RuntimeError("radmmm_b200.loss.AttentionCTCLoss: expected a CUDA tensor (the kernels have no CPU path)")
+        dev = attn_logprob.device
+        il = torch.as_tensor(in_lens).to(device=dev, dtype=torch.int32).contiguous()
+        ol = torch.as_tensor(out_lens).to(device=dev, dtype=torch.int32).contiguous()
+        cost, each = _AttentionCTC.apply(attn_logprob, il, ol, float(self.blank_logprob))
+        if return_all:
+            return cost, list(each.unbind(0))
+        return cost

@@ -299,9 +299,43 @@ def radam_case():
         step=np.asarray(st["step"]))
 
 
+def alignment_maps():
+    """Seeded soft attention maps (B, 1, T1, T2) with ragged lengths: softmax over the text axis of smooth logits around a
+    diagonal plus noise -- one sharp enough that many probabilities underflow to exactly 0 (log = -inf ties)."""
+    B, T1, T2 = 4, 96, 40
+    in_lens = torch.tensor([40, 23, 31, 7])
+    out_lens = torch.tensor([96, 57, 80, 5])          # the last one has fewer frames than text positions
+    t1 = torch.arange(T1, dtype=torch.float32)[None, :, None]
+    t2 = torch.arange(T2, dtype=torch.float32)[None, None, :]
+    sharp = torch.tensor([0.05, 0.4, 6.0, 0.2])[:, None, None]
+    centre = t1 * (in_lens[:, None, None].float() / out_lens[:, None, None].float())
+    logits = -sharp * (t2 - centre) ** 2 + 2.0 * syn.hash_uniform("align.noise", (B, T1, T2))
+    logprob = logits.unsqueeze(1).contiguous()
+    mask = t2 >= in_lens[:, None, None]
+    attn = torch.softmax(logits.masked_fill(mask, -float("inf")), dim=2).unsqueeze(1).contiguous()
+    return attn, logprob, in_lens, out_lens
+
+
+def alignment_case():
+    """Reference alignment.mas_width1 (numba, alignment.py:31-59) through the loop of binarize_attention
+    (tts_lightning_modules.py:270-284), and reference loss.AttentionCTCLoss (loss.py:112-140) forward + gradient."""
+    from alignment import mas_width1 as mas
+    from loss import AttentionCTCLoss
+    attn, logprob, in_lens, out_lens = alignment_maps()
+    a = attn.numpy()
+    hard = torch.zeros_like(attn)
+    for b in range(attn.shape[0]):
+        hard[b, 0, :out_lens[b], :in_lens[b]] = torch.tensor(mas(a[b, 0, :out_lens[b], :in_lens[b]]))
+    lp = logprob.clone().requires_grad_(True)
+    cost, each = AttentionCTCLoss()(lp, in_lens, out_lens, return_all=True)
+    cost.backward()
+    npz("alignment.npz", attn=attn, logprob=logprob, in_lens=in_lens, out_lens=out_lens, hard=hard, ctc_cost=cost.detach(),
+        ctc_each=torch.stack([c.detach() for c in each]), ctc_grad=lp.grad)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["keys", "ops", "spline", "frontend", "small", "full", "radam"]
+    which = sys.argv[1:] or ["keys", "ops", "spline", "frontend", "small", "full", "radam", "alignment"]
     if "keys" in which:
         state_dict_keys()
     if "ops" in which:
@@ -316,3 +350,5 @@ if __name__ == "__main__":
         decoder_case("decoder_full.npz", n_flows=8, batch=2, frames=96)
     if "radam" in which:
         radam_case()
+    if "alignment" in which:
+        alignment_case()

@@ -268,7 +268,9 @@ def test_linear_spline_kernels():
         close(o, y_ref.detach(), 2e-5, what=f"linear spline fwd ({nb} bins)")
         close(l, l_ref.detach(), 2e-4, what=f"linear spline log J ({nb} bins)")
         outside = (z < -3) | (z > 3)
-        assert torch.equal(o.cpu()[outside], z[outside])
+        # out-of-range elements pass through the spline untouched; like the reference they still go through the
+        # (z - lo) / (hi - lo) normalisation and back, so equality holds to rounding, not bit for bit
+        close(o.cpu()[outside], z[outside], 1e-6, what=f"linear spline pass-through ({nb} bins)")
         mask = of.length_mask(ln.long(), T)[:, None].double()
         g1, g2 = syn.hash_uniform("spll.g1", (B, Ch, T)).double(), syn.hash_uniform("spll.g2", (B, 1, T)).double()
         ((y_ref * g1 * mask).sum() + (l_ref * g2 * mask).sum()).backward()

@@ -291,3 +291,21 @@ def test_radam_trajectory():
     close(m[0], gd["exp_avg_a"], 1e-8)
     close(v[0], gd["exp_avg_sq_a"], 1e-9)
     assert int(gd["step"]) == 9
+
+
+def test_alignment_oracle_vs_reference():
+    """oracle.alignment against outputs of the unmodified reference (numba alignment.mas_width1 looped as
+    TTSModel.binarize_attention does; loss.AttentionCTCLoss forward + gradient) on ragged maps that include exact-zero
+    probabilities (-inf ties), fewer frames than text positions (the extra opt[0, 0] = 1) and an infeasible CTC target."""
+    from oracle import alignment as oa
+    gd = g("alignment.npz")
+    hard = oa.binarize_attention(gd["attn"], gd["in_lens"], gd["out_lens"])
+    assert torch.equal(hard, gd["hard"])
+    assert (gd["attn"] == 0).sum() > 1000 and gd["hard"][3, 0, 0].sum() == 2
+    lp = gd["logprob"].clone().requires_grad_(True)
+    cost, each = oa.attention_ctc_loss(lp, gd["in_lens"], gd["out_lens"])
+    cost.backward()
+    close(cost.detach(), gd["ctc_cost"], 1e-6)
+    close(torch.stack([e.detach() for e in each]), gd["ctc_each"], 1e-6)
+    assert float(gd["ctc_each"][3]) == 0.0
+    close(lp.grad, gd["ctc_grad"], 1e-7)
