@@ -37,7 +37,7 @@ TRAIN_MFLOP_PER_FRAME = 656.4    # 3 x forward (fwd + dgrad + wgrad; recompute n
 K5_FLOP_PER_GROUPED_FRAME = 2 * 1024 * 1024 * 5      # one dilated k=5 layer (the dominant kernel), per grouped frame
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at B=8 x T=800, bf16, from the
 # committed `ncu --set full` capture named below (re-measured whenever the kernel changes)
-K5_DRAM_BYTES_NCU = {"bytes": 17337856, "source": "profiles/r1_ncu_full_k5_final.md"}
+K5_DRAM_BYTES_NCU = {"bytes": 17335552, "source": "profiles/r2_ncu_full_k5.md"}
 MODEL_ARGS = dict(n_speaker_dim=16, use_accent=True, n_accent_dim=8, n_text_dim=520, n_group_size=2, n_mel_channels=80,
                   n_flows=8)
 
@@ -316,6 +316,84 @@ def frontend_bench(dev, pk, batch, frames):
             "us": ms * 1e3, "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"],
             "algorithmic_bytes_per_frame": 1344,
             "cpu_frames_per_s": 2 * mel.shape[2] / cpu_s, "cpu_note": f"oracle dense-DFT restatement of TacotronSTFT on {os.cpu_count()} host threads, 2 utterances"}
+
+
+def alignment_bench(dev, batch, frames):
+    """Hard alignment after `binarization_start_iter`: batched GPU monotonic alignment search and the batched
+    attention CTC loss (forward + gradient) against the reference's own code on the same maps -- numba `mas_width1` looped
+    over the batch with the device->host / host->device copies of TTSModel.binarize_attention, and loss.AttentionCTCLoss
+    (per-utterance log_softmax + nn.CTCLoss) forward + backward on the same GPU."""
+    from radmmm_b200.alignment import binarize_attention
+    from radmmm_b200.loss import AttentionCTCLoss
+    T1, T2 = frames, 120
+    gen = torch.Generator().manual_seed(7)
+    out_lens = torch.randint(frames // 2, frames + 1, (batch,), generator=gen)
+    out_lens[0] = frames
+    in_lens = torch.clamp((out_lens.float() * 0.15).long(), 8, T2)
+    in_lens[0] = T2
+    t1 = torch.arange(T1, dtype=torch.float32)[None, :, None]
+    t2 = torch.arange(T2, dtype=torch.float32)[None, None, :]
+    logits = -0.3 * (t2 - t1 * (in_lens[:, None, None].float() / out_lens[:, None, None].float())) ** 2 + torch.randn(batch, T1, T2, generator=gen)
+    attn = torch.softmax(logits.masked_fill(t2 >= in_lens[:, None, None], -float("inf")), dim=2).unsqueeze(1).contiguous().to(dev)
+    logprob = logits.unsqueeze(1).contiguous().to(dev)
+    il, ol = in_lens.to(dev), out_lens.to(dev)
+
+    def timed_us(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        torch.cuda._sleep(2_000_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    ctc = AttentionCTCLoss()
+
+    def ctc_step():
+        lp = logprob.detach().requires_grad_(True)
+        ctc(lp, il, ol).backward()
+    res = {"shape": f"{batch} utterances, {T1} mel frames x {T2} text positions (ragged)",
+           "mas_us": timed_us(lambda: binarize_attention(attn, il, ol)), "ctc_fwd_bwd_us": timed_us(ctc_step)}
+    try:
+        from oracle import ref_import
+        ref_import.import_reference()
+        from alignment import mas_width1 as ref_mas
+        from loss import AttentionCTCLoss as RefCTC
+
+        def ref_binarize():                                   # tts_lightning_modules.py:270-284
+            a = attn.data.cpu().numpy()
+            out = torch.zeros_like(attn)
+            for b in range(batch):
+                out[b, 0, :out_lens[b], :in_lens[b]] = torch.tensor(ref_mas(a[b, 0, :out_lens[b], :in_lens[b]]), device=dev)
+            return out
+        ref_binarize()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ref_binarize()
+        torch.cuda.synchronize()
+        res["reference_mas_us"] = (time.perf_counter() - t0) / 5 * 1e6
+        rctc = RefCTC()
+
+        def ref_ctc_step():
+            lp = logprob.detach().requires_grad_(True)
+            rctc(lp, in_lens, out_lens).backward()
+        for _ in range(2):
+            ref_ctc_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ref_ctc_step()
+        torch.cuda.synchronize()
+        res["reference_ctc_fwd_bwd_us"] = (time.perf_counter() - t0) / 5 * 1e6
+        res["reference_note"] = "unmodified reference code (staged copy): numba MAS on the host with its copies, torch CTC loop on the same GPU; wall clock"
+    except Exception as exc:
+        res["reference_note"] = f"reference unavailable: {type(exc).__name__}: {exc}"[:200]
+    return res
 
 
 def precision_errors(dev, precisions):
@@ -648,6 +726,10 @@ def run_ours(args):
             extras["frontend"] = frontend_bench(dev, pk, batch, frames)
         except Exception as exc:
             extras["frontend"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            extras["hard_alignment"] = alignment_bench(dev, batch, frames)
+        except Exception as exc:
+            extras["hard_alignment"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         _finish(world)

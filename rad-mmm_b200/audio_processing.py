@@ -111,3 +111,62 @@ class TacotronSTFT(torch.nn.Module):
         N.check(lib.radmmm_stft_mel(N.fptr(y), N.fptr(self.mel_basis), N.fptr(mel), None, b, s, st.filter_length,
                                     st.hop_length, self.n_mel_channels, 1e-5, N.stream()))
         return mel
+
+
+class BatchedFrontEnd(torch.nn.Module):
+    """The data-path front end as one batched GPU call: what the reference's ``Data.get_mel`` +
+    ``Data.get_energy_average`` do per utterance on a CPU worker (data.py:363-376: ``audio / max_wav_value`` ->
+    ``TacotronSTFT.mel_spectrogram`` -> optional mel noise; energy = mean over mel channels, ``(x + 20) / 20`` when
+    ``use_scaled_energy``), for a padded batch of raw audio in the training process.
+
+    ``forward(audio, audio_lens)``: audio (B, S_max) raw samples (int16 range when ``max_wav_value`` = 32768), audio_lens (B)
+    -> mel (B, n_mel, T_max), energy_avg (B, T_max), out_lens (B) with ``out_lens = audio_lens // hop + 1`` -- the frame
+    count the per-utterance call produces.  Frames at or beyond ``out_lens`` are zero.  Frames whose analysis window reaches
+    past the end of the utterance see the reflect padding of the UTTERANCE in the reference and the batch padding (zeros)
+    here; ``exact_tail=True`` (default) re-computes those last ``n_fft / (2 hop) + 1`` frames from a short clip ending at the
+    utterance's end, so the result is the per-utterance one everywhere (one tiny extra launch per utterance; ``audio_lens``
+    is read on the host)."""
+
+    def __init__(self, filter_length=1024, hop_length=256, win_length=1024, n_mel_channels=80, sampling_rate=22050,
+                 mel_fmin=0.0, mel_fmax=8000.0, max_wav_value=32768.0, use_scaled_energy=True, mel_noise_scale=0.0,
+                 exact_tail=True):
+        super().__init__()
+        self.stft = TacotronSTFT(filter_length, hop_length, win_length, n_mel_channels, sampling_rate, mel_fmin, mel_fmax)
+        self.max_wav_value = max_wav_value
+        self.use_scaled_energy = use_scaled_energy
+        self.mel_noise_scale = mel_noise_scale
+        self.exact_tail = exact_tail
+        self.hop, self.n_fft = hop_length, filter_length
+
+    def energy_avg_normalize(self, x):
+        return (x + 20.0) / 20.0 if self.use_scaled_energy else x          # data.py:339-342
+
+    @torch.no_grad()
+    def forward(self, audio, audio_lens):
+        audio = audio.float() / self.max_wav_value
+        b, s_max = audio.shape
+        lens = torch.as_tensor(audio_lens, device=audio.device).long()
+        out_lens = torch.div(lens, self.hop, rounding_mode="floor") + 1
+        mel = self.stft.mel_spectrogram(audio.clamp(-1, 1), check_range=False)
+        if self.exact_tail:
+            # The last frames of an utterance (window centre within n_fft/2 of its end) see the utterance's own reflection in
+            # the reference and the batch padding here.  Re-compute them from a short clip that ends exactly at the utterance
+            # end and starts on a hop boundary far enough back that the clip's own leading reflection is not used.
+            half, hop = self.n_fft // 2, self.hop
+            for i, n in enumerate(lens.tolist()):          # host lengths (the loader knows them); B tiny launches
+                if n >= s_max or n <= half:
+                    continue                               # the longest utterance is exact already; tiny clips: left as is
+                f_first = max(0, (n - half) // hop)
+                start = max(0, (f_first - half // hop - 1) * hop)
+                clip = audio[i:i + 1, start:n].clamp(-1, 1)
+                tm = self.stft.mel_spectrogram(clip, check_range=False)[0]
+                f0 = f_first - start // hop
+                n_fix = n // hop + 1 - f_first
+                mel[i, :, f_first:f_first + n_fix] = tm[:, f0:f0 + n_fix]
+        t = torch.arange(mel.shape[2], device=mel.device)[None]
+        keep = (t < out_lens[:, None])
+        if self.mel_noise_scale > 0:
+            mel = mel + torch.randn_like(mel) * self.mel_noise_scale
+        mel = mel * keep[:, None]
+        energy = self.energy_avg_normalize(mel.mean(1)) * keep              # data.py:358-361
+        return mel, energy, out_lens

@@ -182,20 +182,22 @@ int coupling_bwd(const float* dz_out, const float* dlog_s, const float* z, const
 // A small fp32 GEMM per utterance (M = Cout <= 256, N = T', K = Cin), kept in fp32 FFMA because the flow's invertibility and
 // log-determinant ride on it.  HBM-bound in principle (2*C*4 bytes per grouped frame; W, 100 KB, comes from L2), latency-bound
 // in practice: the whole problem is 0.5 M outputs, so the tile shape is chosen for the number of resident warps, not for
-// register reuse.  One CTA (256 threads) per 32 (co) x 128 (t) tile, a thread owns 4 channels x 4 consecutive frames (two
+// register reuse.  One CTA (128 threads) per 32 (co) x 64 (t) tile, a thread owns 4 channels x 4 consecutive frames (two
 // 16-byte shared loads per 16 FMAs), K in chunks of 32 through shared memory with the next chunk prefetched into registers.
+// At B=8, C=160, T'=400 that is 280 CTAs, all resident at once (two per SM, two warps per scheduler): 32 x 128 tiles made
+// 160 CTAs of 8 warps -- 1.08 waves, so the 12 SMs that got a second CTA doubled the kernel's duration (16.6 us).
 // History (profiles/r2_ncu_inv1x1.md): a 4 x 8 micro-tile with 128-thread CTAs left ONE warp per scheduler -- 23 us per
 // call at B=8, T'=400, issue slots 25 % busy, every shared load's latency exposed (short-scoreboard 2.1 cycles per issue).
 // =========================================================================================================
-constexpr int INV_TC = 32, INV_TN = 128, INV_TK = 32;
-__global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
+constexpr int INV_TC = 32, INV_TN = 64, INV_TK = 32, INV_THREADS = 128;
+__global__ void __launch_bounds__(INV_THREADS) inv1x1_kernel(const float* __restrict__ in, long long in_bs,
                                                      const float* __restrict__ W, const float* __restrict__ pre,
                                                      const float* __restrict__ post, float* __restrict__ out,
                                                      long long out_bs, int Cin, int Cout, int Tp) {
     __shared__ __align__(16) float ws[INV_TK][INV_TC + 4];      // [k][co]
     __shared__ __align__(16) float xs[INV_TK][INV_TN];          // [k][t]
     const int t0 = blockIdx.x * INV_TN, co0 = blockIdx.y * INV_TC, b = blockIdx.z;
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;      // 32 (t quads) x 8 (co quads)
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // 16 (t quads) x 8 (co quads)
     const float* inb = in + (long long)b * in_bs;
     const bool vec_ok = (Tp & 3) == 0 && (in_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     float acc[4][4];
@@ -203,17 +205,17 @@ __global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ i
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    float wreg[4];
+    float wreg[8];
     float4 xreg[4];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                              // W tile: 32 co x 32 ci, rows of 32 consecutive ci
-            const int i = j * 256 + tid, c = i >> 5, k = i & 31;
+        for (int j = 0; j < 8; ++j) {                              // W tile: 32 co x 32 ci, rows of 32 consecutive ci
+            const int i = j * INV_THREADS + tid, c = i >> 5, k = i & 31;
             wreg[j] = (co0 + c < Cout && k0 + k < Cin) ? __ldg(W + (long long)(co0 + c) * Cin + k0 + k) : 0.0f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                              // x tile: 32 ci x 128 t, 16-byte pieces
-            const int i = j * 256 + tid, k = i >> 5, q = i & 31;
+        for (int j = 0; j < 4; ++j) {                              // x tile: 32 ci x 64 t, 16-byte pieces
+            const int i = j * INV_THREADS + tid, k = i >> 4, q = i & 15;
             const int ci = k0 + k, t = t0 + 4 * q;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ci < Cin && t < Tp) {
@@ -237,9 +239,9 @@ __global__ void __launch_bounds__(256) inv1x1_kernel(const float* __restrict__ i
     fetch(0);
     for (int k0 = 0; k0 < Cin; k0 += INV_TK) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int i = j * 256 + tid; ws[i & 31][i >> 5] = wreg[j]; }
+        for (int j = 0; j < 8; ++j) { const int i = j * INV_THREADS + tid; ws[i & 31][i >> 5] = wreg[j]; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int i = j * 256 + tid; *reinterpret_cast<float4*>(&xs[i >> 5][4 * (i & 31)]) = xreg[j]; }
+        for (int j = 0; j < 4; ++j) { const int i = j * INV_THREADS + tid; *reinterpret_cast<float4*>(&xs[i >> 4][4 * (i & 15)]) = xreg[j]; }
         __syncthreads();
         if (k0 + INV_TK < Cin) fetch(k0 + INV_TK);
         float4 w4 = *reinterpret_cast<const float4*>(&ws[0][4 * ty]);
@@ -281,7 +283,7 @@ int inv1x1(const float* in, long long in_bs, const float* W, const float* pre, c
            long long out_bs, int B, int Cin, int Cout, int Tp, cudaStream_t st) {
     RADMMM_REQUIRE(Cout >= 1 && Cin >= 1, "inv1x1: channel count out of range (Cin=%d, Cout=%d)", Cin, Cout);
     dim3 grid(cdiv(Tp, INV_TN), cdiv(Cout, INV_TC), B);
-    inv1x1_kernel<<<grid, 256, 0, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
+    inv1x1_kernel<<<grid, INV_THREADS, 0, st>>>(in, in_bs, W, pre, post, out, out_bs, Cin, Cout, Tp);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }

@@ -805,6 +805,10 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // split K (= rows) so that the persistent grid sees >= ~4 tiles per SM while every tile keeps >= 8 K blocks
         const int tiles0 = P.m_tiles * P.n_tiles * P.taps;
         int split = args.split_k;
+        // RADMMM_B200_WGRAD_WHOLE=1: whole tiles, no split-K (plain stores, no zero-fill) whenever there are at least as many
+        // tiles as CTAs -- for A/B measurements of the reduction strategy
+        static const bool whole = []() { const char* e = getenv("RADMMM_B200_WGRAD_WHOLE"); return e && e[0] == '1'; }();
+        if (split < 1 && whole && tiles0 >= sm_count()) split = 1;
         if (split < 1 && 2 * (long long)tiles0 >= 3 * sm_count()) split = 1;      // enough tiles already
         if (split < 1) {
             split = cdiv(2 * sm_count(), tiles0);
@@ -823,7 +827,7 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // more than 10 % (the 5-tap dilated conv: 80 pair tiles on 74 pairs -- 78 K-block times split in two, 56 balanced).
         // RADMMM_B200_WGRAD_BALANCED=0 keeps whole tiles (A/B measurements).
         static const bool allow_balanced = []() { const char* e = getenv("RADMMM_B200_WGRAD_BALANCED"); return !(e && e[0] == '0'); }();
-        if (allow_balanced && args.zero_output && !P.acc_segs && args.split_k < 1) {
+        if (allow_balanced && !whole && args.zero_output && !P.acc_segs && args.split_k < 1) {
             const int cl = use_cl ? 2 : 1;
             const long long workers = sm_count() / cl;
             const long long items = (long long)(tiles0 / cl) * split;

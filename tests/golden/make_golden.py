@@ -333,9 +333,59 @@ def alignment_case():
         ctc_each=torch.stack([c.detach() for c in each]), ctc_grad=lp.grad)
 
 
+def _seeded_state(module, tag, scale=0.3):
+    """Overwrite every PARAMETER with a hashed tensor (buffers -- spectral-norm u / v -- keep their constructed values)."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            base = syn.hash_uniform(f"{tag}.{name}", tuple(p.shape), -1, 1) * scale
+            if name.endswith("weight_g") or name.endswith(".1.weight"):
+                base = base.abs() + 0.5
+            p.copy_(base)
+    # converge the spectral-norm power iteration (u, v buffers) the way training would: a freshly constructed module has
+    # random u / v, i.e. an arbitrary "sigma" and recurrent weights of norm >> 1 -- a chaotic LSTM no fixture can pin
+    module.train()
+    for m in module.modules():
+        if isinstance(m, torch.nn.LSTM):
+            for _ in range(50):
+                for hook in m._forward_pre_hooks.values():
+                    hook(m, None)
+    module.eval()
+    return {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
+def encoder_case():
+    """Reference common.Encoder (common.py:423-500, spectral-normed LSTM as configs/RADMMM_model_config.yaml:15) and
+    common.ConvLSTMLinear (common.py:240-330) in eval mode on a ragged batch -- the per-utterance loops are the reference's
+    path for B > 1 -- with input and parameter gradients."""
+    import common as C
+    torch.manual_seed(0)
+    lens = torch.tensor([29, 11, 20])
+    out = {}
+    enc = C.Encoder(3, 64, 5, lstm_norm_fn="spectral").eval()
+    sd = _seeded_state(enc, "enc")
+    x = syn.hash_uniform("enc.x", (3, 64, 29)).requires_grad_(True)
+    y = enc(x, lens)
+    g = syn.hash_uniform("enc.g", tuple(y.shape))
+    (y * g).sum().backward()
+    out.update({"enc_sd." + k: v for k, v in sd.items()})
+    out.update(enc_x=x.detach(), enc_y=y.detach(), enc_g=g, enc_dx=x.grad,
+               enc_dv0=enc.convolutions[0][0].conv.weight_v.grad, enc_dgamma2=enc.convolutions[2][1].weight.grad,
+               enc_dwhh=enc.lstm.weight_hh_l0_orig.grad, enc_dwih_r=enc.lstm.weight_ih_l0_reverse.grad)
+    cll = C.ConvLSTMLinear(in_dim=24, out_dim=2, n_layers=2, n_channels=32, kernel_size=3, p_dropout=0.1).eval()
+    sd2 = _seeded_state(cll, "cll")
+    c = syn.hash_uniform("cll.x", (3, 24, 29)).requires_grad_(True)
+    z = cll(c, C.SequenceLength(lens))
+    g2 = syn.hash_uniform("cll.g", tuple(z.shape))
+    (z * g2).sum().backward()
+    out.update({"cll_sd." + k: v for k, v in sd2.items()})
+    out.update(cll_x=c.detach(), cll_y=z.detach(), cll_g=g2, cll_dx=c.grad, cll_dv1=cll.convolutions[1].conv.weight_v.grad,
+               cll_dwhh_r=cll.bilstm.weight_hh_l0_reverse_orig.grad, cll_ddense=cll.dense.weight.grad, lens=lens)
+    npz("encoder.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["keys", "ops", "spline", "frontend", "small", "full", "radam", "alignment"]
+    which = sys.argv[1:] or ["keys", "ops", "spline", "frontend", "small", "full", "radam", "alignment", "encoder"]
     if "keys" in which:
         state_dict_keys()
     if "ops" in which:
@@ -352,3 +402,5 @@ if __name__ == "__main__":
         radam_case()
     if "alignment" in which:
         alignment_case()
+    if "encoder" in which:
+        encoder_case()

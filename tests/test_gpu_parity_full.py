@@ -512,3 +512,70 @@ def test_fused_radam_inside_the_graphed_step():
     assert losses_e[0] != losses_e[2]
     for (n, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
         close(q.detach(), p.detach(), 2e-5 * max(1.0, p.detach().abs().max().item()), what="parameter after 3 steps " + n)
+
+
+def test_batched_front_end_equals_per_utterance_calls():
+    """BatchedFrontEnd: mel / energy / lengths of a padded batch equal what the reference's per-utterance
+    Data.get_mel + get_energy_average produce (data.py:358-376) -- checked against this package's TacotronSTFT on each
+    utterance alone (itself pinned to the reference fixtures in test_gpu_ops) and against the oracle restatement on one."""
+    from oracle import frontend as ofe
+    from radmmm_b200.audio_processing import BatchedFrontEnd, TacotronSTFT
+    lens = [40000, 23117, 31999, 8192, 40000 - 255]
+    audio = torch.zeros(len(lens), max(lens))
+    for i, n in enumerate(lens):
+        audio[i, :n] = syn.hash_uniform(f"fe.audio{i}", (n,), -0.9, 0.9) * 32768.0
+    fe = BatchedFrontEnd().to(DEV)
+    mel, energy, out_lens = fe(audio.to(DEV), lens)
+    single = TacotronSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0).to(DEV)
+    assert out_lens.tolist() == [n // 256 + 1 for n in lens]
+    for i, n in enumerate(lens):
+        ref = single.mel_spectrogram((audio[i:i + 1, :n] / 32768.0).to(DEV))[0]
+        assert ref.shape[1] == out_lens[i]
+        close(mel[i, :, :ref.shape[1]], ref, 2e-4, what=f"batched mel, utterance {i}")
+        close(energy[i, :ref.shape[1]], (ref.mean(0) + 20.0) / 20.0, 2e-5, what=f"energy_avg, utterance {i}")
+        assert float(mel[i, :, ref.shape[1]:].abs().sum()) == 0.0 and float(energy[i, ref.shape[1]:].abs().sum()) == 0.0
+    oracle_mel = ofe.mel_spectrogram(audio[1:2, :lens[1]] / 32768.0)[0]
+    close(mel[1, :, :oracle_mel.shape[1]], oracle_mel, 2e-3, what="batched mel vs oracle")
+
+
+def _sub(gd, prefix):
+    return {k[len(prefix):]: v for k, v in gd.items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_batched_text_encoder_vs_reference(precision):
+    """encoders.Encoder: the padded-batch forward and its gradients equal the reference Encoder's
+    per-utterance loop (fixture made by the unmodified common.Encoder, spectral-normed LSTM); reference state_dict loads
+    with strict=True."""
+    from radmmm_b200.encoders import Encoder
+    gd = gold("encoder.npz")
+    enc = Encoder(3, 64, 5, lstm_norm_fn="spectral").eval()
+    enc.load_state_dict(_sub(gd, "enc_sd."), strict=True)
+    enc = enc.to(DEV)
+    enc.precision = precision
+    x = gd["enc_x"].to(DEV).requires_grad_(True)
+    y = enc(x, gd["lens"].to(DEV))
+    (y * gd["enc_g"].to(DEV)).sum().backward()
+    close(y, gd["enc_y"], 2e-4, what="encoder output")
+    close(x.grad, gd["enc_dx"], 5e-4 * max(1.0, gd["enc_dx"].abs().max().item()), what="encoder dx")
+    for name, p in (("enc_dv0", enc.convolutions[0][0].conv.weight_v), ("enc_dgamma2", enc.convolutions[2][1].weight),
+                    ("enc_dwhh", enc.lstm.weight_hh_l0_orig), ("enc_dwih_r", enc.lstm.weight_ih_l0_reverse)):
+        close(p.grad, gd[name], 5e-4 * max(1.0, gd[name].abs().max().item()), what=name)
+
+
+def test_batched_conv_lstm_linear_vs_reference():
+    """encoders.ConvLSTMLinear (attribute-predictor backbone, common.py:240-330) against the reference's per-utterance path."""
+    from radmmm_b200.common import SequenceLength
+    from radmmm_b200.encoders import ConvLSTMLinear
+    gd = gold("encoder.npz")
+    net = ConvLSTMLinear(in_dim=24, out_dim=2, n_layers=2, n_channels=32, kernel_size=3, p_dropout=0.1).eval()
+    net.load_state_dict(_sub(gd, "cll_sd."), strict=True)
+    net = net.to(DEV)
+    x = gd["cll_x"].to(DEV).requires_grad_(True)
+    y = net(x, SequenceLength(gd["lens"].to(DEV)))
+    (y * gd["cll_g"].to(DEV)).sum().backward()
+    close(y, gd["cll_y"], 2e-4, what="ConvLSTMLinear output")
+    close(x.grad, gd["cll_dx"], 5e-4 * max(1.0, gd["cll_dx"].abs().max().item()), what="ConvLSTMLinear dx")
+    for name, p in (("cll_dv1", net.convolutions[1].conv.weight_v), ("cll_dwhh_r", net.bilstm.weight_hh_l0_reverse_orig),
+                    ("cll_ddense", net.dense.weight)):
+        close(p.grad, gd[name], 5e-4 * max(1.0, gd[name].abs().max().item()), what=name)

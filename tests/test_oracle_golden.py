@@ -309,3 +309,38 @@ def test_alignment_oracle_vs_reference():
     close(torch.stack([e.detach() for e in each]), gd["ctc_each"], 1e-6)
     assert float(gd["ctc_each"][3]) == 0.0
     close(lp.grad, gd["ctc_grad"], 1e-7)
+
+
+def _sub(gd, prefix):
+    return {k[len(prefix):]: v for k, v in gd.items() if k.startswith(prefix)}
+
+
+def test_encoder_oracle_vs_reference():
+    """oracle.encoders (per-utterance loops) against the unmodified reference Encoder / ConvLSTMLinear outputs."""
+    from oracle import encoders as oe
+    gd = g("encoder.npz")
+    with torch.no_grad():
+        y = oe.encoder_forward(_sub(gd, "enc_sd."), gd["enc_x"], gd["lens"])
+        z = oe.conv_lstm_linear_forward(_sub(gd, "cll_sd."), gd["cll_x"], gd["lens"])
+    close(y, gd["enc_y"], 2e-6)
+    close(z, gd["cll_y"], 2e-6)
+
+
+def test_batched_encoder_convs_equal_per_utterance_loop():
+    """The product's batched conv banks (masked input, closed-form partial-conv ratio, masked instance norm) are plain torch
+    ops, so their equality with the per-utterance loop is checked here on the CPU; the LSTM half needs the GPU
+    (tests/test_gpu_parity_full.py)."""
+    from oracle import encoders as oe
+    from radmmm_b200 import encoders as pe
+    gd = g("encoder.npz")
+    enc = pe.Encoder(3, 64, 5, lstm_norm_fn="spectral").eval()
+    enc.load_state_dict(_sub(gd, "enc_sd."), strict=True)
+    lens = gd["lens"]
+    with torch.no_grad():
+        got = enc._convs(gd["enc_x"], lens.long())
+        ref = oe.encoder_convs(_sub(gd, "enc_sd."), gd["enc_x"], lens)
+    for b, r in enumerate(ref):
+        close(got[b, :, :r.shape[0]].t(), r, 2e-5)
+        assert float(got[b, :, r.shape[0]:].abs().sum()) == 0.0
+    cll = pe.ConvLSTMLinear(in_dim=24, out_dim=2, n_layers=2, n_channels=32, kernel_size=3, p_dropout=0.1).eval()
+    cll.load_state_dict(_sub(gd, "cll_sd."), strict=True)
