@@ -396,6 +396,56 @@ def alignment_bench(dev, batch, frames):
     return res
 
 
+def reference_gpu_bench(dev, batch, frames):
+    """Context for a user switching over: the UNMODIFIED reference decoder (staged copy) running the same train step on the
+    SAME B200 with stock PyTorch kernels (cuDNN convolutions, cuDNN LSTM), fp32 and bf16 autocast.  Not the baseline the
+    metric is defined against (that is the CPU arm) -- an extra line."""
+    from oracle import ref_import
+    from radmmm_b200 import synthetic as syn
+    root, mods = ref_import.import_reference()
+    bt = {k: v.to(dev) for k, v in syn.synthetic_batch(batch, frames, tag="bench.rank0").items()}
+    valid = int(bt["out_lens"].sum())
+    dec = mods["decoders"].RADMMMFlow(**MODEL_ARGS, n_conv_layers_per_step=4, n_early_size=2, n_early_every=2,
+                                      affine_model="wavenet", scaling_fn="tanh", affine_activation="softplus",
+                                      use_partial_padding=True)
+    dec.load_state_dict(syn.synthetic_state_dict(), strict=True)
+    dec = dec.to(dev).train()
+    SL, cfl = mods["common"].SequenceLength, mods["loss"].compute_flow_loss
+    lens_g = bt["out_lens"] // 2
+    mask = (torch.arange(frames // 2, device=dev)[None] < lens_g[:, None])[:, None].float()
+    n_el = torch.div(bt["out_lens"].sum(), 2, rounding_mode="floor")
+    res = {}
+    for name, amp in (("fp32", False), ("bf16_autocast", True)):
+        def step():
+            for p in dec.parameters():
+                p.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                out = dec(bt["mel"], bt["spk_vecs"], bt["context"], SL(bt["out_lens"]), f0=bt["f0"],
+                          energy_avg=bt["energy_avg"], accent_vecs=bt["accent_vecs"])
+            loss, _ = cfl(out["z_mel"].float(), [x.float() for x in out["log_det_W_list"]], [x.float() for x in out["log_s_list"]],
+                          n_el, out["z_mel"].size(1), mask, 1.0)
+            loss.backward()
+        try:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                step()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            res[name] = {"ms_per_step": ms, "value": valid / (ms * 1e-3), "unit": UNIT}
+        except Exception as exc:
+            res[name] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    del dec
+    torch.cuda.empty_cache()
+    res["note"] = ("unmodified reference decoders.RADMMMFlow + compute_flow_loss + backward on this GPU, stock PyTorch kernels, "
+                   f"same batch ({batch} x {frames}); eager, no optimizer")
+    return res
+
+
 def precision_errors(dev, precisions):
     """max-abs z error and relative loss error of each contraction mode against the oracle (fp32 CPU) on a small sample:
     the 8-flow decoder, 2 utterances x 96 frames (the shape of tests/golden/decoder_full.npz)."""
@@ -726,6 +776,10 @@ def run_ours(args):
             extras["frontend"] = frontend_bench(dev, pk, batch, frames)
         except Exception as exc:
             extras["frontend"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            extras["reference_same_gpu"] = reference_gpu_bench(dev, batch, frames)
+        except Exception as exc:
+            extras["reference_same_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         try:
             extras["hard_alignment"] = alignment_bench(dev, batch, frames)
         except Exception as exc:

@@ -805,9 +805,12 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // split K (= rows) so that the persistent grid sees >= ~4 tiles per SM while every tile keeps >= 8 K blocks
         const int tiles0 = P.m_tiles * P.n_tiles * P.taps;
         int split = args.split_k;
-        // RADMMM_B200_WGRAD_WHOLE=1: whole tiles, no split-K (plain stores, no zero-fill) whenever there are at least as many
-        // tiles as CTAs -- for A/B measurements of the reduction strategy
-        static const bool whole = []() { const char* e = getenv("RADMMM_B200_WGRAD_WHOLE"); return e && e[0] == '1'; }();
+        // Whole tiles, no split-K (plain stores, no zero-fill, no red.add) whenever there are at least as many tiles as CTAs.
+        // Inside the train step several weight-grad launches and the dgrad chain share the SMs, so a launch's own
+        // quantisation tail (160 tiles on 148 CTAs) is filled by its neighbours and what counts is the total work: measured
+        // 8.57 ms per step against 8.84 (two-way split-K) and 8.80 (balanced K-block runs) -- profiles/r2_wgrad_reduction_ab.md.
+        // RADMMM_B200_WGRAD_WHOLE=0 restores the split; RADMMM_B200_WGRAD_BALANCED=1 selects the balanced walk.
+        static const bool whole = []() { const char* e = getenv("RADMMM_B200_WGRAD_WHOLE"); return !(e && e[0] == '0'); }();
         if (split < 1 && whole && tiles0 >= sm_count()) split = 1;
         if (split < 1 && 2 * (long long)tiles0 >= 3 * sm_count()) split = 1;      // enough tiles already
         if (split < 1) {
@@ -825,15 +828,23 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // Whole tiles or equal K-block runs?  Whole tiles cost `rounds * K blocks per item`; the balanced walk costs
         // `units / workers` plus roughly one more epilogue (counted as 4 K blocks).  Take the balanced walk when it wins by
         // more than 10 % (the 5-tap dilated conv: 80 pair tiles on 74 pairs -- 78 K-block times split in two, 56 balanced).
-        // RADMMM_B200_WGRAD_BALANCED=0 keeps whole tiles (A/B measurements).
-        static const bool allow_balanced = []() { const char* e = getenv("RADMMM_B200_WGRAD_BALANCED"); return !(e && e[0] == '0'); }();
-        if (allow_balanced && !whole && args.zero_output && !P.acc_segs && args.split_k < 1) {
+        // Off by default (see above); RADMMM_B200_WGRAD_BALANCED=1 enables it for A/B measurements.
+        static const bool allow_balanced = []() { const char* e = getenv("RADMMM_B200_WGRAD_BALANCED"); return e && e[0] == '1'; }();
+        if (allow_balanced && args.zero_output && !P.acc_segs && args.split_k < 1) {
+            split = args.split_k;                      // undo the whole-tile choice above: compare against the split it replaces
+            if (split < 1) {
+                split = cdiv(2 * sm_count(), tiles0);
+                const int max_split = P.k_blocks_total / 8 > 1 ? P.k_blocks_total / 8 : 1;
+                if (split > max_split) split = max_split;
+                const int per = cdiv(P.k_blocks_total, split);
+                split = cdiv(P.k_blocks_total, per);
+            }
             const int cl = use_cl ? 2 : 1;
             const long long workers = sm_count() / cl;
             const long long items = (long long)(tiles0 / cl) * split;
-            const long long whole = cdiv(items, workers) * cdiv(P.k_blocks_total, split);
+            const long long tile_cost = cdiv(items, workers) * cdiv(P.k_blocks_total, split);
             const long long even = cdiv((long long)(tiles0 / cl) * P.k_blocks_total, workers) + 4;
-            if (items > workers / 2 && 10 * even < 9 * whole) { P.balanced = 1; split = 1; }
+            if (items > workers / 2 && 10 * even < 9 * tile_cost) { P.balanced = 1; split = 1; }
         }
         P.split_k = split;
         n_tiles_total = P.m_tiles * P.n_tiles * P.taps * P.split_k;
