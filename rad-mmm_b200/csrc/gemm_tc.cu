@@ -810,8 +810,10 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // quantisation tail (160 tiles on 148 CTAs) is filled by its neighbours and what counts is the total work: measured
         // 8.57 ms per step against 8.84 (two-way split-K) and 8.80 (balanced K-block runs) -- profiles/r2_wgrad_reduction_ab.md.
         // RADMMM_B200_WGRAD_WHOLE=0 restores the split; RADMMM_B200_WGRAD_BALANCED=1 selects the balanced walk.
-        static const bool whole = []() { const char* e = getenv("RADMMM_B200_WGRAD_WHOLE"); return !(e && e[0] == '0'); }();
+        static const int whole_mode = []() { const char* e = getenv("RADMMM_B200_WGRAD_WHOLE"); return e ? atoi(e) : 1; }();
+        const bool whole = whole_mode != 0;
         if (split < 1 && whole && tiles0 >= sm_count()) split = 1;
+        if (split < 1 && whole_mode == 2) split = 1;                               // A/B: never split, however few tiles
         if (split < 1 && 2 * (long long)tiles0 >= 3 * sm_count()) split = 1;      // enough tiles already
         if (split < 1) {
             split = cdiv(2 * sm_count(), tiles0);

@@ -77,3 +77,15 @@ def test_no_cpu_fallback():
     stft = audio_processing.TacotronSTFT()
     with pytest.raises(RuntimeError, match="CUDA"):
         stft.mel_spectrogram(torch.zeros(1, 4096))
+
+
+def test_integration_doc_flowdesc_matches_binding():
+    """INTEGRATION.md shows the ctypes struct a maintainer would write: its field list must be the real one (round 1's
+    copy had lost `side_stream`) and the ABI version it asserts must be the current one."""
+    import re
+    from radmmm_b200 import _native
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class FlowDesc(C.Structure)"):text.index("assert C.sizeof(FlowDesc)")]
+    doc_fields = re.findall(r'\("(\w+)",', block)
+    assert doc_fields == [f[0] for f in _native.FlowDesc._fields_]
+    assert f"radmmm_abi_version() == {_native.ABI_VERSION}" in text
