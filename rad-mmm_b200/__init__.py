@@ -1,2 +1,2 @@
 """radmmm_b200 -- B200-native flow decoder + mel front end for RAD-MMM (drop-in for decoders.RADMMMFlow)."""
-__version__ = "0.1.0"
+__version__ = "0.2.0"
