@@ -24,13 +24,22 @@ def main():
     args = ap.parse_args()
     from radmmm_b200 import decoders, loss as L, synthetic as syn
     from radmmm_b200.common import SequenceLength
-    dev = torch.device("cuda", 0)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:      # torchrun: the step's bucketed NCCL all-reduce is part of the timeline; rank 0 reports
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = False
     dec = decoders.RADMMMFlow(n_speaker_dim=16, use_accent=True, n_accent_dim=8, n_text_dim=520, n_group_size=2,
                               n_mel_channels=80, n_flows=8)
     dec.load_state_dict(syn.synthetic_state_dict())
     dec = dec.to(dev).set_precision(args.precision).train()
-    bt = {k: v.to(dev) for k, v in syn.synthetic_batch(args.batch, args.frames, tag="bench.rank0").items()}
+    bt = {k: v.to(dev) for k, v in syn.synthetic_batch(args.batch, args.frames, tag=f"bench.rank{rank}").items()}
+    reducer = None
+    if world > 1:
+        from radmmm_b200.ddp import BucketedGradReducer
+        reducer = BucketedGradReducer(dec).install()
 
     def step():
         for p in dec.parameters():
@@ -39,17 +48,25 @@ def main():
                   energy_avg=bt["energy_avg"], accent_vecs=bt["accent_vecs"])
         loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], bt["out_lens"] // 2)
         loss.backward()
+        if reducer is not None:
+            reducer.finish()
 
     for _ in range(4):
         step()
     torch.cuda.synchronize()
     if args.graph:
         from radmmm_b200.graphs import GraphedTrainStep
-        gstep = GraphedTrainStep(dec, bt)
+        gstep = GraphedTrainStep(dec, bt, reducer=reducer)
         for _ in range(3):
             gstep(bt)
         torch.cuda.synchronize()
         step = lambda: gstep(bt)      # noqa: E731
+    if world > 1 and rank != 0:             # the other ranks just take part in the collectives of the profiled step
+        import torch.distributed as dist
+        step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize()
@@ -91,7 +108,19 @@ def main():
         agg[e["name"][:90]][1] += e["dur"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
         print(f"{v[1]:9.1f} us {v[0]:5d}  {k}")
+    # collectives: when each NCCL kernel starts / ends relative to the step, and what compute is still running by then
+    nccl = [e for e in ker if "nccl" in e["name"].lower()]
+    if nccl:
+        comp_end = max(e["ts"] + e["dur"] for e in ker if "nccl" not in e["name"].lower())
+        print(f"  NCCL kernels: {len(nccl)}; last compute kernel ends at {comp_end - t0:.0f} us, step ends at {t1 - t0:.0f} us "
+              f"(exposed tail {t1 - comp_end:.0f} us)")
+        for e in nccl:
+            print(f"    nccl start {e['ts'] - t0:8.0f} us  dur {e['dur']:7.0f} us  end {e['ts'] + e['dur'] - t0:8.0f} us  stream {e['args'].get('stream')}  {e['name'][:60]}")
     os.remove(path)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":
