@@ -810,10 +810,14 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // quantisation tail (160 tiles on 148 CTAs) is filled by its neighbours and what counts is the total work: measured
         // 8.57 ms per step against 8.84 (two-way split-K) and 8.80 (balanced K-block runs) -- profiles/r2_wgrad_reduction_ab.md.
         // RADMMM_B200_WGRAD_WHOLE=0 restores the split; RADMMM_B200_WGRAD_BALANCED=1 selects the balanced walk.
-        static const int whole_mode = []() { const char* e = getenv("RADMMM_B200_WGRAD_WHOLE"); return e ? atoi(e) : 1; }();
+        static const int whole_mode = []() { const char* e = getenv("RADMMM_B200_WGRAD_WHOLE"); return e ? atoi(e) : 2; }();
         const bool whole = whole_mode != 0;
         if (split < 1 && whole && tiles0 >= sm_count()) split = 1;
-        if (split < 1 && whole_mode == 2) split = 1;                               // A/B: never split, however few tiles
+        // Few tiles AND a short K (<= 128 blocks of 64 rows, i.e. the benchmark's B=8 x T=800): still no split.  The launch
+        // fills only part of the machine, but it runs on a weight-grad lane next to three others and the dgrad chain, and the
+        // memset + red.add a split costs is pure extra work: 8.50 vs 8.64 ms per step.  Long K keeps the split (a handful of
+        // CTAs walking thousands of K blocks would become the step's tail).  RADMMM_B200_WGRAD_WHOLE=1: tiles >= SMs only.
+        if (split < 1 && whole_mode >= 2 && P.k_blocks_total <= 128) split = 1;
         if (split < 1 && 2 * (long long)tiles0 >= 3 * sm_count()) split = 1;      // enough tiles already
         if (split < 1) {
             split = cdiv(2 * sm_count(), tiles0);

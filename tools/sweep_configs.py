@@ -63,6 +63,14 @@ def config5(points):
         sys.stdout.flush()
 
 
+def _durations(syn, batch, n_tok):
+    """Token durations 2..10 frames (config 4: ~600 frames from 100 tokens); every utterance's total is made even so the
+    grouped (n_group_size = 2) frame count is exact."""
+    dur = (2 + (syn.hash_uniform(f"c4.dur{batch}", (batch, n_tok), 0, 1) * 9).floor().clamp(max=8)).long()
+    dur[:, 0] += dur.sum(1) % 2
+    return dur
+
+
 def config4():
     import torch
     from radmmm_b200 import decoders, synthetic as syn
@@ -81,10 +89,9 @@ def config4():
     n_tok = 100
     results = {}
     for batch in (1, 8):
-        dur = (2 + (syn.hash_uniform(f"c4.dur{batch}", (batch, n_tok), 0, 1) * 9).floor().clamp(max=8)).long()
+        dur = _durations(syn, batch, n_tok)
         out_lens = dur.sum(1)
         T = int(out_lens.max())
-        T += T % 2
         ex = {"spk_vec": syn.hash_uniform("c4.spk", (batch, 16)).to(dev), "txt_enc": syn.hash_uniform("c4.txt", (batch, 520, n_tok)).to(dev),
               "dur": dur.to(dev), "f0": syn.hash_uniform("c4.f0", (batch, T), 0, 1).to(dev),
               "energy_avg": syn.hash_uniform("c4.en", (batch, T), 0, 1).to(dev), "out_lens": out_lens.to(dev)}
@@ -140,10 +147,9 @@ def config4():
         print("\nReference `decoders.RADMMMFlow.infer` (unmodified, staged copy) on the host cores, fp32, sigma 0.8:\n")
         print("| B | frames | ms/call | frames/s | GPU graph speed-up (bf16) |\n|---|---|---|---|---|")
         for batch in (1, 8):
-            dur = (2 + (syn.hash_uniform(f"c4.dur{batch}", (batch, n_tok), 0, 1) * 9).floor().clamp(max=8)).long()
+            dur = _durations(syn, batch, n_tok)
             out_lens = dur.sum(1)
             T = int(out_lens.max())
-            T += T % 2
             spk, txt = syn.hash_uniform("c4.spk", (batch, 16)), syn.hash_uniform("c4.txt", (batch, 520, n_tok))
             f0, en = syn.hash_uniform("c4.f0", (batch, T), 0, 1), syn.hash_uniform("c4.en", (batch, T), 0, 1)
             acc = syn.hash_uniform("c4.acc", (batch, 8))
@@ -169,7 +175,7 @@ def config4():
         print("| B | frames | autocast | ms/call | frames/s | this package (graph, bf16) speed-up |\n|---|---|---|---|---|---|")
         gdec = rdec.to(dev)
         for batch in (1, 8):
-            dur = (2 + (syn.hash_uniform(f"c4.dur{batch}", (batch, n_tok), 0, 1) * 9).floor().clamp(max=8)).long()
+            dur = _durations(syn, batch, n_tok)
             out_lens = dur.sum(1)
             T = int(out_lens.max())
             spk, txt = syn.hash_uniform("c4.spk", (batch, 16)).to(dev), syn.hash_uniform("c4.txt", (batch, 520, n_tok)).to(dev)
