@@ -13,91 +13,123 @@ namespace {
 
 constexpr int ROWS = 8;   // query frames (warps) per CTA
 
-__global__ void __launch_bounds__(ROWS * 32) soft_attention_kernel(
+// Forward: FROWS query frames per CTA (one warp each for the softmax), then ALL threads of the CTA -- one per text-encoding
+// channel -- do the context matmul for those frames.  Round 1 ran 8 frames per 256-thread CTA: every CTA re-read all keys
+// (42 KB) and the whole text encoding (270 KB at Dt=520, T2=130) from L2 for 8 frames, the channel loop took 3 passes with
+// the last one 3 % full, and each inner step needed 8 scalar shared loads: 283 us at B=8, T1=800.  Now 16 frames, the
+// attention rows transposed in shared memory so a step is 4 x LDS.128 + 1 LDG per 16 FMAs, and a block of
+// round_up(Dt, 32) threads so the channel loop is one pass.
+constexpr int FROWS = 16;
+
+__global__ void __launch_bounds__(1024) soft_attention_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ prior,
     const int* __restrict__ in_lens, float* __restrict__ attn, float* __restrict__ attn_logprob,
     const float* __restrict__ txt_enc, float* __restrict__ context, int Ca, int T1, int T2, int Dt, float temp) {
     extern __shared__ float sm[];
     float* ks = sm;                          // [Ca][T2]
-    float* qs = ks + (size_t)Ca * T2;        // [ROWS][Ca]
-    float* as = qs + ROWS * Ca;              // [ROWS][T2]  attention rows
-    const int b = blockIdx.y, t1_0 = blockIdx.x * ROWS;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float* qs = ks + (size_t)Ca * T2;        // [FROWS][Ca]
+    float* as = qs + FROWS * Ca;             // [FROWS][T2]  attention rows
+    float* ast = sm + (((size_t)Ca * T2 + (size_t)FROWS * Ca + (size_t)FROWS * T2 + 3) & ~(size_t)3);   // [T2][FROWS] transposed, 16-byte aligned
+    const int b = blockIdx.y, t1_0 = blockIdx.x * FROWS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x;
     const float* kb = k + (long long)b * Ca * T2;
-    for (int i = tid; i < Ca * T2; i += ROWS * 32) ks[i] = kb[i];
-    for (int i = tid; i < ROWS * Ca; i += ROWS * 32) {
+    for (int i = tid; i < Ca * T2; i += nthr) ks[i] = kb[i];
+    for (int i = tid; i < FROWS * Ca; i += nthr) {
         const int r = i / Ca, c = i % Ca, t1 = t1_0 + r;
         qs[i] = (t1 < T1) ? q[((long long)b * Ca + c) * T1 + t1] : 0.0f;
     }
     __syncthreads();
     const int t1 = t1_0 + wid;
     const int len = min(in_lens[b], T2);
-    float* arow = as + (size_t)wid * T2;
-    if (t1 < T1) {
-        // logits
-        float mx = -INFINITY;
-        for (int t2 = lane; t2 < T2; t2 += 32) {
-            float d = 0.0f;
-            for (int c = 0; c < Ca; ++c) {
-                const float df = qs[wid * Ca + c] - ks[c * T2 + t2];
-                d = fmaf(df, df, d);
+    if (wid < FROWS) {
+        float* arow = as + (size_t)wid * T2;
+        if (t1 < T1) {
+            // logits
+            float mx = -INFINITY;
+            for (int t2 = lane; t2 < T2; t2 += 32) {
+                float d = 0.0f;
+                for (int c = 0; c < Ca; ++c) {
+                    const float df = qs[wid * Ca + c] - ks[c * T2 + t2];
+                    d = fmaf(df, df, d);
+                }
+                const float lg = -temp * d;
+                arow[t2] = lg;
+                mx = fmaxf(mx, lg);
             }
-            const float lg = -temp * d;
-            arow[t2] = lg;
-            mx = fmaxf(mx, lg);
-        }
-        const long long orow = ((long long)b * T1 + t1) * T2;
-        if (prior != nullptr) {
-            // log_softmax over ALL T2 keys (padded ones included, as the reference does), then + log(prior + 1e-8)
+            const long long orow = ((long long)b * T1 + t1) * T2;
+            if (prior != nullptr) {
+                // log_softmax over ALL T2 keys (padded ones included, as the reference does), then + log(prior + 1e-8)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            float se = 0.0f;
-            for (int t2 = lane; t2 < T2; t2 += 32) se += expf(arow[t2] - mx);
-            se = warp_sum(se);
-            const float lse = mx + logf(se);
-            for (int t2 = lane; t2 < T2; t2 += 32) arow[t2] = arow[t2] - lse + logf(prior[orow + t2] + 1e-8f);
-        }
-        // attn_logprob = pre-mask copy; softmax over the unmasked keys
-        float m2 = -INFINITY;
-        for (int t2 = lane; t2 < T2; t2 += 32) {
-            const float v = arow[t2];
-            attn_logprob[orow + t2] = v;
-            if (t2 < len) m2 = fmaxf(m2, v);
-        }
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float se = 0.0f;
+                for (int t2 = lane; t2 < T2; t2 += 32) se += expf(arow[t2] - mx);
+                se = warp_sum(se);
+                const float lse = mx + logf(se);
+                for (int t2 = lane; t2 < T2; t2 += 32) arow[t2] = arow[t2] - lse + logf(prior[orow + t2] + 1e-8f);
+            }
+            // attn_logprob = pre-mask copy; softmax over the unmasked keys
+            float m2 = -INFINITY;
+            for (int t2 = lane; t2 < T2; t2 += 32) {
+                const float v = arow[t2];
+                attn_logprob[orow + t2] = v;
+                if (t2 < len) m2 = fmaxf(m2, v);
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-        float s2 = 0.0f;
-        for (int t2 = lane; t2 < T2; t2 += 32) {
-            const float e = (t2 < len) ? expf(arow[t2] - m2) : 0.0f;
-            arow[t2] = e;
-            s2 += e;
-        }
-        s2 = warp_sum(s2);
-        const float inv = 1.0f / s2;
-        for (int t2 = lane; t2 < T2; t2 += 32) {
-            const float a = arow[t2] * inv;
-            arow[t2] = a;
-            attn[orow + t2] = a;
+            for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+            float s2 = 0.0f;
+            for (int t2 = lane; t2 < T2; t2 += 32) {
+                const float e = (t2 < len) ? expf(arow[t2] - m2) : 0.0f;
+                arow[t2] = e;
+                s2 += e;
+            }
+            s2 = warp_sum(s2);
+            const float inv = 1.0f / s2;
+            for (int t2 = lane; t2 < T2; t2 += 32) {
+                const float a = arow[t2] * inv;
+                arow[t2] = a;
+                attn[orow + t2] = a;
+            }
+        } else {
+            for (int t2 = lane; t2 < T2; t2 += 32) arow[t2] = 0.0f;       // frames past T1: zero weights, nothing stored
         }
     }
     if (txt_enc == nullptr) return;
     __syncthreads();
-    // context[b, d, t1] = sum_t2 txt_enc[b, d, t2] * attn[t1, t2]; thread = (row r, channel slice): coalesced over t1 is
-    // impossible with 8 rows, so lanes run over channels and the ROWS frames are written as one 32-byte segment.
+    for (int i = tid; i < FROWS * T2; i += nthr) {
+        const int r = i / T2, t2 = i - r * T2;
+        ast[t2 * FROWS + r] = as[i];
+    }
+    __syncthreads();
+    // context[b, d, t1_0 .. t1_0+15] = sum_t2 txt_enc[b, d, t2] * attn[t1, t2]: one thread per channel d, 16 accumulators;
+    // the thread walks its own txt_enc row (32-byte sectors stay in L1 across 8 steps), the weights are broadcast LDS.128
     const float* tb = txt_enc + (long long)b * Dt * T2;
-    for (int d = tid; d < Dt; d += ROWS * 32) {
-        float acc[ROWS];
+    for (int d = tid; d < Dt; d += nthr) {
+        float acc[FROWS];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) acc[r] = 0.0f;
+        for (int r = 0; r < FROWS; ++r) acc[r] = 0.0f;
         const float* trow = tb + (long long)d * T2;
         for (int t2 = 0; t2 < len; ++t2) {
             const float tv = __ldg(trow + t2);
+            const float4* w4 = reinterpret_cast<const float4*>(ast + t2 * FROWS);
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(tv, as[r * T2 + t2], acc[r]);
+            for (int j = 0; j < FROWS / 4; ++j) {
+                const float4 w = w4[j];
+                acc[4 * j + 0] = fmaf(tv, w.x, acc[4 * j + 0]);
+                acc[4 * j + 1] = fmaf(tv, w.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(tv, w.z, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(tv, w.w, acc[4 * j + 3]);
+            }
         }
+        float* o = context + ((long long)b * Dt + d) * T1 + t1_0;
+        if (t1_0 + FROWS <= T1 && (T1 & 3) == 0) {
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r)
-            if (t1_0 + r < T1) context[((long long)b * Dt + d) * T1 + t1_0 + r] = acc[r];
+            for (int j = 0; j < FROWS / 4; ++j)
+                reinterpret_cast<float4*>(o)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < FROWS; ++r)
+                if (t1_0 + r < T1) o[r] = acc[r];
+        }
     }
 }
 
@@ -233,13 +265,22 @@ int soft_attention(const float* q, const float* k, const float* prior, const int
                    float temperature, cudaStream_t st) {
     RADMMM_REQUIRE(B > 0 && Ca > 0 && T1 > 0 && T2 > 0, "soft_attention: bad sizes");
     RADMMM_REQUIRE(txt_enc == nullptr || context != nullptr, "soft_attention: context output missing");
-    const size_t smem = sizeof(float) * ((size_t)Ca * T2 + (size_t)ROWS * Ca + (size_t)ROWS * T2);
+    // ks + qs + as, rounded to 16 bytes so that the transposed copy can be read with LDS.128, + ast
+    const size_t head = ((size_t)Ca * T2 + (size_t)FROWS * Ca + (size_t)FROWS * T2 + 3) & ~(size_t)3;
+    const size_t smem = sizeof(float) * (head + (size_t)FROWS * T2);
     RADMMM_REQUIRE(smem <= 220 * 1024, "soft_attention: T2=%d keys do not fit in shared memory", T2);
-    if (smem > 48 * 1024)
-        RADMMM_CUDA(cudaFuncSetAttribute(soft_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(T1, ROWS), B);
-    soft_attention_kernel<<<grid, ROWS * 32, smem, st>>>(q, k, prior, in_lens, attn, attn_logprob, txt_enc, context, Ca,
-                                                         T1, T2, Dt, temperature);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        RADMMM_CUDA(cudaFuncSetAttribute(soft_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set[dev & 63] = true;
+    }
+    int threads = FROWS * 32;                                   // one warp per frame; one thread per text channel if more
+    if (txt_enc != nullptr && Dt > threads) threads = (int)round_up(Dt < 1024 ? Dt : 1024, 32);
+    dim3 grid(cdiv(T1, FROWS), B);
+    soft_attention_kernel<<<grid, threads, smem, st>>>(q, k, prior, in_lens, attn, attn_logprob, txt_enc, context, Ca,
+                                                       T1, T2, Dt, temperature);
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }
