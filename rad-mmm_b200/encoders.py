@@ -162,3 +162,86 @@ class ConvLSTMLinear(nn.Module):
         if self.use_linear:
             x = self.dense(x.transpose(1, 2)).transpose(1, 2)
         return x
+
+
+class BottleneckLayer(nn.Module):
+    """attribute_predictors.py:27-51: weight-normed ConvNorm(in_dim -> in_dim / reduction_factor, k) on the masked input,
+    re-masked, LeakyReLU (or ReLU).  ``norm='instancenorm'`` is not covered (no shipped predictor config uses it)."""
+
+    def __init__(self, in_dim, reduction_factor=16, norm="weightnorm", non_linearity="leakyrelu", kernel_size=3,
+                 use_partial_padding=True):
+        super().__init__()
+        if norm != "weightnorm":
+            raise NotImplementedError("radmmm_b200.encoders.BottleneckLayer: only norm='weightnorm' (the shipped configs)")
+        self.reduction_factor = reduction_factor
+        self.out_dim = int(in_dim / reduction_factor)
+        self.kernel_size = kernel_size
+        if self.reduction_factor > 1:
+            self.projection_fn = _ConvNormHolder(in_dim, self.out_dim, kernel_size)
+            self.non_linearity = nn.LeakyReLU() if non_linearity == "leakyrelu" else nn.ReLU()
+
+    def forward(self, x, mask):
+        if self.reduction_factor > 1:
+            m = mask.unsqueeze(1).to(x.dtype)
+            conv = self.projection_fn.conv
+            x = F.conv1d(x, _weight(conv), conv.bias, padding=(self.kernel_size - 1) // 2) * m      # ConvNorm.forward(signal, mask)
+            x = self.non_linearity(x)
+        return x
+
+
+class ConvLSTMLinearDAP(nn.Module):
+    """attribute_predictors.py:142-197 (f0 / energy / voiced / duration predictors of configs/RADMMM_*model_config.yaml):
+    bottleneck -> [speaker (accent) embedding concat] -> ConvLSTMLinear.  Same constructor, ``forward`` / ``infer``
+    signatures and ``state_dict`` keys; the target transforms are attribute_predictors.py:64-126 without their
+    ``assert ...item()`` host syncs."""
+
+    def __init__(self, n_speaker_dim=16, n_accent_dim=0, in_dim=512, out_dim=1, reduction_factor=16, n_backbone_layers=2,
+                 n_hidden=256, kernel_size=3, p_dropout=0.25, target_scale=1, target_offset=0, log_target=False,
+                 lstm_type: Optional[str] = "bilstm", use_speaker_embedding=True, use_accent_embedding=False,
+                 normalize_target=False, normalization_type=None):
+        super().__init__()
+        self.target_scale, self.target_offset, self.log_target = target_scale, target_offset, log_target
+        self.normalize_target, self.normalization_type = normalize_target, normalization_type
+        self.use_speaker_embedding = bool(use_speaker_embedding)
+        self.use_accent_embedding = bool(use_accent_embedding)
+        self.bottleneck_layer = BottleneckLayer(in_dim=in_dim, reduction_factor=reduction_factor)
+        backbone_in = self.bottleneck_layer.out_dim + (n_speaker_dim if use_speaker_embedding else 0) + \
+            (n_accent_dim if use_accent_embedding else 0)
+        self.feat_pred_fn = ConvLSTMLinear(in_dim=backbone_in, out_dim=out_dim, n_layers=n_backbone_layers, n_channels=n_hidden,
+                                           kernel_size=kernel_size, p_dropout=p_dropout, lstm_type=lstm_type)
+
+    def tx_data(self, x, x_mean=None, x_std=None):
+        if self.normalize_target:
+            if self.normalization_type == "norm_lin_space":
+                x = torch.log(x - (x_mean / x_std)[:, None] + 10) / 3          # attribute_predictors.py:71-79 (precedence as written)
+            elif self.normalization_type == "norm_log_space":
+                x = ((x - x_mean[:, None, None]) / x_std[:, None, None] + 5) / 10
+            return x
+        x = x * self.target_scale + self.target_offset
+        return torch.log(x + 1) if self.log_target else x
+
+    def inv_tx_data(self, x, x_mean=None, x_std=None):
+        if self.normalize_target:
+            if self.normalization_type == "norm_lin_space" and x_mean is not None and x_std is not None:
+                x = (torch.exp(x * 3) - 10) * x_std + x_mean
+            elif self.normalization_type == "norm_log_space" and x_mean is not None and x_std is not None:
+                x = (x * 10 - 5) * x_std[:, None, None] + x_mean[:, None, None]
+            return x
+        if self.log_target:
+            x = torch.exp(x) - 1
+        return (x - self.target_offset) / self.target_scale
+
+    def forward(self, x_target, text_enc, spk_emb, lens, x_mean=None, x_std=None, accent_emb=None):
+        if x_target is not None:
+            x_target = self.tx_data(x_target, x_mean, x_std)
+        ln = _lens_tensor(lens, text_enc.device)
+        mask = torch.arange(text_enc.shape[2], device=text_enc.device)[None, :] < ln[:, None]
+        context = self.bottleneck_layer(text_enc, mask)
+        if self.use_speaker_embedding:
+            context = torch.cat((context, spk_emb[..., None].expand(-1, -1, text_enc.shape[2])), 1)
+        if self.use_accent_embedding:
+            context = torch.cat((context, accent_emb[..., None].expand(-1, -1, text_enc.shape[2])), 1)
+        return {"x_hat": self.feat_pred_fn(context, ln), "x": x_target}
+
+    def infer(self, text_enc, spk_emb, lens, x_mean=None, x_std=None, accent_emb=None):
+        return self.inv_tx_data(self.forward(None, text_enc, spk_emb, lens, accent_emb=accent_emb)["x_hat"], x_mean, x_std)

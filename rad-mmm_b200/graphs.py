@@ -49,17 +49,22 @@ class GraphedTrainStep:
     ``reducer``: the ``BucketedGradReducer`` of a multi-GPU run (its ``finish`` -- the bucketed all-reduce -- is captured
     after ``backward``); single-process runs get a private gradient arena.  ``after_backward`` (optional) is called inside
     the captured region after that.  The loss follows ``RADMMMLoss.forward`` (loss.py:518-528):
-    ``n_elements = floor(sum(out_lens) / n_group_size)``.
+    ``n_elements = floor(sum(out_lens) / n_group_size)``.  ``extra_loss(static_inputs)`` (optional) returns a scalar that is
+    added to the flow loss before the single backward pass -- the text encoder and attribute predictors of the reference's
+    joint training (tts_lightning_modules.py:643-686); pass their parameters as ``extra_params`` (and a ``reducer`` built over
+    a module that contains them when running on several GPUs).  The returned loss is the flow loss alone.
     """
 
     def __init__(self, decoder, example: Dict[str, torch.Tensor], sigma: float = 1.0, warmup: int = 3,
-                 after_backward: Optional[Callable[[], None]] = None, reducer=None):
+                 after_backward: Optional[Callable[[], None]] = None, reducer=None,
+                 extra_loss: Optional[Callable[[Dict[str, torch.Tensor]], torch.Tensor]] = None, extra_params=()):
         dev = next(decoder.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("radmmm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         self.decoder, self.sigma, self.after_backward = decoder, sigma, after_backward
+        self.extra_loss = extra_loss
         self.arena = grad_arena(decoder, reducer)
-        self.params = [p for p in decoder.parameters() if p.requires_grad]
+        self.params = [p for p in decoder.parameters() if p.requires_grad] + [p for p in extra_params if p.requires_grad]
         self.static = {k: example[k].detach().to(dev).clone() for k in _INPUT_KEYS if example.get(k) is not None}
         self.frames = int(self.static["mel"].shape[2])
         self.group = decoder.n_group_size
@@ -86,7 +91,10 @@ class GraphedTrainStep:
         lens_g = torch.div(st["out_lens"], self.group, rounding_mode="floor")
         loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g, self.sigma,
                              n_elements=L.n_elements_like_reference(st["out_lens"], self.group))
-        loss.backward()
+        total = loss
+        if self.extra_loss is not None:        # joint training (config 3): encoder / predictor losses share the backward pass
+            total = loss + self.extra_loss(st)
+        total.backward()
         self.arena.finish()                    # multi-GPU: the bucketed all-reduce; always: re-arm the arena
         if self.after_backward is not None:
             self.after_backward()

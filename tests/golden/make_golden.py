@@ -380,6 +380,19 @@ def encoder_case():
     out.update({"cll_sd." + k: v for k, v in sd2.items()})
     out.update(cll_x=c.detach(), cll_y=z.detach(), cll_g=g2, cll_dx=c.grad, cll_dv1=cll.convolutions[1].conv.weight_v.grad,
                cll_dwhh_r=cll.bilstm.weight_hh_l0_reverse_orig.grad, cll_ddense=cll.dense.weight.grad, lens=lens)
+    import attribute_predictors as AP
+    dap = AP.ConvLSTMLinearDAP(n_speaker_dim=4, in_dim=64, out_dim=1, reduction_factor=4, n_backbone_layers=2, n_hidden=32,
+                               kernel_size=3, p_dropout=0.1, log_target=True).eval()
+    sd3 = _seeded_state(dap, "dap")
+    te = syn.hash_uniform("dap.txt", (3, 64, 29)).requires_grad_(True)
+    spk = syn.hash_uniform("dap.spk", (3, 4))
+    tgt = syn.hash_uniform("dap.tgt", (3, 1, 29), 0.0, 4.0)
+    res = dap(tgt, te, spk, C.SequenceLength(lens))
+    g3 = syn.hash_uniform("dap.g", tuple(res["x_hat"].shape))
+    (res["x_hat"] * g3).sum().backward()
+    out.update({"dap_sd." + k: v for k, v in sd3.items()})
+    out.update(dap_txt=te.detach(), dap_spk=spk, dap_tgt=tgt, dap_xhat=res["x_hat"].detach(), dap_x=res["x"].detach(), dap_g=g3,
+               dap_dtxt=te.grad, dap_dbott=dap.bottleneck_layer.projection_fn.conv.weight_v.grad)
     npz("encoder.npz", **out)
 
 

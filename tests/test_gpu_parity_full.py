@@ -579,3 +579,25 @@ def test_batched_conv_lstm_linear_vs_reference():
     for name, p in (("cll_dv1", net.convolutions[1].conv.weight_v), ("cll_dwhh_r", net.bilstm.weight_hh_l0_reverse_orig),
                     ("cll_ddense", net.dense.weight)):
         close(p.grad, gd[name], 5e-4 * max(1.0, gd[name].abs().max().item()), what=name)
+
+
+def test_attribute_predictor_vs_reference():
+    """encoders.ConvLSTMLinearDAP (attribute_predictors.py:142-197: bottleneck + speaker embedding + ConvLSTMLinear, log
+    target) against the unmodified reference class: outputs, transformed target, input and bottleneck gradients."""
+    from radmmm_b200.common import SequenceLength
+    from radmmm_b200.encoders import ConvLSTMLinearDAP
+    gd = gold("encoder.npz")
+    dap = ConvLSTMLinearDAP(n_speaker_dim=4, in_dim=64, out_dim=1, reduction_factor=4, n_backbone_layers=2, n_hidden=32,
+                            kernel_size=3, p_dropout=0.1, log_target=True).eval()
+    dap.load_state_dict(_sub(gd, "dap_sd."), strict=True)
+    dap = dap.to(DEV)
+    te = gd["dap_txt"].to(DEV).requires_grad_(True)
+    res = dap(gd["dap_tgt"].to(DEV), te, gd["dap_spk"].to(DEV), SequenceLength(gd["lens"].to(DEV)))
+    (res["x_hat"] * gd["dap_g"].to(DEV)).sum().backward()
+    close(res["x_hat"], gd["dap_xhat"], 2e-4, what="predictor x_hat")
+    close(res["x"], gd["dap_x"], 1e-6, what="predictor target transform")
+    close(te.grad, gd["dap_dtxt"], 5e-4 * max(1.0, gd["dap_dtxt"].abs().max().item()), what="predictor d text_enc")
+    close(dap.bottleneck_layer.projection_fn.conv.weight_v.grad, gd["dap_dbott"],
+          5e-4 * max(1.0, gd["dap_dbott"].abs().max().item()), what="predictor d bottleneck weight")
+    back = dap.inv_tx_data(res["x"])
+    close(back, gd["dap_tgt"], 1e-5, what="inverse target transform")
