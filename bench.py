@@ -525,6 +525,62 @@ def optimizer_bench(dev, pk, build, resident, host, valid_frames, timed, args):
     return out
 
 
+def joint_training_bench(dev, dec, resident, reducer, world, timed, valid_frames, frames, args):
+    """BASELINE.json config 3: the decoder step JOINTLY with the text encoder and the four attribute predictors
+    (configs/RADMMM_{f0,energy,vpred,duration}model_config.yaml: ConvLSTMLinearDAP, in_dim 520, 3 backbone layers, hidden 256,
+    k=5, dropout 0.5, spectral-normed bi-LSTM), one backward pass, everything in ONE CUDA graph; on several GPUs the encoder /
+    predictor gradients travel in their own bucket next to the decoder's nine.  Frame-level predictors (f0, energy, voiced) read
+    the frame-level text encoding (the batch's `context`), the duration predictor the token-level encoder output."""
+    import torch.distributed as dist
+    from radmmm_b200.ddp import BucketedGradReducer
+    from radmmm_b200.encoders import ConvLSTMLinearDAP, Encoder
+    from radmmm_b200.graphs import GraphedTrainStep
+    B = resident["mel"].shape[0]
+    n_tok = max(8, frames // 6)
+    mk = lambda: ConvLSTMLinearDAP(n_speaker_dim=16, in_dim=520, out_dim=1, reduction_factor=16, n_backbone_layers=3,   # noqa: E731
+                                   n_hidden=256, kernel_size=5, p_dropout=0.5)
+    aux = torch.nn.ModuleDict({"encoder": Encoder(3, 520, 5, lstm_norm_fn="spectral"), "f0": mk(), "energy": mk(), "voiced": mk(),
+                               "duration": mk()}).to(dev).train()
+    if world > 1:
+        for p in aux.parameters():
+            dist.broadcast(p.data, 0)
+    gen = torch.Generator().manual_seed(11)
+    txt_emb = torch.randn(B, 520, n_tok, generator=gen).to(dev)
+    in_lens = torch.clamp(resident["out_lens"] // 6, min=8, max=n_tok)
+    tgt = {k: torch.rand(B, 1, frames, generator=gen).to(dev) for k in ("f0", "energy", "voiced")}
+    dur_tgt = (torch.rand(B, 1, n_tok, generator=gen) * 8 + 2).to(dev)
+    spk = resident["spk_vecs"]
+
+    def masked_mse(x_hat, x, lens):
+        m = (torch.arange(x.shape[2], device=dev)[None, :] < lens[:, None])[:, None].float()
+        return (((x_hat - x) * m) ** 2).sum() / m.sum().clamp(min=1)
+
+    def extra_loss(st):
+        text_enc = aux["encoder"](txt_emb, in_lens).transpose(1, 2)
+        loss = 0.0
+        for k in ("f0", "energy", "voiced"):
+            r = aux[k](tgt[k], st["context"], spk, st["out_lens"])
+            loss = loss + masked_mse(r["x_hat"], r["x"], st["out_lens"])
+        r = aux["duration"](dur_tgt, text_enc, spk, in_lens)
+        return loss + masked_mse(r["x_hat"], r["x"], in_lens)
+
+    aux_reducer = BucketedGradReducer(aux, bucket_key=lambda name: "aux") if world > 1 else None
+    g = GraphedTrainStep(dec, resident, reducer=reducer, extra_loss=extra_loss, extra_params=list(aux.parameters()),
+                         after_backward=(aux_reducer.finish if aux_reducer is not None else None))
+    for _ in range(3):
+        g(resident)
+    ms = timed(lambda: g(resident), max(5, args.steps // 2))
+    n_aux = sum(p.numel() for p in aux.parameters())
+    out = {"ms_per_step": ms, "value": world * valid_frames / (ms * 1e-3), "unit": UNIT, "aux_parameters": n_aux,
+           "aux_grad_nonzero": bool(sum(float(p.grad.abs().sum()) for p in aux.parameters() if p.grad is not None) > 0),
+           "note": "decoder train step + text encoder (3 conv + bi-LSTM) + f0 / energy / voiced / duration predictors "
+                   f"(radmmm_b200.encoders, {n_tok} tokens), one backward, one CUDA graph"
+                   + ("; encoder / predictor gradients all-reduced in a 10th bucket" if world > 1 else "")}
+    del g
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     from radmmm_b200 import _native as N
@@ -654,14 +710,29 @@ def run_ours(args):
         w0, reducer.world = reducer.world, 1                       # local gradients only: no collective is issued
         train_step(dec, resident, reducer)
         reducer.world = w0
-        worst, gmax = 0.0, 0.0
+        worst, gmax, per_bucket, worst_param = 0.0, 0.0, {}, None
         for k, b in reducer.buckets.items():
             parts = [torch.empty_like(b["flat"]) for _ in range(world)]
             dist.all_gather(parts, b["flat"].contiguous())
             mean = torch.stack(parts).double().mean(0)
-            worst = max(worst, float((got[k].double() - mean).abs().max()))
+            diff = (got[k].double() - mean).abs()
+            per_bucket[k] = float(diff.max())
+            if per_bucket[k] > worst:
+                worst = per_bucket[k]
+                at = int(diff.argmax())
+                for name, off, p in zip(b["names"], b["offsets"], b["params"]):
+                    if off <= at < off + p.numel():
+                        worst_param = name
             gmax = max(gmax, float(mean.abs().max()))
+        # run-to-run noise of the local gradients themselves (fp32 atomics in the bias / 1x1 reductions): a second local step
+        local1 = {k: b["flat"].clone() for k, b in reducer.buckets.items()}
+        reducer.world = 1
+        train_step(dec, resident, reducer)
+        reducer.world = w0
+        noise = max(float((local1[k].double() - b["flat"].double()).abs().max()) for k, b in reducer.buckets.items())
         allreduce_check = {"max_abs_diff": worst, "max_abs_grad": gmax, "buckets": len(reducer.buckets),
+                           "per_bucket_max_abs_diff": per_bucket, "worst_parameter": worst_param,
+                           "local_run_to_run_max_abs_diff": noise,
                            "bytes_per_step": reducer.bytes_per_step(),
                            "note": "gradients of the captured step (bucketed NCCL AVG inside the CUDA graph) vs all_gather + "
                                    "mean of the ranks' local gradients of the same step, fp64 compare"}
@@ -743,6 +814,13 @@ def run_ours(args):
 
     # ---- rank 0, N = 1 only: parity-grade mode beside the headline, measured errors, HBM-bound kernels, front end, CPU arm
     extras = {}
+    if (world == 1 and not args.quick) or args.config3:
+        # config 3.  On several GPUs only with --config3 (all ranks take part: the encoder / predictor gradients are a 10th
+        # all-reduce bucket); the default multi-GPU line stays the plain decoder step the driver's scaling run expects.
+        try:
+            extras["joint_training"] = joint_training_bench(dev, dec, resident, reducer, world, timed, valid_frames, frames, args)
+        except Exception as exc:
+            extras["joint_training"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if world == 1 and not args.quick:
         if gstep is not None:
             del gstep
@@ -872,6 +950,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0, help="reference arm: utterances (default: --batch, the same config)")
     ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames (default: --frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config3", action="store_true", help="also time the joint step with text encoder + attribute predictors (BASELINE config 3) at N > 1")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (no parity-mode / HBM-kernel / front-end / CPU sections)")
     ap.add_argument("--eager", action="store_true", help="skip the CUDA-graph capture; time the eager module path only")
     args = ap.parse_args()

@@ -230,6 +230,12 @@ int radmmm_spline_linear_backward(const float* z1, const float* q, const int32_t
 int radmmm_stft_mel(const float* audio, const float* mel_basis, float* mel, float* magnitude_or_null, int B, int S,
                     int n_fft, int hop, int n_mel, float clip, void* stream);
 
+/* The same with the mel basis' row supports: support (n_mel x 2 int32: first / last non-zero bin of every row, written by
+ * radmmm_mel_support once per basis) lets a CTA read ~9 weights per mel row instead of scanning n_fft/2+1. */
+int radmmm_mel_support(const float* mel_basis, int n_mel, int n_bins, int32_t* support, void* stream);
+int radmmm_stft_mel_sparse(const float* audio, const float* mel_basis, const int32_t* support, float* mel,
+                           float* magnitude_or_null, int B, int S, int n_fft, int hop, int n_mel, float clip, void* stream);
+
 /* Soft attention (common.py:1259-1276) and the context matmul (tts_lightning_modules.py:670).
  * q (B,Ca,T1), k (B,Ca,T2) are the projected queries/keys; prior (B,T1,T2) or NULL; in_lens (B).
  * attn, attn_logprob: (B,1,T1,T2).  If txt_enc (B,Dt,T2) != NULL also writes context (B,Dt,T1). */

@@ -95,6 +95,8 @@ SIGNATURES = {
     "radmmm_spline_linear_forward": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _i, _fp]),
     "radmmm_spline_linear_backward": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _fp]),
     "radmmm_stft_mel": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
+    "radmmm_mel_support": (_i, [_fp, _i, _i, _fp, _fp]),
+    "radmmm_stft_mel_sparse": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
     "radmmm_soft_attention": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
     "radmmm_soft_attention_backward": (_i, [_fp] * 12 + [_i, _i, _i, _i, _i, _f, _fp]),
     "radmmm_mas_workspace_bytes": (_ll, [_i, _i, _i]),

@@ -108,9 +108,20 @@ class TacotronSTFT(torch.nn.Module):
         b, s = y.shape
         st = self.stft_fn
         mel = torch.empty(b, self.n_mel_channels, s // st.hop_length + 1, device=y.device)
-        N.check(lib.radmmm_stft_mel(N.fptr(y), N.fptr(self.mel_basis), N.fptr(mel), None, b, s, st.filter_length,
-                                    st.hop_length, self.n_mel_channels, 1e-5, N.stream()))
+        N.check(lib.radmmm_stft_mel_sparse(N.fptr(y), N.fptr(self.mel_basis), N.ptr(self._support()), N.fptr(mel), None, b, s,
+                                           st.filter_length, st.hop_length, self.n_mel_channels, 1e-5, N.stream()))
         return mel
+
+    def _support(self) -> torch.Tensor:
+        """[first, last] non-zero bin of every mel-basis row (int32, on the basis' device); recomputed when the buffer is
+        replaced or modified (load_state_dict, .to())."""
+        key = (self.mel_basis.data_ptr(), self.mel_basis._version)
+        if getattr(self, "_support_key", None) != key:
+            sup = torch.empty(self.n_mel_channels, 2, dtype=torch.int32, device=self.mel_basis.device)
+            N.check(N.lib().radmmm_mel_support(N.fptr(self.mel_basis), self.n_mel_channels, self.mel_basis.shape[1], N.ptr(sup),
+                                               N.stream()))
+            self._support_buf, self._support_key = sup, key
+        return self._support_buf
 
 
 class BatchedFrontEnd(torch.nn.Module):

@@ -266,7 +266,14 @@ int radmmm_spline_linear_backward(const float* z1, const float* q, const int32_t
 }
 int radmmm_stft_mel(const float* audio, const float* mel_basis, float* mel, float* magnitude_or_null, int B, int S,
                     int n_fft, int hop, int n_mel, float clip, void* stream) {
-    return stft_mel(audio, mel_basis, mel, magnitude_or_null, B, S, n_fft, hop, n_mel, clip, ST(stream));
+    return stft_mel(audio, mel_basis, nullptr, mel, magnitude_or_null, B, S, n_fft, hop, n_mel, clip, ST(stream));
+}
+int radmmm_mel_support(const float* mel_basis, int n_mel, int n_bins, int32_t* support, void* stream) {
+    return mel_support(mel_basis, n_mel, n_bins, support, ST(stream));
+}
+int radmmm_stft_mel_sparse(const float* audio, const float* mel_basis, const int32_t* support, float* mel,
+                           float* magnitude_or_null, int B, int S, int n_fft, int hop, int n_mel, float clip, void* stream) {
+    return stft_mel(audio, mel_basis, support, mel, magnitude_or_null, B, S, n_fft, hop, n_mel, clip, ST(stream));
 }
 long long radmmm_mas_workspace_bytes(int B, int T1, int T2) { return mas_workspace_bytes(B, T1, T2); }
 int radmmm_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, float* out, int B, int T1, int T2,

@@ -53,8 +53,9 @@ int spline_linear(const float* z1, const float* q, const int* lens, float* z1_ou
                   float lo, float hi, int inverse, cudaStream_t st);
 int spline_linear_bwd(const float* z1, const float* q, const int* lens, const float* dz1_out, const float* dlog_s, float* dz1, float* dq,
                       int B, int Ch, int Tp, int n_bins, float lo, float hi, cudaStream_t st);
-int stft_mel(const float* audio, const float* mel_basis, float* mel, float* mag, int B, int S, int n_fft, int hop,
-             int n_mel, float clip, cudaStream_t st);
+int mel_support(const float* mel_basis, int n_mel, int n_bins, int* support, cudaStream_t st);
+int stft_mel(const float* audio, const float* mel_basis, const int* support, float* mel, float* mag, int B, int S, int n_fft,
+             int hop, int n_mel, float clip, cudaStream_t st);
 long long mas_workspace_bytes(int B, int T1, int T2);
 int mas_width1(const float* attn, const int* in_lens, const int* out_lens, float* out, int B, int T1, int T2, int is_log,
                void* workspace, long long workspace_bytes, cudaStream_t st);

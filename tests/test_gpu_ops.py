@@ -327,6 +327,27 @@ def test_stft_mel(tag, sr):
     # ragged / odd length input, single utterance
     y2 = y[:1, :5000]
     close(stft.mel_spectrogram(y2.to(DEV)), ofe.mel_spectrogram(y2, sr=sr), 2e-4)
+    # the module uses the row-support table (radmmm_stft_mel_sparse); the dense entry point must agree (the lanes sum the
+    # same products in a different order), and the table must be the basis' true support
+    lib = N.lib()
+    yd = y.to(DEV).contiguous()
+    dense = torch.empty_like(mel)
+    N.check(lib.radmmm_stft_mel(N.fptr(yd), N.fptr(stft.mel_basis), N.fptr(dense), None, 2, n, 1024, 256, 80, 1e-5, N.stream()))
+    close(dense, mel, 1e-5, what="dense vs sparse mel")
+    sup = stft._support().cpu()
+    nz = stft.mel_basis.cpu() != 0
+    for m in range(80):
+        idx = nz[m].nonzero().flatten()
+        assert (int(sup[m, 0]), int(sup[m, 1])) == ((int(idx[0]), int(idx[-1])) if len(idx) else (1, 0))
+    # a basis with an all-zero row and a row with two separate runs still works (the range covers both runs)
+    odd = stft.mel_basis.clone()
+    odd[3] = 0
+    odd[5, 400] = 0.25
+    stft2 = ap.TacotronSTFT(1024, 256, 1024, 80, sr, 0.0, 8000.0).to(DEV)
+    stft2.mel_basis.copy_(odd)
+    mag_full, _ = stft2.stft_fn.transform(yd)
+    want = torch.log(torch.clamp(torch.matmul(odd.double(), mag_full.double()), min=1e-5))
+    close(stft2.mel_spectrogram(yd), want, 2e-4, what="mel with an irregular basis")
 
 
 # ------------------------------------------------------------------------------------------------ attention
