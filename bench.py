@@ -555,14 +555,31 @@ def joint_training_bench(dev, dec, resident, reducer, world, timed, valid_frames
         m = (torch.arange(x.shape[2], device=dev)[None, :] < lens[:, None])[:, None].float()
         return (((x_hat - x) * m) ** 2).sum() / m.sum().clamp(min=1)
 
+    for m in aux.modules():
+        if hasattr(m, "precision"):
+            m.precision = "bf16"               # like the decoder: bf16 contractions, cluster-resident LSTM recurrence
+    # four independent chains (three frame-level predictors; encoder -> duration predictor), each on its own stream: their
+    # bi-LSTM recurrences are T sequential steps on 32 CTAs each, so they run next to each other and next to the decoder
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+
     def extra_loss(st):
-        text_enc = aux["encoder"](txt_emb, in_lens).transpose(1, 2)
-        loss = 0.0
-        for k in ("f0", "energy", "voiced"):
-            r = aux[k](tgt[k], st["context"], spk, st["out_lens"])
-            loss = loss + masked_mse(r["x_hat"], r["x"], st["out_lens"])
-        r = aux["duration"](dur_tgt, text_enc, spk, in_lens)
-        return loss + masked_mse(r["x_hat"], r["x"], in_lens)
+        cur = torch.cuda.current_stream(dev)
+        parts = []
+        for i, k in enumerate(("f0", "energy", "voiced")):
+            streams[i].wait_stream(cur)
+            with torch.cuda.stream(streams[i]):
+                r = aux[k](tgt[k], st["context"], spk, st["out_lens"])
+                parts.append(masked_mse(r["x_hat"], r["x"], st["out_lens"]))
+        streams[3].wait_stream(cur)
+        with torch.cuda.stream(streams[3]):
+            text_enc = aux["encoder"](txt_emb, in_lens).transpose(1, 2)
+            r = aux["duration"](dur_tgt, text_enc, spk, in_lens)
+            parts.append(masked_mse(r["x_hat"], r["x"], in_lens))
+
+        def join():
+            for s_ in streams:
+                cur.wait_stream(s_)
+        return parts, join
 
     aux_reducer = BucketedGradReducer(aux, bucket_key=lambda name: "aux") if world > 1 else None
     g = GraphedTrainStep(dec, resident, reducer=reducer, extra_loss=extra_loss, extra_params=list(aux.parameters()),

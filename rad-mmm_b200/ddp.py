@@ -64,6 +64,7 @@ class BucketedGradReducer:
             b["views"] = [b["flat"][off:off + p.numel()].view_as(p) for p, off in zip(b["params"], b["offsets"])]
             b["pending"] = len(b["params"])
             b["launched"] = False
+            b["streams"] = {}
             for p, v in zip(b["params"], b["views"]):
                 p.register_post_accumulate_grad_hook(self._make_hook(key, v))
         self.reset()
@@ -101,6 +102,7 @@ class BucketedGradReducer:
         for b in self.buckets.values():
             b["pending"] = len(b["params"])
             b["launched"] = False
+            b["streams"] = {}
             for p, v, off in zip(b["params"], b["views"], b["offsets"]):
                 self._view_of[id(p)] = v
                 self._slot_of[p.data_ptr()] = (b["flat"], off, tuple(p.shape), p)
@@ -112,17 +114,38 @@ class BucketedGradReducer:
             if b["launched"]:          # a new backward began without finish() (single-process eager use): re-arm
                 b["launched"] = False
                 b["pending"] = len(b["params"])
+                b["streams"] = {}
             g = param.grad
             if g.data_ptr() != view.data_ptr():      # gradient did not land in the bucket: copy it in and alias
                 view.copy_(g)
                 param.grad = view
+            if g.is_cuda:
+                # the stream this gradient was finalised on.  AccumulateGrad nodes keep the stream of their FIRST use (the
+                # hooks keep them alive), so parameters of one bucket can be finalised on different streams; the collective
+                # must wait for all of them, not only for the stream the last hook happens to run on
+                cs = torch.cuda.current_stream(g.device)
+                b["streams"][cs.cuda_stream] = cs
             b["pending"] -= 1
             if b["pending"] == 0:
                 self._launch(b)
         return hook
 
+    def _join_streams(self, b: dict):
+        """Make the current stream wait for every stream a gradient of this bucket was finalised on."""
+        if not b["streams"]:
+            return
+        dev = b["flat"].device
+        cur = torch.cuda.current_stream(dev)
+        for key, s in b["streams"].items():
+            if key != cur.cuda_stream:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                cur.wait_event(ev)
+        b["streams"] = {}
+
     def _launch(self, b: dict):
         b["launched"] = True
+        self._join_streams(b)
         if self.world > 1:
             op = dist.ReduceOp.SUM
             if self.average:

@@ -49,8 +49,9 @@ class GraphedTrainStep:
     ``reducer``: the ``BucketedGradReducer`` of a multi-GPU run (its ``finish`` -- the bucketed all-reduce -- is captured
     after ``backward``); single-process runs get a private gradient arena.  ``after_backward`` (optional) is called inside
     the captured region after that.  The loss follows ``RADMMMLoss.forward`` (loss.py:518-528):
-    ``n_elements = floor(sum(out_lens) / n_group_size)``.  ``extra_loss(static_inputs)`` (optional) returns a scalar that is
-    added to the flow loss before the single backward pass -- the text encoder and attribute predictors of the reference's
+    ``n_elements = floor(sum(out_lens) / n_group_size)``.  ``extra_loss(static_inputs)`` (optional) returns a scalar -- or
+    ``(list of scalars, join)`` when it computes them on side streams; ``join()`` must make the current stream wait for
+    those -- that is added to the flow loss before the single backward pass -- the text encoder and attribute predictors of the reference's
     joint training (tts_lightning_modules.py:643-686); pass their parameters as ``extra_params`` (and a ``reducer`` built over
     a module that contains them when running on several GPUs).  The returned loss is the flow loss alone.
     """
@@ -86,14 +87,23 @@ class GraphedTrainStep:
         # kernels wrote into (no copy, no accumulate) and ``p.grad`` ends up aliasing the persistent arena
         for p in self.params:
             p.grad = None
+        extra_parts, extra_join = None, None
+        if self.extra_loss is not None:
+            # BEFORE the decoder: a callable that works on side streams (it returns (list of scalar losses, join)) then
+            # overlaps the whole decoder forward, and its backward -- enqueued on the same side streams -- the decoder backward
+            r = self.extra_loss(st)
+            extra_parts, extra_join = r if isinstance(r, tuple) else ([r], None)
         out = dec(st["mel"], st["spk_vecs"], st["context"], SequenceLength(st["out_lens"], self.frames),
                   f0=st.get("f0"), energy_avg=st.get("energy_avg"), accent_vecs=st.get("accent_vecs"))
         lens_g = torch.div(st["out_lens"], self.group, rounding_mode="floor")
         loss, _ = L.flow_nll(out["z_mel"], out["log_det_W_list"], out["log_s_list"], lens_g, self.sigma,
                              n_elements=L.n_elements_like_reference(st["out_lens"], self.group))
         total = loss
-        if self.extra_loss is not None:        # joint training (config 3): encoder / predictor losses share the backward pass
-            total = loss + self.extra_loss(st)
+        if extra_parts is not None:            # joint training (config 3): encoder / predictor losses share the backward pass
+            if extra_join is not None:
+                extra_join()
+            for part in extra_parts:
+                total = total + part
         total.backward()
         self.arena.finish()                    # multi-GPU: the bucketed all-reduce; always: re-arm the arena
         if self.after_backward is not None:
