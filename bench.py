@@ -283,10 +283,11 @@ def hbm_rooflines(dev, pk, batch, frames):
         0.0005, st)))
     dattn, dlogp, dcx = f32(B, 1, T1, T2), f32(B, 1, T1, T2), f32(B, Dt, T1)
     dq, dk, dtxt = torch.empty_like(qq), torch.empty_like(kk), torch.empty_like(txt)
+    att_ws = torch.empty(lib.radmmm_soft_attention_backward_workspace_bytes(B, T1, T2), dtype=torch.uint8, device=dev)
     timed("soft_attention_backward (+ context matmul)", att_bytes + B * (2 * T1 * T2 + Dt * T1) * 4,
           lambda: N.check(lib.radmmm_soft_attention_backward(
               N.fptr(qq), N.fptr(kk), N.fptr(prior), N.ptr(in_lens), N.fptr(attn), N.fptr(dattn), N.fptr(dlogp), N.fptr(txt),
-              N.fptr(dcx), N.fptr(dq), N.fptr(dk), N.fptr(dtxt), B, Ca, T1, T2, Dt, 0.0005, st)))
+              N.fptr(dcx), N.fptr(dq), N.fptr(dk), N.fptr(dtxt), B, Ca, T1, T2, Dt, 0.0005, N.ptr(att_ws), att_ws.numel(), st)))
     return out
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RADMMM_ABI_VERSION 2
+#define RADMMM_ABI_VERSION 3
 
 /* precision of the WN contractions */
 #define RADMMM_MODE_F32 0     /* fp32 FFMA, exact-parity path                                   */
@@ -245,11 +245,13 @@ int radmmm_soft_attention(const float* q, const float* k, const float* prior, co
 
 /* Backward of radmmm_soft_attention: gradients w.r.t. the projected queries / keys (dq (B,Ca,T1), dk (B,Ca,T2)) and, when
  * the context matmul was fused (txt_enc/dcontext != NULL), w.r.t. txt_enc (dtxt (B,Dt,T2)).  dattn / dlogprob are the
- * incoming gradients of attn / attn_logprob (either may be NULL). */
+ * incoming gradients of attn / attn_logprob (either may be NULL).  workspace: device scratch of
+ * radmmm_soft_attention_backward_workspace_bytes(B,T1,T2) bytes (the gradient w.r.t. the squared distances). */
+long long radmmm_soft_attention_backward_workspace_bytes(int B, int T1, int T2);
 int radmmm_soft_attention_backward(const float* q, const float* k, const float* prior, const int32_t* in_lens,
                                    const float* attn, const float* dattn, const float* dlogprob, const float* txt_enc,
                                    const float* dcontext, float* dq, float* dk, float* dtxt, int B, int Ca, int T1, int T2,
-                                   int Dt, float temperature, void* stream);
+                                   int Dt, float temperature, void* workspace, long long workspace_bytes, void* stream);
 
 /* Monotonic alignment search, width 1 (alignment.py:31-59 `mas_width1`), batched the way its caller loops
  * (tts_lightning_modules.py:270-284 `binarize_attention`): attn (B,1,T1,T2) soft attention (probabilities; is_log != 0:

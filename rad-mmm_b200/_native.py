@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RADMMM_B200_LIB") or os.path.join(_HERE, "libradmmm_b200.so")   # env override: A/B builds
 MAX_LAYERS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 ROW_GAP = 16
 MODE_F32, MODE_BF16, MODE_BF16X3 = 0, 1, 2
 MODES = {"fp32": MODE_F32, "bf16": MODE_BF16, "bf16x3": MODE_BF16X3}
@@ -98,7 +98,8 @@ SIGNATURES = {
     "radmmm_mel_support": (_i, [_fp, _i, _i, _fp, _fp]),
     "radmmm_stft_mel_sparse": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
     "radmmm_soft_attention": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _f, _fp]),
-    "radmmm_soft_attention_backward": (_i, [_fp] * 12 + [_i, _i, _i, _i, _i, _f, _fp]),
+    "radmmm_soft_attention_backward_workspace_bytes": (_ll, [_i, _i, _i]),
+    "radmmm_soft_attention_backward": (_i, [_fp] * 12 + [_i, _i, _i, _i, _i, _f, _fp, _ll, _fp]),
     "radmmm_mas_workspace_bytes": (_ll, [_i, _i, _i]),
     "radmmm_mas_width1": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _ll, _fp]),
     "radmmm_attention_ctc": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp]),

@@ -717,10 +717,12 @@ class _SoftAttentionFunction(torch.autograd.Function):
         use_txt = ctx.has_txt and dctx is not None
         dq, dk = torch.empty_like(q), torch.empty_like(k)
         dtxt = torch.empty_like(txt) if use_txt else None
+        nws = lib.radmmm_soft_attention_backward_workspace_bytes(b, t1, t2)
+        ws = torch.empty(nws, dtype=torch.uint8, device=q.device)
         N.check(lib.radmmm_soft_attention_backward(
             N.fptr(q), N.fptr(k), N.fptr(prior) if ctx.has_prior else None, N.ptr(in_lens), N.fptr(attn), N.fptr(dattn),
             N.fptr(dlogp), N.fptr(txt) if use_txt else None, N.fptr(dctx), N.fptr(dq), N.fptr(dk), N.fptr(dtxt), b, ca, t1, t2,
-            dt, ctx.temperature, N.stream()))
+            dt, ctx.temperature, N.ptr(ws), nws, N.stream()))
         return dq, dk, None, None, dtxt, None
 
 

@@ -291,12 +291,15 @@ int radmmm_soft_attention(const float* q, const float* k, const float* prior, co
                           ST(stream));
 }
 
+long long radmmm_soft_attention_backward_workspace_bytes(int B, int T1, int T2) {
+    return soft_attention_bwd_workspace_bytes(B, T1, T2);
+}
 int radmmm_soft_attention_backward(const float* q, const float* k, const float* prior, const int32_t* in_lens,
                                    const float* attn, const float* dattn, const float* dlogprob, const float* txt_enc,
                                    const float* dcontext, float* dq, float* dk, float* dtxt, int B, int Ca, int T1, int T2,
-                                   int Dt, float temperature, void* stream) {
+                                   int Dt, float temperature, void* workspace, long long workspace_bytes, void* stream) {
     return soft_attention_bwd(q, k, prior, in_lens, attn, dattn, dlogprob, txt_enc, dcontext, dq, dk, dtxt, B, Ca, T1, T2,
-                              Dt, temperature, ST(stream));
+                              Dt, temperature, workspace, workspace_bytes, ST(stream));
 }
 
 }  // extern "C"

@@ -65,8 +65,10 @@ int soft_attention(const float* q, const float* k, const float* prior, const int
                    float* attn_logprob, const float* txt_enc, float* context, int B, int Ca, int T1, int T2, int Dt,
                    float temperature, cudaStream_t st);
 
+long long soft_attention_bwd_workspace_bytes(int B, int T1, int T2);
 int soft_attention_bwd(const float* q, const float* k, const float* prior, const int* in_lens, const float* attn,
                        const float* dattn, const float* dlogprob, const float* txt_enc, const float* dcontext, float* dq,
-                       float* dk, float* dtxt, int B, int Ca, int T1, int T2, int Dt, float temperature, cudaStream_t st);
+                       float* dk, float* dtxt, int B, int Ca, int T1, int T2, int Dt, float temperature, void* workspace,
+                       long long workspace_bytes, cudaStream_t st);
 
 }  // namespace radmmm
