@@ -776,27 +776,34 @@ __global__ void __launch_bounds__(256) wn_bwd_staged_kernel(const float* __restr
 // bytes in flight at once, several CTAs per SM overlapping their load / compute / store phases.  dW stays in its
 // [tap][ci] layout; the dot product and dv read it transposed out of shared memory (stride ksize: conflict-free for 5).
 // Needs 16-byte aligned rows (ci_total % 4 == 0 and a single source block); other shapes use the staged kernel above.
+// KS (taps) is a template parameter so that i -> (ci, k) is a multiplication, and the dW rows ([k][ci], as the weight-grad GEMM
+// writes them) are staged with a row pitch of ci_total + 8 floats: with the natural pitch (a multiple of 32 banks) the KS
+// consecutive threads that share one ci hit ONE bank in both passes -- a 5-way conflict that made this kernel LSU-bound at
+// ~2.7 TB/s; the padded pitch keeps the bulk copies 16-byte aligned and spreads them over 8k + ci banks.
+constexpr int WNB_PAD = 8;
+template <int KS>
 __global__ void __launch_bounds__(256) wn_bwd_bulk_kernel(const float* __restrict__ src, long long ld, long long tap_stride,
                                                           const float* __restrict__ v, const float* __restrict__ g,
-                                                          const float* __restrict__ norm, int ci_total, int ksize,
+                                                          const float* __restrict__ norm, int ci_total,
                                                           float* __restrict__ dv, float* __restrict__ dg) {
     extern __shared__ __align__(128) float wsm[];
     const int co = blockIdx.x;
-    const int per_co = ci_total * ksize;
+    const int per_co = ci_total * KS;
+    const int pitch = ci_total + WNB_PAD;
     float* sv = wsm;                 // [ci][k]  (the layout of v)
-    float* sd = wsm + per_co;        // [k][ci]  (the layout of dW)
+    float* sd = wsm + per_co;        // [k][pitch]  (the layout of dW, padded rows)
     __shared__ __align__(8) unsigned long long bar;
     const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const unsigned bytes_v = (unsigned)per_co * 4u, bytes_row = (unsigned)ci_total * 4u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes_v + bytes_row * ksize) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes_v + bytes_row * KS) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((unsigned)__cvta_generic_to_shared(sv)), "l"(v + (long long)co * per_co), "r"(bytes_v), "r"(bar_addr) : "memory");
-        for (int k = 0; k < ksize; ++k)
+        for (int k = 0; k < KS; ++k)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"((unsigned)__cvta_generic_to_shared(sd + k * ci_total)), "l"(src + k * tap_stride + (long long)co * ld),
+                         ::"r"((unsigned)__cvta_generic_to_shared(sd + k * pitch)), "l"(src + k * tap_stride + (long long)co * ld),
                            "r"(bytes_row), "r"(bar_addr) : "memory");
     }
     __syncthreads();                                   // the barrier is initialised before anyone polls it
@@ -814,8 +821,8 @@ __global__ void __launch_bounds__(256) wn_bwd_bulk_kernel(const float* __restric
         float part = 0.0f;               // <= 8 products per fp32 partial, then fp64
         int n = 0;
         for (int i = threadIdx.x; i < per_co; i += 256) {
-            const int ci = i / ksize, k = i - ci * ksize;
-            part = fmaf(sd[k * ci_total + ci], sv[i], part);
+            const int ci = i / KS, k = i - ci * KS;
+            part = fmaf(sd[k * pitch + ci], sv[i], part);
             if (++n == 8) { dot += (double)part; part = 0.0f; n = 0; }
         }
         dot += (double)part;
@@ -840,8 +847,8 @@ __global__ void __launch_bounds__(256) wn_bwd_bulk_kernel(const float* __restric
         float r[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int i = 4 * i4 + e, ci = i / ksize, k = i - ci * ksize;
-            r[e] = sc * (sd[k * ci_total + ci] - sv[i] * coef);
+            const int i = 4 * i4 + e, ci = i / KS, k = i - ci * KS;
+            r[e] = sc * (sd[k * pitch + ci] - sv[i] * coef);
         }
         o[i4] = make_float4(r[0], r[1], r[2], r[3]);
     }
@@ -854,8 +861,10 @@ int wn_bwd(const float* src0, long long ld0, long long tap0, int n_ci0, const fl
     static const bool bulk_on = []() { const char* e = getenv("RADMMM_B200_WNBWD_BULK"); return !(e && e[0] == '0'); }();
     const bool aligned = src1 == nullptr && n_ci0 == ci_total && (ci_total & 3) == 0 && (ld0 & 3) == 0 && (tap0 & 3) == 0 &&
                          ((reinterpret_cast<uintptr_t>(src0) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0;
-    if (bulk_on && aligned && smem <= 48 * 1024) {
-        wn_bwd_bulk_kernel<<<n_co, 256, smem, st>>>(src0, ld0, tap0, v, g, norm, ci_total, ksize, dv, dg);
+    const size_t smem_bulk = smem + sizeof(float) * (size_t)ksize * WNB_PAD;
+    if (bulk_on && aligned && smem_bulk <= 48 * 1024 && (ksize == 5 || ksize == 1)) {
+        if (ksize == 5) wn_bwd_bulk_kernel<5><<<n_co, 256, smem_bulk, st>>>(src0, ld0, tap0, v, g, norm, ci_total, dv, dg);
+        else wn_bwd_bulk_kernel<1><<<n_co, 256, smem_bulk, st>>>(src0, ld0, tap0, v, g, norm, ci_total, dv, dg);
     } else if (smem <= 48 * 1024) {
         wn_bwd_staged_kernel<<<n_co, 256, smem, st>>>(src0, ld0, tap0, n_ci0, src1, ld1, tap1, v, g, norm, ci_total, ksize, dv, dg);
     } else {

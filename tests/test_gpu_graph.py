@@ -100,3 +100,31 @@ def test_graphed_infer_matches_eager():
         assert mel.shape == ref.shape
         for i, n in enumerate(ex["out_lens"].tolist()):
             close(mel[i, :, :n // 2 * 2], ref[i, :, :n // 2 * 2], 1e-6, what="graphed infer mel")
+
+
+@pytest.mark.gpu
+def test_reducer_collective_waits_for_every_finalising_stream():
+    """Regression (found by bench.py's allreduce_check at N=2): parameters of one bucket can be finalised on different
+    streams (AccumulateGrad nodes keep the stream of their first use); the bucket's collective must wait for all of them, not
+    only for the stream the last hook runs on.  Here the weight's gradient lands in the bucket on a slow stream s1, the bias'
+    on s2; whatever s2 does after the bucket is launched must see the weight's gradient."""
+    from radmmm_b200.ddp import BucketedGradReducer
+    lin = torch.nn.Linear(512, 512).to("cuda")
+    red = BucketedGradReducer(lin, force_single=True)
+    b = red.buckets["rest"]
+    hooks = {n: list(p._post_accumulate_grad_hooks.values())[0] for n, p in lin.named_parameters()}
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        torch.cuda._sleep(40_000_000)                      # ~20 ms: s1 is far behind
+        lin.weight.grad = torch.full_like(lin.weight, 3.0)
+        hooks["weight"](lin.weight)                        # copies into the bucket ON s1
+    with torch.cuda.stream(s2):
+        lin.bias.grad = torch.full_like(lin.bias, 5.0)
+        hooks["bias"](lin.bias)                            # last parameter: launches the bucket from s2
+        seen = b["flat"].clone()                           # stands for the collective: enqueued on s2 right after the launch
+    torch.cuda.synchronize()
+    assert b["launched"] and not b["streams"]
+    assert float(seen[:lin.weight.numel()].min()) == 3.0, "the bucket was read before the weight gradient had landed"
+    assert float(seen[b["offsets"][1]:b["offsets"][1] + lin.bias.numel()].min()) == 5.0
+    red.finish()
