@@ -3,12 +3,12 @@
 # inside, allreduce_check), then a torch.profiler timeline of one replay on rank 0.  Hard timeouts throughout.
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "N=$N exit $?"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --config3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "N=$N exit $?"
 python - "$N" <<'PY'
 import json, sys
 d = json.loads(open(f'gpurun_out/r2_bench_n{sys.argv[1]}.json').read().strip().splitlines()[-1])
 print('train ms', d['ms_per_step'], 'frames/s', d['value'], 'e2e ms', d['e2e']['ms_per_step'], 'eager ms', d['eager']['ms_per_step'], 'graph', d['graph']['captured'], d['graph']['error'])
-print('allreduce_check', json.dumps(d.get('allreduce_check')))
+c = d.get('allreduce_check') or {}; print('allreduce_check', c.get('max_abs_diff'), c.get('worst_parameter'), c.get('local_run_to_run_max_abs_diff')); print('joint', json.dumps(d.get('joint_training')))
 PY
 tail -n 5 gpurun_out/r2_bench_n$N.err | cut -c1-300
 echo "=== timeline N=$N"
