@@ -113,12 +113,15 @@ class ContextLSTMFunction(torch.autograd.Function):
         wta = ctx.wta                       # the transposed input weights the forward pass prepared
         dg_act = _cast(mode, dg)
         k8 = 8 * hid
-        # dX = dG . [W_ih_f; W_ih_r]  (row GEMM, K = 8H)
-        dx_rows = torch.empty(r, inp, device=dev)
-        N.check(lib.radmmm_conv_rows(mode, N.ptr(dg_act), k8, r * k8, N.ptr(wta), n8, inp * n8, 0, None, N.fptr(dx_rows),
-                                     inp, r, k8, inp, 1, 1, N.stream()))
-        dx = torch.empty(b, t, n_in, device=dev)
-        N.check(lib.radmmm_context_rows_backward(N.fptr(dx_rows), N.ptr(lens), b, t, n_in, N.fptr(dx), 0, N.stream()))
+        # dX = dG . [W_ih_f; W_ih_r]  (row GEMM, K = 8H) -- only when the input wants a gradient: in decoder-only training the
+        # LSTM input (text encoding, speaker vector, f0, energy) is data, and this GEMM sits on the step's exposed tail
+        dx = None
+        if ctx.needs_input_grad[2]:
+            dx_rows = torch.empty(r, inp, device=dev)
+            N.check(lib.radmmm_conv_rows(mode, N.ptr(dg_act), k8, r * k8, N.ptr(wta), n8, inp * n8, 0, None, N.fptr(dx_rows),
+                                         inp, r, k8, inp, 1, 1, N.stream()))
+            dx = torch.empty(b, t, n_in, device=dev)
+            N.check(lib.radmmm_context_rows_backward(N.fptr(dx_rows), N.ptr(lens), b, t, n_in, N.fptr(dx), 0, N.stream()))
         # dW_ih = dG^T X
         dwih = torch.empty(k8, inp, device=dev)
         N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dg_act), k8, r * k8, N.ptr(x_rows), inp, r * inp, N.fptr(dwih), inp,
