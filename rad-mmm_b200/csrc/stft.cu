@@ -1,7 +1,7 @@
 // Fused STFT -> magnitude -> mel filterbank -> log-clamp (audio_processing.py:137-154, 227-255).
 // The reference computes the STFT as a dense windowed-DFT convolution (2.1 MFLOP/frame); here each CTA runs
-// in-shared-memory radix-2 FFTs for FR consecutive frames (reflect padding and the periodic Hann window applied on
-// load, bit-reversed store), forms |X| in place and applies the (n_mel x n_bins) mel basis once for all FR frames so
+// in-shared-memory radix-2 FFTs for FR consecutive frames, two real frames per complex transform (reflect padding and the
+// periodic Hann window applied on load, bit-reversed store), splits the packed spectra into |X| per frame and applies the (n_mel x n_bins) mel basis once for all FR frames so
 // each basis element is read once per CTA.  HBM-bound by design: 256 new samples in + 80 values out per frame
 // (1344 B); the audio tile of a CTA is read once (overlapping frames are served from L1/L2).
 // The mel basis is triangular: row m is non-zero on one short run of bins (727 non-zeros of 80 x 513 for the shipped
@@ -15,7 +15,7 @@ namespace radmmm {
 
 namespace {
 
-constexpr int FR = 8;          // frames per CTA (64 KB of FFT buffers: dynamic shared memory)
+constexpr int FR = 8;          // frames per CTA: 4 complex FFTs of two real frames each (32 KB) + 16 KB of magnitudes
 constexpr int NT = 256;
 
 __device__ __forceinline__ int reflect_index(int j, int S) {
@@ -30,9 +30,11 @@ __global__ void __launch_bounds__(NT) stft_mel_kernel(const float* __restrict__ 
                                                       float* __restrict__ mag_out, int S, int hop, int n_frames, int n_mel,
                                                       float clip) {
     constexpr int NBINS = NFFT / 2 + 1;
+    constexpr int NP = FR / 2;                       // complex transforms per CTA: two REAL frames ride one complex FFT
     extern __shared__ float2 stft_smem[];
-    float2 (*buf)[NFFT] = reinterpret_cast<float2 (*)[NFFT]>(stft_smem);          // [FR][NFFT]
-    float2* tw = stft_smem + FR * NFFT;                                           // [NFFT / 2]
+    float2 (*buf)[NFFT] = reinterpret_cast<float2 (*)[NFFT]>(stft_smem);          // [NP][NFFT]: (frame 2p, frame 2p+1)
+    float2* tw = stft_smem + NP * NFFT;                                           // [NFFT / 2]
+    float (*mag)[NBINS + 3] = reinterpret_cast<float (*)[NBINS + 3]>(tw + NFFT / 2);   // [FR][NBINS + 3]
     const int b = blockIdx.y, f0 = blockIdx.x * FR, tid = threadIdx.x;
     const float* x = audio + (long long)b * S;
     for (int i = tid; i < NFFT / 2; i += NT) {
@@ -40,24 +42,23 @@ __global__ void __launch_bounds__(NT) stft_mel_kernel(const float* __restrict__ 
         sincospif(-2.0f * (float)i / (float)NFFT, &sn, &cs);
         tw[i] = make_float2(cs, sn);
     }
-    // load + window + bit-reverse
-    for (int fr = 0; fr < FR; ++fr) {
-        const int f = f0 + fr;
-        for (int i = tid; i < NFFT; i += NT) {
-            float v = 0.0f;
-            if (f < n_frames) {
-                const int j = reflect_index(f * hop + i - NFFT / 2, S);
-                const float win = 0.5f - 0.5f * cospif(2.0f * (float)i / (float)NFFT);   // periodic Hann
-                v = x[j] * win;
-            }
-            buf[fr][__brev((unsigned)i) >> (32 - LOG2N)] = make_float2(v, 0.0f);
+    // load + window + bit-reverse; frame 2p goes to the real part, frame 2p+1 to the imaginary part
+    for (int i = tid; i < NFFT; i += NT) {
+        const float win = 0.5f - 0.5f * cospif(2.0f * (float)i / (float)NFFT);   // periodic Hann
+        const int dst = __brev((unsigned)i) >> (32 - LOG2N);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int fa = f0 + 2 * p, fb = fa + 1;
+            const float va = (fa < n_frames) ? x[reflect_index(fa * hop + i - NFFT / 2, S)] * win : 0.0f;
+            const float vb = (fb < n_frames) ? x[reflect_index(fb * hop + i - NFFT / 2, S)] * win : 0.0f;
+            buf[p][dst] = make_float2(va, vb);
         }
     }
     __syncthreads();
     // iterative radix-2 decimation-in-time
     for (int s = 1; s <= LOG2N; ++s) {
         const int half = 1 << (s - 1);
-        for (int idx = tid; idx < FR * (NFFT / 2); idx += NT) {
+        for (int idx = tid; idx < NP * (NFFT / 2); idx += NT) {
             const int fr = idx / (NFFT / 2), j = idx % (NFFT / 2);
             const int k = j & (half - 1);
             const int i0 = ((j >> (s - 1)) << s) + k, i1 = i0 + half;
@@ -69,13 +70,20 @@ __global__ void __launch_bounds__(NT) stft_mel_kernel(const float* __restrict__ 
         }
         __syncthreads();
     }
-    // magnitude (into .x of the first NBINS entries)
-    for (int idx = tid; idx < FR * NBINS; idx += NT) {
-        const int fr = idx / NBINS, k = idx % NBINS;
-        const float2 v = buf[fr][k];
-        const float m = sqrtf(v.x * v.x + v.y * v.y);
-        buf[fr][k].x = m;
-        if (mag_out && f0 + fr < n_frames) mag_out[((long long)b * NBINS + k) * n_frames + f0 + fr] = m;
+    // split the packed spectrum Z = A + iB (A, B spectra of the two real frames):  A[k] = (Z[k] + conj Z[N-k]) / 2,
+    // B[k] = (Z[k] - conj Z[N-k]) / (2i); magnitudes of both
+    for (int idx = tid; idx < NP * NBINS; idx += NT) {
+        const int p = idx / NBINS, k = idx % NBINS;
+        const float2 z = buf[p][k], zc = buf[p][(NFFT - k) & (NFFT - 1)];
+        const float ar = 0.5f * (z.x + zc.x), ai = 0.5f * (z.y - zc.y);
+        const float br = 0.5f * (z.y + zc.y), bi = -0.5f * (z.x - zc.x);
+        const float ma = sqrtf(ar * ar + ai * ai), mb = sqrtf(br * br + bi * bi);
+        mag[2 * p][k] = ma;
+        mag[2 * p + 1][k] = mb;
+        if (mag_out) {
+            if (f0 + 2 * p < n_frames) mag_out[((long long)b * NBINS + k) * n_frames + f0 + 2 * p] = ma;
+            if (f0 + 2 * p + 1 < n_frames) mag_out[((long long)b * NBINS + k) * n_frames + f0 + 2 * p + 1] = mb;
+        }
     }
     __syncthreads();
     // mel: warp w handles rows w, w+8, ...
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(NT) stft_mel_kernel(const float* __restrict__ 
             const float wgt = __ldg(row + k);
             if (wgt != 0.0f) {
 #pragma unroll
-                for (int fr = 0; fr < FR; ++fr) acc[fr] = fmaf(wgt, buf[fr][k].x, acc[fr]);
+                for (int fr = 0; fr < FR; ++fr) acc[fr] = fmaf(wgt, mag[fr][k], acc[fr]);
             }
         }
         // lane fr ends up holding frame fr's sum: FR consecutive frames of one mel row leave as one 32-byte segment
@@ -135,7 +143,7 @@ int stft_mel(const float* audio, const float* mel_basis, const int* support, flo
     RADMMM_REQUIRE(hop > 0 && B > 0 && n_mel > 0, "stft_mel: bad sizes");
     const int n_frames = S / hop + 1;
     dim3 grid(cdiv(n_frames, FR), B);
-    constexpr size_t smem = sizeof(float2) * (FR * 1024 + 512);
+    constexpr size_t smem = sizeof(float2) * ((FR / 2) * 1024 + 512) + sizeof(float) * FR * (513 + 3);
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -601,3 +601,46 @@ def test_attribute_predictor_vs_reference():
           5e-4 * max(1.0, gd["dap_dbott"].abs().max().item()), what="predictor d bottleneck weight")
     back = dap.inv_tx_data(res["x"])
     close(back, gd["dap_tgt"], 1e-5, what="inverse target transform")
+
+
+def test_joint_step_with_predictor_on_a_side_stream():
+    """GraphedTrainStep(extra_loss=...) -- the joint training of config 3: a ConvLSTMLinearDAP predictor's loss, computed on a
+    side stream, shares the single backward pass inside the captured graph.  After a replay the decoder's gradients equal the
+    decoder-only eager step (the predictor does not touch the decoder) and the predictor's equal plain autograd of its loss."""
+    from radmmm_b200.encoders import ConvLSTMLinearDAP
+    from radmmm_b200.graphs import GraphedTrainStep
+    T = 64
+    bt = {k: v.to(DEV) for k, v in syn.synthetic_batch(2, T, tag="joint").items()}
+    dec = _decoder(2, "fp32")
+    _, want = _eager_grads(dec, bt, T)
+    torch.manual_seed(3)
+    dap = ConvLSTMLinearDAP(n_speaker_dim=16, in_dim=520, out_dim=1, reduction_factor=16, n_backbone_layers=2, n_hidden=32,
+                            kernel_size=3, p_dropout=0.0).to(DEV).eval()      # eval: the spectral-norm buffers stay put
+    tgt = syn.hash_uniform("joint.tgt", (2, 1, T), 0.0, 1.0).to(DEV)
+    side = torch.cuda.Stream()
+
+    def aux_loss(st):
+        r = dap(tgt, st["context"], st["spk_vecs"], st["out_lens"])
+        m = (torch.arange(T, device=DEV)[None, :] < st["out_lens"][:, None])[:, None].float()
+        return (((r["x_hat"] - r["x"]) * m) ** 2).sum() / m.sum()
+
+    def extra(st):
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            part = aux_loss(st)
+        return [part], lambda: cur.wait_stream(side)
+
+    step = GraphedTrainStep(dec, bt, extra_loss=extra, extra_params=list(dap.parameters()))
+    step(bt)
+    torch.cuda.synchronize()
+    got_aux = {n: p.grad.detach().clone() for n, p in dap.named_parameters()}
+    for n, p in dec.named_parameters():
+        if n in want:
+            close(p.grad, want[n], 2e-5 * max(1.0, want[n].abs().max().item()), what="decoder grad in the joint step: " + n)
+    for p in dap.parameters():
+        p.grad = None
+    aux_loss(bt).backward()
+    for n, p in dap.named_parameters():
+        close(got_aux[n], p.grad, 2e-5 * max(1.0, p.grad.abs().max().item()), what="predictor grad in the joint step: " + n)
+        assert float(p.grad.abs().sum()) > 0
