@@ -799,6 +799,9 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         const bool grouped = args.wgrad == 3;
         RADMMM_REQUIRE(!grouped || args.n_seg <= 4, "gemm_tc: at most 4 grouped weight-grad problems per launch");
         P.m_tiles = cdiv(M, BM);
+        // an odd number of 128-row tiles (the LSTM's dW_ih: M = 8 x 528 = 33 tiles) would fall back to the 1-CTA kernel; one
+        // more all-zero tile (TMA zero-fills beyond M, the epilogue skips rows >= M) keeps it on CTA pairs: 59 -> ~30 us
+        if (P.m_tiles > 1 && (P.m_tiles & 1) && pair_mode_enabled()) P.m_tiles += 1;
         P.acc_segs = args.wgrad == 2;
         P.taps = P.acc_segs ? 1 : args.n_seg;
         P.k_blocks_total = args.R / BK;
