@@ -707,7 +707,11 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
 
     // output tiling
     const int N = args.epi.N;
-    const int n_pad = (int)round_up(N, 128);
+    int n_pad = (int)round_up(N, 128);
+    // weight-grads whose width is an odd number of 128-column tiles (the context / LSTM input weights: N = 1088) take one more
+    // all-zero half tile so that they run 256-wide: MN-major 128-wide tiles stream twice the operand bytes per tensor cycle
+    // and run at less than half the rate (see the weight-grad tiling note below)
+    if (args.wgrad && !x3 && N >= 512 && n_pad % 256 != 0) n_pad += 128;
     int BN = (!x3 && n_pad % 256 == 0) ? 256 : 128;
     if (args.wgrad && BN == 256 && args.split_k < 1) {
         // Weight-grad tiling.  128-wide tiles (160 pair tiles for the 5-tap dilated conv: plain stores, no split-K) looked
