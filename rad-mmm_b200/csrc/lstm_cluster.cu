@@ -29,17 +29,26 @@ namespace radmmm {
 
 namespace {
 
-constexpr int CL = 16;                 // CTAs per cluster = row slices of W_hh
-constexpr int UPC = 33;                // hidden units per CTA (16 x 33 = 528 >= H)
-constexpr int SLOT = 34;               // unit slots per CTA in the K ordering (33 units + 1 zero slot: K = 544 = 34 k-tiles)
-constexpr int KP = CL * SLOT;          // 544
-constexpr int KT = KP / 16;            // 34 k-tiles
+constexpr int UPC = 33;                // hidden units per CTA
 constexpr int MT = 9;                  // m-tiles per CTA: 4 * 33 = 132 gate rows -> 144
 constexpr int ROWS = MT * 16;          // 144
 constexpr int NT = 640;                // 20 warps (register allocation is per 4 warps: 640 threads -> 96 registers each);
-                                       // 18 of them hold W: 9 m-tiles x 2 k-halves (forward) / 17 x 2 m-tiles (backward)
-constexpr int TPW = KT / 2;            // 17 k-tiles per warp (forward)
-constexpr int HMAX = CL * UPC;         // 528
+                                       // forward: 18 of them hold W (9 m-tiles x 2 k-halves); backward: KT / 2 of them
+// Cluster geometry.  L16 (hidden <= 528: the decoder's context LSTM): 16 CTAs, 34 unit slots per CTA in the K ordering (33 units +
+// 1 zero slot: K = 544 = 34 k-tiles).  L4 (hidden <= 132: the attribute predictors' hidden-128 bi-LSTMs): 4 CTAs, 40 slots per CTA
+// (K = 160 = 10 k-tiles) -- the same kernels on a quarter of the SMs with 3 instead of 15 exchange partners.
+template <int CL_, int SLOT_>
+struct LC {
+    static constexpr int CL = CL_;             // CTAs per cluster = row slices of W_hh
+    static constexpr int SLOT = SLOT_;         // unit slots per CTA in the K ordering (>= UPC; the rest are zero columns)
+    static constexpr int KP = CL * SLOT;       // K of the recurrent product
+    static constexpr int KT = KP / 16;         // k-tiles
+    static constexpr int TPW = KT / 2;         // k-tiles per warp (forward: two K halves)
+    static constexpr int HMAX = CL * UPC;
+    static_assert(KP % 32 == 0 && TPW % 2 == 1 && SLOT >= UPC, "cluster geometry");
+};
+using L16 = LC<16, 34>;
+using L4 = LC<4, 40>;
 
 struct ClParams {
     const float* xproj;       // [R][8H]  W_ih x + b_ih + b_hh, columns [dir][gate i,f,g,o][H]
@@ -143,13 +152,15 @@ __device__ __forceinline__ float tanhf_(float x) {
 
 // K ordering shared by forward and backward: slot p in [0, 544) belongs to CTA p / 34; its unit is 33 * (p / 34) + p % 34 when
 // p % 34 < 33 and that unit exists, else the slot is a zero column.
+template <class C>
 __device__ __forceinline__ int slot_unit(int p, int H) {
-    const int j = p % SLOT, u = (p / SLOT) * UPC + j;
+    const int j = p % C::SLOT, u = (p / C::SLOT) * UPC + j;
     return (j < UPC && u < H) ? u : -1;
 }
 // local gate row r in [0, 144): unit j = r / 4 of this CTA, gate r % 4 (i, f, g, o); rows >= 132 are padding
+template <class C>
 __device__ __forceinline__ float whh_at(const float* __restrict__ Whh, int H, int rank, int r, int p) {
-    const int j = r >> 2, g = r & 3, unit = rank * UPC + j, col = slot_unit(p, H);
+    const int j = r >> 2, g = r & 3, unit = rank * UPC + j, col = slot_unit<C>(p, H);
     if (j >= UPC || unit >= H || col < 0) return 0.0f;
     return __ldg(Whh + (size_t)(g * H + unit) * H + col);
 }
@@ -157,18 +168,18 @@ __device__ __forceinline__ float whh_at(const float* __restrict__ Whh, int H, in
 // =========================================================================================================== forward
 // shared memory: [2 mbarriers | lens[32] | hs[2][NB][544][8] bf16 | part[2][144][8 NB] fp32 | hstage[NB][34][8] bf16 |
 //                 (x2) | cst[33 * 8 NB] fp32 | xps[3][4][33 * 8 NB] fp32 | itab[33 * 8 NB] int4 | stash[6][33 * 8 NB] fp32]
-template <bool TRACE>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_kernel(const ClParams p) {
+template <bool TRACE, class C>
+__global__ void __cluster_dims__(C::CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int H = p.H, NB = p.NB, NBN = 8 * NB, NIT = UPC * NBN;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     int* slen = reinterpret_cast<int*>(smem + 128);                                          // [32]
     __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem + 256);                       // [2][NB][KP][8]
-    float* part = reinterpret_cast<float*>(smem + 256 + (size_t)2 * NB * KP * 16);           // [2][ROWS][NBN]
+    float* part = reinterpret_cast<float*>(smem + 256 + (size_t)2 * NB * C::KP * 16);           // [2][ROWS][NBN]
     // hstage is double-buffered: the bulk copies of step s may still be reading it while step s+1 writes (they are known to
     // be complete once h_{s+1} of every peer has arrived, i.e. before step s+2 writes the same half again)
     __nv_bfloat16* hstage2 = reinterpret_cast<__nv_bfloat16*>(part + (size_t)2 * ROWS * NBN); // [2][NB][SLOT][8]
-    float* cst = reinterpret_cast<float*>(hstage2 + (size_t)2 * NB * SLOT * 8);              // [NIT]
+    float* cst = reinterpret_cast<float*>(hstage2 + (size_t)2 * NB * C::SLOT * 8);              // [NIT]
     float* xps = cst + NIT;                                                                   // [3][4][NIT]
     int4* itab = reinterpret_cast<int4*>(xps + (size_t)3 * 4 * NIT);                          // [NIT]
     float* stash = reinterpret_cast<float*>(itab + NIT);                                      // [6][NIT] values saved for backward
@@ -184,7 +195,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) slen[tid] = (tid < 8 * NB && n0 + tid < p.B) ? min(p.lens[n0 + tid], p.Tp) : 0;
-    for (int i = tid; i < 2 * NB * KP; i += NT) reinterpret_cast<uint4*>(hs)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0, zero slots
+    for (int i = tid; i < 2 * NB * C::KP; i += NT) reinterpret_cast<uint4*>(hs)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0, zero slots
     for (int i = tid; i < NIT; i += NT) cst[i] = 0.0f;
     // per-item constants (item it = j * NBN + n: unit j of this CTA, sequence n), so that the per-step gate code does no index
     // arithmetic: .x = length (0: nothing to do), .y = offset of (row of frame 0, this direction, this unit) in xproj / gates
@@ -200,16 +211,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
         itab[it] = e;
     }
     // W_hh slice -> A fragments (rows = local gate rows of m-tile `mt`, k = slots of this warp's K half)
-    uint32_t wf[TPW][4];
+    uint32_t wf[C::TPW][4];
     if (mma_warp) {
         const int r0 = mt * 16 + (lane >> 2), r1 = r0 + 8;
 #pragma unroll
-        for (int i = 0; i < TPW; ++i) {
-            const int c0 = (kh * TPW + i) * 16 + 2 * (lane & 3);
-            wf[i][0] = pack_bf16(whh_at(Whh, H, rank, r0, c0), whh_at(Whh, H, rank, r0, c0 + 1));
-            wf[i][1] = pack_bf16(whh_at(Whh, H, rank, r1, c0), whh_at(Whh, H, rank, r1, c0 + 1));
-            wf[i][2] = pack_bf16(whh_at(Whh, H, rank, r0, c0 + 8), whh_at(Whh, H, rank, r0, c0 + 9));
-            wf[i][3] = pack_bf16(whh_at(Whh, H, rank, r1, c0 + 8), whh_at(Whh, H, rank, r1, c0 + 9));
+        for (int i = 0; i < C::TPW; ++i) {
+            const int c0 = (kh * C::TPW + i) * 16 + 2 * (lane & 3);
+            wf[i][0] = pack_bf16(whh_at<C>(Whh, H, rank, r0, c0), whh_at<C>(Whh, H, rank, r0, c0 + 1));
+            wf[i][1] = pack_bf16(whh_at<C>(Whh, H, rank, r1, c0), whh_at<C>(Whh, H, rank, r1, c0 + 1));
+            wf[i][2] = pack_bf16(whh_at<C>(Whh, H, rank, r0, c0 + 8), whh_at<C>(Whh, H, rank, r0, c0 + 9));
+            wf[i][3] = pack_bf16(whh_at<C>(Whh, H, rank, r1, c0 + 8), whh_at<C>(Whh, H, rank, r1, c0 + 9));
         }
     }
     int tmax = 0;                                  // this chunk's longest sequence
@@ -235,24 +246,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     };
     fetch_xp(0);
     fetch_xp(1);
-    const uint32_t tx_bytes = (uint32_t)(CL * UPC * NB * 16);
+    const uint32_t tx_bytes = (uint32_t)(C::CL * UPC * NB * 16);
     // diagnostic phase timers of thread 0: [0] wait for h, [1] mat-vec, [2] cp.async wait + barrier, [3] gates, [4] barrier, [5] push
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
     auto lap = [&](int i) { if (TRACE && tid == 0) { const long long now = clock64(); tacc[i] += now - tlast; tlast = now; } };
 
     for (int s = 0; s < tmax; ++s) {
         const int cur = s & 1, prev = cur ^ 1;
-        __nv_bfloat16* hstage = hstage2 + (size_t)cur * NB * SLOT * 8;
+        __nv_bfloat16* hstage = hstage2 + (size_t)cur * NB * C::SLOT * 8;
         lap(5);
         if (s > 0) mbar_wait(&bars[prev], ((s - 1) >> 1) & 1);         // the 16 slices of h_{s-1} have landed in hs[prev]
         lap(0);
         // ---- recurrent mat-vec on the tensor cores: part[kh][row][n] = sum_{k in half kh} W[row][k] h_{s-1}[k][n]
         if (mma_warp) {
             for (int nb = 0; nb < NB; ++nb) {
-                const uint32_t hbase = smem_u32(hs + ((size_t)(prev * NB + nb) * KP + (size_t)kh * TPW * 16) * 8);
+                const uint32_t hbase = smem_u32(hs + ((size_t)(prev * NB + nb) * C::KP + (size_t)kh * C::TPW * 16) * 8);
                 float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i + 1 < TPW; i += 2) {
+                for (int i = 0; i + 1 < C::TPW; i += 2) {
                     uint32_t b0, b1, b2, b3;
                     ldmatrix_x4_trans(hbase + (uint32_t)(i * 16 + lane) * 16, b0, b1, b2, b3);
                     mma_bf16(acc0, wf[i], b0, b1);
@@ -260,8 +271,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
                 }
                 {
                     uint32_t b0, b1;
-                    ldmatrix_x2_trans(hbase + (uint32_t)((TPW - 1) * 16 + (lane & 15)) * 16, b0, b1);
-                    mma_bf16(acc0, wf[TPW - 1], b0, b1);
+                    ldmatrix_x2_trans(hbase + (uint32_t)((C::TPW - 1) * 16 + (lane & 15)) * 16, b0, b1);
+                    mma_bf16(acc0, wf[C::TPW - 1], b0, b1);
                 }
                 float* o = part + ((size_t)kh * ROWS + mt * 16 + (lane >> 2)) * NBN + nb * 8 + 2 * (lane & 3);
                 *reinterpret_cast<float2*>(o) = make_float2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
@@ -292,7 +303,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
                 float* sp = stash + it;
                 sp[0] = gi; sp[NIT] = gf; sp[2 * NIT] = gg; sp[3 * NIT] = go; sp[4 * NIT] = c; sp[5 * NIT] = h;
             }
-            hstage[((size_t)(n >> 3) * SLOT + j) * 8 + (n & 7)] = __float2bfloat16_rn(h);
+            hstage[((size_t)(n >> 3) * C::SLOT + j) * 8 + (n & 7)] = __float2bfloat16_rn(h);
         }
         auto write_saved = [&]() {             // each thread writes what it parked itself: no barrier needed
             if (p.probe & 1) return;
@@ -316,16 +327,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
         // ---- push this CTA's h slice into every CTA of the cluster (own copy included)
         if (tid == 0) mbar_expect_tx(&bars[cur], tx_bytes);
         if (p.bulk) {                          // ONE bulk copy of 33 units x 16 bytes per (tile, peer)
-            if (tid < CL * NB) {
-                const int peer = tid % CL, nb = tid / CL;
-                const uint32_t dst = smem_u32(hs + ((size_t)(cur * NB + nb) * KP + rank * SLOT) * 8);
-                bulk_copy_to_peer(mapa(dst, peer), smem_u32(hstage + (size_t)nb * SLOT * 8), UPC * 16, mapa(smem_u32(&bars[cur]), peer));
+            if (tid < C::CL * NB) {
+                const int peer = tid % C::CL, nb = tid / C::CL;
+                const uint32_t dst = smem_u32(hs + ((size_t)(cur * NB + nb) * C::KP + rank * C::SLOT) * 8);
+                bulk_copy_to_peer(mapa(dst, peer), smem_u32(hstage + (size_t)nb * C::SLOT * 8), UPC * 16, mapa(smem_u32(&bars[cur]), peer));
             }
         } else {                               // 16 bytes per (unit, tile, peer)
-            for (int i = tid; i < UPC * NB * CL; i += NT) {
-                const int peer = i % CL, rest = i / CL, j = rest % UPC, nb = rest / UPC;
-                const uint4 v = *reinterpret_cast<const uint4*>(hstage + ((size_t)nb * SLOT + j) * 8);
-                const uint32_t dst = smem_u32(hs + ((size_t)(cur * NB + nb) * KP + rank * SLOT + j) * 8);
+            for (int i = tid; i < UPC * NB * C::CL; i += NT) {
+                const int peer = i % C::CL, rest = i / C::CL, j = rest % UPC, nb = rest / UPC;
+                const uint4 v = *reinterpret_cast<const uint4*>(hstage + ((size_t)nb * C::SLOT + j) * 8);
+                const uint32_t dst = smem_u32(hs + ((size_t)(cur * NB + nb) * C::KP + rank * C::SLOT + j) * 8);
                 st_async_v4(mapa(dst, peer), mapa(smem_u32(&bars[cur]), peer), v);
             }
         }
@@ -335,7 +346,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
     }
     cp_async_wait_all();
     cluster_sync_all();                       // no CTA leaves while a peer could still push into its shared memory
-    if (TRACE && p.trace != nullptr && tid == 0 && blockIdx.x < 2 * CL)          // the trace buffer holds the first two clusters
+    if (TRACE && p.trace != nullptr && tid == 0 && blockIdx.x < 2 * C::CL)          // the trace buffer holds the first two clusters
         for (int i = 0; i < 6; ++i) p.trace[blockIdx.x * 8 + i] = (unsigned long long)tacc[i];
 }
 
@@ -348,14 +359,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_fwd_
 // shared memory: [2 mbarriers | lens[32] | recv[2][CL][NB][SLOT][8] fp32 | dgs[NB][144][8] bf16 | dcn[33 * 8 NB] fp32 |
 //                 sv[3][7][33 * 8 NB] fp32 | itab[33 * 8 NB] int4 | stash[4][33 * 8 NB] fp32 |
 //                 pstage[2][NB][544][8] fp32 (bulk exchange only)]
-template <bool TRACE>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_kernel(const ClParams p) {
+template <bool TRACE, class C>
+__global__ void __cluster_dims__(C::CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_kernel(const ClParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int H = p.H, NB = p.NB, NBN = 8 * NB, NIT = UPC * NBN;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     int* slen = reinterpret_cast<int*>(smem + 128);
     float* recv = reinterpret_cast<float*>(smem + 256);                                      // [2][CL][NB][SLOT][8]
-    __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(recv + (size_t)2 * CL * NB * SLOT * 8);   // [NB][ROWS][8]
+    __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(recv + (size_t)2 * C::CL * NB * C::SLOT * 8);   // [NB][ROWS][8]
     float* dcn = reinterpret_cast<float*>(dgs + (size_t)NB * ROWS * 8);                      // [NIT]
     float* sv = dcn + NIT;                                                                    // [3][7][NIT]
     int4* itab = reinterpret_cast<int4*>(sv + (size_t)3 * 7 * NIT);                           // [NIT]
@@ -365,7 +376,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* Whh = p.whh[dir];
     constexpr int MTW = 2;                    // m-tiles (of 16 unit slots) per warp
-    const bool mma_warp = warp < KT / MTW;    // 17 warps
+    const bool mma_warp = warp < C::KT / MTW;    // 17 warps
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -394,10 +405,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
 #pragma unroll
             for (int k = 0; k < MT; ++k) {
                 const int c0 = k * 16 + 2 * (lane & 3);
-                wf[a][k][0] = pack_bf16(whh_at(Whh, H, rank, c0, m0), whh_at(Whh, H, rank, c0 + 1, m0));
-                wf[a][k][1] = pack_bf16(whh_at(Whh, H, rank, c0, m1), whh_at(Whh, H, rank, c0 + 1, m1));
-                wf[a][k][2] = pack_bf16(whh_at(Whh, H, rank, c0 + 8, m0), whh_at(Whh, H, rank, c0 + 9, m0));
-                wf[a][k][3] = pack_bf16(whh_at(Whh, H, rank, c0 + 8, m1), whh_at(Whh, H, rank, c0 + 9, m1));
+                wf[a][k][0] = pack_bf16(whh_at<C>(Whh, H, rank, c0, m0), whh_at<C>(Whh, H, rank, c0 + 1, m0));
+                wf[a][k][1] = pack_bf16(whh_at<C>(Whh, H, rank, c0, m1), whh_at<C>(Whh, H, rank, c0 + 1, m1));
+                wf[a][k][2] = pack_bf16(whh_at<C>(Whh, H, rank, c0 + 8, m0), whh_at<C>(Whh, H, rank, c0 + 9, m0));
+                wf[a][k][3] = pack_bf16(whh_at<C>(Whh, H, rank, c0 + 8, m1), whh_at<C>(Whh, H, rank, c0 + 9, m1));
             }
         }
     }
@@ -426,7 +437,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     };
     load_saved(tmax - 1);
     load_saved(tmax - 2);
-    const uint32_t tx_bytes = (uint32_t)(CL * NB * SLOT * 8 * 4);          // 16 sources x (34 slots x 8 sequences) fp32 per tile
+    const uint32_t tx_bytes = (uint32_t)(C::CL * NB * C::SLOT * 8 * 4);          // 16 sources x (34 slots x 8 sequences) fp32 per tile
     // diagnostic phase timers of thread 0: [0] wait for dh, [1] cp.async wait, [2] gate gradients, [3] barrier, [4] mat-vec + push
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
     auto lap = [&](int i) { if (TRACE && tid == 0) { const long long now = clock64(); tacc[i] += now - tlast; tlast = now; } };
@@ -447,9 +458,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                 const float* v = sv + (size_t)(s % 3) * 7 * NIT + it;
                 float dh = v[6 * NIT];
                 if (step > 0) {
-                    const float* rc = recv + (((size_t)prev * CL * NB + (n >> 3)) * SLOT + j) * 8 + (n & 7);
+                    const float* rc = recv + (((size_t)prev * C::CL * NB + (n >> 3)) * C::SLOT + j) * 8 + (n & 7);
 #pragma unroll
-                    for (int src = 0; src < CL; ++src) dh += rc[(size_t)src * NB * SLOT * 8];
+                    for (int src = 0; src < C::CL; ++src) dh += rc[(size_t)src * NB * C::SLOT * 8];
                 }
                 const float gi = v[0], gf = v[NIT], gg = v[2 * NIT], go = v[3 * NIT];
                 const float c_prev = s > 0 ? v[5 * NIT] : 0.0f;
@@ -507,7 +518,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                 }
                 if (p.bulk) {
                     // C fragment (rows lane/4 and +8, sequences 2 (lane%4) + {0,1}) -> local staging tile [slot][8] fp32
-                    float* ps = pstage2 + ((size_t)(cur * NB + nb) * KP) * 8;
+                    float* ps = pstage2 + ((size_t)(cur * NB + nb) * C::KP) * 8;
 #pragma unroll
                     for (int a = 0; a < MTW; ++a) {
                         float* o = ps + (size_t)((warp * MTW + a) * 16 + (lane >> 2)) * 8 + 2 * (lane & 3);
@@ -527,8 +538,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
                         else v = make_float4(r0, r1, acc[a][2], acc[a][3]);             // row lane/4 + 8
                         const int slot = (warp * MTW + a) * 16 + (lane >> 2) + (odd ? 8 : 0);
                         const int n0 = 4 * ((lane & 3) >> 1);                            // lanes 0,1 -> sequences 0..3; lanes 2,3 -> 4..7
-                        const int owner = slot / SLOT, js = slot % SLOT;
-                        const uint32_t dst = smem_u32(recv + ((((size_t)cur * CL + rank) * NB + nb) * SLOT + js) * 8 + n0);
+                        const int owner = slot / C::SLOT, js = slot % C::SLOT;
+                        const uint32_t dst = smem_u32(recv + ((((size_t)cur * C::CL + rank) * NB + nb) * C::SLOT + js) * 8 + n0);
                         st_async_v4(mapa(dst, owner), mapa(smem_u32(&bars[cur]), owner), *reinterpret_cast<uint4*>(&v));
                     }
                 }
@@ -537,11 +548,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
         if (p.bulk) {       // the staged partial sums go to their owners: ONE bulk copy of 34 slots x 32 bytes per (tile, owner)
             fence_proxy_async();
             __syncthreads();
-            if (tid < CL * NB) {
-                const int owner = tid % CL, nb = tid / CL;
-                const uint32_t src = smem_u32(pstage2 + ((size_t)(cur * NB + nb) * KP + owner * SLOT) * 8);
-                const uint32_t dst = smem_u32(recv + (((size_t)cur * CL + rank) * NB + nb) * SLOT * 8);
-                bulk_copy_to_peer(mapa(dst, owner), src, SLOT * 32, mapa(smem_u32(&bars[cur]), owner));
+            if (tid < C::CL * NB) {
+                const int owner = tid % C::CL, nb = tid / C::CL;
+                const uint32_t src = smem_u32(pstage2 + ((size_t)(cur * NB + nb) * C::KP + owner * C::SLOT) * 8);
+                const uint32_t dst = smem_u32(recv + (((size_t)cur * C::CL + rank) * NB + nb) * C::SLOT * 8);
+                bulk_copy_to_peer(mapa(dst, owner), src, C::SLOT * 32, mapa(smem_u32(&bars[cur]), owner));
             }
         }
         write_saved();
@@ -550,7 +561,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
     }
     cp_async_wait_all();
     cluster_sync_all();
-    if (TRACE && p.trace != nullptr && tid == 0 && blockIdx.x < 2 * CL)          // the trace buffer holds the first two clusters
+    if (TRACE && p.trace != nullptr && tid == 0 && blockIdx.x < 2 * C::CL)          // the trace buffer holds the first two clusters
         for (int i = 0; i < 6; ++i) p.trace[blockIdx.x * 8 + i] = (unsigned long long)tacc[i];
 }
 
@@ -561,48 +572,59 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) lstm_cl_bwd_
 static unsigned long long* g_lstm_trace = nullptr;
 void lstm_cluster_set_trace(void* buf) { g_lstm_trace = reinterpret_cast<unsigned long long*>(buf); }
 
-bool lstm_cluster_supported(int B, int H) { return H >= 1 && H <= HMAX && B >= 1 && B <= 256; }
+bool lstm_cluster_supported(int B, int H) { return H >= 1 && H <= L16::HMAX && B >= 1 && B <= 256; }
 
+// RADMMM_B200_LSTM_CL4=0 keeps every hidden size on the 16-CTA geometry (A/B measurements)
+static bool use_small_geometry(int H) {
+    static const bool allow = []() { const char* e = getenv("RADMMM_B200_LSTM_CL4"); return !(e && e[0] == '0'); }();
+    return allow && H <= L4::HMAX;
+}
+
+template <class C>
 static size_t fwd_smem(int NB) {
     const size_t nit = (size_t)UPC * 8 * NB;
-    return 256 + (size_t)2 * NB * KP * 16 + (size_t)2 * ROWS * 8 * NB * 4 + (size_t)2 * NB * SLOT * 16 + nit * 4 + 3 * 4 * nit * 4 + nit * 16 + 6 * nit * 4;
+    return 256 + (size_t)2 * NB * C::KP * 16 + (size_t)2 * ROWS * 8 * NB * 4 + (size_t)2 * NB * C::SLOT * 16 + nit * 4 + 3 * 4 * nit * 4 + nit * 16 + 6 * nit * 4;
 }
+template <class C>
 static size_t bwd_smem(int NB) {
     const size_t nit = (size_t)UPC * 8 * NB;
-    return 256 + (size_t)2 * CL * NB * SLOT * 8 * 4 + (size_t)NB * ROWS * 16 + nit * 4 + 3 * 7 * nit * 4 + nit * 16 + 4 * nit * 4 +
-           (size_t)2 * NB * KP * 8 * 4;
+    return 256 + (size_t)2 * C::CL * NB * C::SLOT * 8 * 4 + (size_t)NB * ROWS * 16 + nit * 4 + 3 * 7 * nit * 4 + nit * 16 + 4 * nit * 4 +
+           (size_t)2 * NB * C::KP * 8 * 4;
 }
 
-template <bool FWD, bool TRACE>
-static int launch_cluster_t(const ClParams& p, size_t smem, cudaStream_t st) {
-    static size_t smem_set[64] = {};          // function attributes are per device
+template <bool FWD, bool TRACE, class C>
+static int launch_cluster_t(const ClParams& p, cudaStream_t st) {
+    static size_t smem_set[64] = {};          // function attributes are per device (and per instantiation)
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    auto kern = FWD ? lstm_cl_fwd_kernel<TRACE> : lstm_cl_bwd_kernel<TRACE>;
+    const size_t smem = FWD ? fwd_smem<C>(p.NB) : bwd_smem<C>(p.NB);
+    auto kern = FWD ? lstm_cl_fwd_kernel<TRACE, C> : lstm_cl_bwd_kernel<TRACE, C>;
     if (smem > smem_set[dev]) {
-        RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        if (C::CL > 8) RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         RADMMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[dev] = smem;
     }
-    kern<<<2 * CL * p.n_chunks, NT, smem, st>>>(p);       // clusters of 16: (chunk, direction); independent of each other
+    kern<<<2 * C::CL * p.n_chunks, NT, smem, st>>>(p);       // one cluster per (chunk, direction); independent of each other
     RADMMM_LAUNCH_CHECK();
     return RADMMM_OK;
 }
 
 template <bool FWD>
-static int launch_cluster(const ClParams& p_in, size_t smem, cudaStream_t st) {
+static int launch_cluster(const ClParams& p_in, cudaStream_t st) {
     // exchange flavour (measured on B200 at B=8, T'=400, profiles/): forward 2.50 us/step with one bulk DSMEM copy per peer
     // vs 2.84 with 16-byte st.async pushes; backward 2.94 vs 2.63 (its payload comes straight from the accumulator registers,
     // the bulk copy needs a staging round trip through shared memory).  RADMMM_B200_LSTM_BULK=0/1 forces one for both.
     static const int forced = []() { const char* e = getenv("RADMMM_B200_LSTM_BULK"); return e ? (e[0] != '0' ? 1 : 0) : -1; }();
     ClParams p = p_in;
     p.bulk = forced >= 0 ? forced : (FWD ? 1 : 0);
-    return p.trace != nullptr ? launch_cluster_t<FWD, true>(p, smem, st) : launch_cluster_t<FWD, false>(p, smem, st);
+    if (use_small_geometry(p.H))
+        return p.trace != nullptr ? launch_cluster_t<FWD, true, L4>(p, st) : launch_cluster_t<FWD, false, L4>(p, st);
+    return p.trace != nullptr ? launch_cluster_t<FWD, true, L16>(p, st) : launch_cluster_t<FWD, false, L16>(p, st);
 }
 
 static int fill(ClParams& p, const int* lens, int B, int Tp, int H) {
-    RADMMM_REQUIRE(lstm_cluster_supported(B, H), "lstm_cluster: B=%d (<= 256) / H=%d (<= %d) out of range", B, H, HMAX);
+    RADMMM_REQUIRE(lstm_cluster_supported(B, H), "lstm_cluster: B=%d (<= 256) / H=%d (<= %d) out of range", B, H, L16::HMAX);
     memset(&p, 0, sizeof(p));
     // one cluster per (8 sequences, direction): a step costs the same for every batch size as long as the clusters are
     // co-resident (148 SMs hold 9 clusters of 16 CTAs, i.e. 32 sequences run in one wave, 64 in two)
@@ -618,7 +640,7 @@ int lstm_cluster_forward(const float* xproj, const float* whh_f, const float* wh
     ClParams p;
     RADMMM_TRY(fill(p, lens, B, Tp, H));
     p.xproj = xproj; p.whh[0] = whh_f; p.whh[1] = whh_r; p.out = out; p.gates = gates; p.cstate = cstate;
-    return launch_cluster<true>(p, fwd_smem(p.NB), st);
+    return launch_cluster<true>(p, st);
 }
 
 int lstm_cluster_backward(const float* dout, const float* gates, const float* cstate, const float* whh_f, const float* whh_r,
@@ -627,7 +649,7 @@ int lstm_cluster_backward(const float* dout, const float* gates, const float* cs
     RADMMM_TRY(fill(p, lens, B, Tp, H));
     p.dout = dout; p.gates = const_cast<float*>(gates); p.cstate = const_cast<float*>(cstate);
     p.whh[0] = whh_f; p.whh[1] = whh_r; p.dgates = dgates;
-    return launch_cluster<false>(p, bwd_smem(p.NB), st);
+    return launch_cluster<false>(p, st);
 }
 
 }  // namespace radmmm

@@ -210,7 +210,11 @@ _LSTM_CASES = [(3, [37, 20, 5], 20, 16), (2, [9, 9], 20, 16), (11, [40, 33, 31, 
                # of the cluster partly / completely empty (RADTTS variant: 524)
                (8, [24, 24, 21, 17, 12, 9, 4, 1], 40, 528), (3, [11, 7, 2], 24, 524),
                # more than one 8-sequence tile per launch, more than one launch (chunks of 32 / 64 sequences)
-               (19, [13 - (i % 13) for i in range(19)], 20, 40), (70, [1 + (7 * i) % 12 for i in range(70)], 12, 16)]
+               (19, [13 - (i % 13) for i in range(19)], 20, 40), (70, [1 + (7 * i) % 12 for i in range(70)], 12, 16),
+               # hidden <= 132 runs on clusters of 4 CTAs in bf16 mode (the attribute predictors' hidden 128; 132 fills all
+               # four CTAs; 100 leaves the last one a third full); 133 is the first size back on clusters of 16
+               (8, [30, 30, 26, 19, 12, 8, 3, 1], 24, 128), (5, [17, 9, 9, 4, 2], 20, 132), (11, [21 - 2 * i for i in range(11)], 20, 100),
+               (3, [12, 7, 5], 20, 133)]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
