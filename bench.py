@@ -569,14 +569,14 @@ def joint_training_bench(dev, dec, resident, reducer, world, timed, valid_frames
         parts = []
         for i, k in enumerate(("f0", "energy", "voiced")):
             streams[i].wait_stream(cur)
-            with torch.cuda.stream(streams[i]):
+            with torch.cuda.stream(streams[i]), torch.autocast("cuda", dtype=torch.bfloat16):
                 r = aux[k](tgt[k], st["context"], spk, st["out_lens"])
-                parts.append(masked_mse(r["x_hat"], r["x"], st["out_lens"]))
+                parts.append(masked_mse(r["x_hat"].float(), r["x"], st["out_lens"]))
         streams[3].wait_stream(cur)
-        with torch.cuda.stream(streams[3]):
-            text_enc = aux["encoder"](txt_emb, in_lens).transpose(1, 2)
+        with torch.cuda.stream(streams[3]), torch.autocast("cuda", dtype=torch.bfloat16):
+            text_enc = aux["encoder"](txt_emb, in_lens).transpose(1, 2)          # the encoder itself opts out of autocast, as the reference's does
             r = aux["duration"](dur_tgt, text_enc, spk, in_lens)
-            parts.append(masked_mse(r["x_hat"], r["x"], in_lens))
+            parts.append(masked_mse(r["x_hat"].float(), r["x"], in_lens))
 
         def join():
             for s_ in streams:
@@ -589,11 +589,33 @@ def joint_training_bench(dev, dec, resident, reducer, world, timed, valid_frames
     for _ in range(3):
         g(resident)
     ms = timed(lambda: g(resident), max(5, args.steps // 2))
+    if os.environ.get("RADMMM_BENCH_JOINT_TRACE"):           # diagnostic: where the joint step's time goes (per stream, LSTM kernels)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            g(resident)
+            torch.cuda.synchronize()
+        path = os.environ["RADMMM_BENCH_JOINT_TRACE"]
+        prof.export_chrome_trace(path)
+        ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+        t0 = min(e["ts"] for e in ev)
+        busy = {}
+        for e in ev:
+            busy.setdefault(e["args"].get("stream"), [0.0, 1e18, 0.0])
+            b_ = busy[e["args"].get("stream")]
+            b_[0] += e["dur"]; b_[1] = min(b_[1], e["ts"] - t0); b_[2] = max(b_[2], e["ts"] + e["dur"] - t0)
+        sys.stderr.write("joint trace: span %.0f us\n" % (max(e["ts"] + e["dur"] for e in ev) - t0))
+        for k_, b_ in sorted(busy.items(), key=lambda kv: -kv[1][0])[:12]:
+            sys.stderr.write("  stream %s busy %.0f us, first %.0f last %.0f\n" % (k_, b_[0], b_[1], b_[2]))
+        for e in ev:
+            if "lstm_cl" in e["name"] or e["dur"] > 300:
+                sys.stderr.write("  %8.0f +%7.0f  s%s %s\n" % (e["ts"] - t0, e["dur"], e["args"].get("stream"), e["name"][:70]))
+        os.remove(path)
     n_aux = sum(p.numel() for p in aux.parameters())
     out = {"ms_per_step": ms, "value": world * valid_frames / (ms * 1e-3), "unit": UNIT, "aux_parameters": n_aux,
            "aux_grad_nonzero": bool(sum(float(p.grad.abs().sum()) for p in aux.parameters() if p.grad is not None) > 0),
            "note": "decoder train step + text encoder (3 conv + bi-LSTM) + f0 / energy / voiced / duration predictors "
-                   f"(radmmm_b200.encoders, {n_tok} tokens), one backward, one CUDA graph"
+                   f"(radmmm_b200.encoders, {n_tok} tokens; predictor convolutions under bf16 autocast like the decoder's contractions, "
+                   "bi-LSTMs on the cluster kernels), one backward, one CUDA graph"
                    + ("; encoder / predictor gradients all-reduced in a 10th bucket" if world > 1 else "")}
     del g
     torch.cuda.empty_cache()

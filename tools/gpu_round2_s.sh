@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round 2, GPU call S: final validation -- full gpu suite, smoke, default bench
+mkdir -p gpurun_out
+echo "=== pytest gpu (all)"; timeout 1500 python -m pytest tests -q -p no:cacheprovider --timeout=900 -m gpu > gpurun_out/r2s_pytest.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/r2s_pytest.log; grep -n "AssertionError\|^FAILED\|Error" gpurun_out/r2s_pytest.log | head -8
+echo "=== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "=== bench"; /usr/bin/time -v timeout 1500 python bench.py > gpurun_out/r2s_bench.json 2> gpurun_out/r2s_bench.err; echo "exit $?"; grep "Elapsed (wall" gpurun_out/r2s_bench.err
+python - <<'PY'
+import json
+d = json.load(open('gpurun_out/r2s_bench.json'))
+print('train ms', d['ms_per_step'], 'frames/s', d['value'], 'e2e ms', d['e2e']['ms_per_step'], 'infer ms', d['infer']['ms_per_call'], 'eager', d['eager']['ms_per_step'], 'frac', d['roofline']['frac'], d['step_tensor_roofline']['frac'])
+print('joint', d['joint_training']['ms_per_step'], 'opt', d['optimizer']['optimizer_ms'], d['optimizer']['full_step']['ms_per_step'], 'x3', d['parity_mode']['ms_per_step'], 'cpu', d['cpu_baseline']['value'])
+PY
+echo "=== ref arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-220
