@@ -104,6 +104,11 @@ inline int zero_wgrad_output(const GemmArgs& a, cudaStream_t st) {
 struct Stager {
     __nv_bfloat16* buf;   // [32 rows][kStageLd] per warp, or nullptr
     int lane;
+    // TMA store of bf16 output tiles (tensor-core path, kinds whose only act-matrix output is `out0`): tensor maps of the
+    // matrix `tma_base` (hi plane / lo plane of the split mode) with 32 x 32 boxes and the 64-byte swizzle; nullptr = off
+    const void* tmap = nullptr;
+    const void* tmap_lo = nullptr;
+    const void* tma_base = nullptr;
 };
 constexpr int kStageLd = 40;   // 32 bf16 + 8 pad (80 B rows: conflict-light 16-byte accesses)
 
@@ -112,6 +117,42 @@ __device__ __forceinline__ void staged_store32(const Stager& st, const ActMat& m
     // r = row of THIS thread (row_base + lane); all 32 lanes call together
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(m.ptr);
     const int row_base = r - st.lane;
+    if (st.tmap != nullptr && m.ptr == st.tma_base) {
+        // One TMA store (cp.async.bulk.tensor, UTMASTG) per 32 x 32 tile instead of four 16-byte st.global per lane: every
+        // lane writes its row (64 bytes) into the staging tile in the 64-byte-swizzle order the tensor map expects -- 16-byte
+        // chunk c of row r sits at chunk c ^ ((r >> 1) & 3), which also makes the 32 concurrent 16-byte shared stores
+        // conflict-free -- and lane 0 hands the tile to the copy engine.  The tile is reused by the next chunk, so the
+        // previous store must have finished READING it first (wait_group.read).
+        uint8_t* tile = reinterpret_cast<uint8_t*>(st.buf);
+        const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
+        const int sw = (st.lane >> 1) & 3;
+#pragma unroll
+        for (int plane = 0; plane < (MODE == MODE_BF16X3 ? 2 : 1); ++plane) {
+            __nv_bfloat162 h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a = v[2 * j], b = v[2 * j + 1];
+                if (plane == 1) {
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+                    a -= __bfloat162float(hi.x); b -= __bfloat162float(hi.y);
+                }
+                h[j] = __floats2bfloat162_rn(a, b);
+            }
+            if (st.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(tile + st.lane * 64 + ((j ^ sw) << 4)) = reinterpret_cast<uint4*>(h)[j];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (st.lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(plane == 0 ? st.tmap : st.tmap_lo), "r"(n0), "r"(row_base), "r"(tile_addr) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int plane = 0; plane < (MODE == MODE_BF16X3 ? 2 : 1); ++plane) {
         __nv_bfloat162 h[16];

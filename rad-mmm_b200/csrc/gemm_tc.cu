@@ -44,6 +44,8 @@ struct TcParams {
     int m_tiles, n_tiles, taps, split_k, k_blocks_total;   // weight-grad: k_blocks_total = R/64
     int acc_segs;                                          // weight-grad: all segments accumulate into one output
     int balanced;                                          // weight-grad: K blocks of all tiles cut into equal runs per CTA (pair)
+    CUtensorMap out_map[2];                                // TMA store of epi.out0 (hi / lo plane): 32 x 32 bf16 boxes, 64-byte swizzle
+    int out_tma;                                           // 1: the epilogue writes epi.out0 with cp.async.bulk.tensor stores
     int debug;                                             // probe bits (tools/gemm_probe.py): 1 no epilogue, 2 no MMA, 4 no TMA
     unsigned long long* trace;                             // tools/gemm_probe.py: [CTA][kTraceSlots] SM-clock / globaltimer stamps
     int trace_ctas;
@@ -219,7 +221,7 @@ struct Cfg {
     static constexpr int stages = (RADMMM_TC_SMEM_KB * 1024) / stage_bytes > 8 ? 8 : (RADMMM_TC_SMEM_KB * 1024) / stage_bytes;
     static constexpr int tmem_cols = 2 * BN;      // 256 or 512: powers of two
     static constexpr int stage_tile_bytes = 32 * kStageLd * 2;     // epilogue staging tile, per epilogue warp
-    static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * stage_tile_bytes;
+    static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers; keeps the staging tiles 512-byte aligned*/ + kEpiWarps * stage_tile_bytes;
 };
 
 // CL == 1: one CTA per 128 x BN tile, tcgen05.mma.cta_group::1.
@@ -247,7 +249,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
     uint64_t* tfull = bars + 2 * C::stages;      // [2]
     uint64_t* tempty = bars + 2 * C::stages + 2; // [2]       (CL == 2: only the leader's are waited on)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::stages + 4);
-    __nv_bfloat16* stage_tiles = reinterpret_cast<__nv_bfloat16*>(smem + C::stages * C::stage_bytes + 256);
+    __nv_bfloat16* stage_tiles = reinterpret_cast<__nv_bfloat16*>(smem + C::stages * C::stage_bytes + 512);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -473,7 +475,8 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
         const int q = (warp - 4) & 3;                // TMEM lane quarter of this warp (== warp % 4)
         const int half = (warp - 4) >> 2;            // which column half of the tile this warp drains
         constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
-        const Stager stager{stage_tiles + (warp - 4) * (32 * kStageLd), lane};
+        const Stager stager{stage_tiles + (warp - 4) * (32 * kStageLd), lane, P.out_tma ? &P.out_map[0] : nullptr,
+                            P.out_tma ? &P.out_map[1] : nullptr, P.out_tma ? P.epi.out0.ptr : nullptr};
         int it = 0;
         int m_blk, n_blk, tap, ikb0 = 0, ikb1 = 0;
         for (int pos = item_first(); item_valid(pos); pos = item_next(pos, ikb0, ikb1), ++it) {
@@ -529,6 +532,7 @@ __global__ void RADMMM_TC_BOUNDS gemm_tc_kernel(const __grid_constant__ TcParams
         }
     }
 
+    if (warp >= 4 && lane == 0 && P.out_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are done
     tc_fence_before();
     __syncthreads();
     if (CL == 2) cluster_sync_all();          // no CTA may exit while its peer can still arrive on its barriers / read its smem
@@ -561,6 +565,21 @@ static EncodeFn get_encode() {
 }
 
 // bf16 matrix [outer][inner] with row pitch ld elements; box = 64 x box_rows, 128B swizzle, zero fill out of bounds
+// bf16 output matrix [outer][ld]: 32-column x 32-row boxes, 64-byte swizzle (the epilogue's TMA stores)
+static int make_store_map(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld) {
+    EncodeFn enc = get_encode();
+    RADMMM_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RADMMM_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled (store map) failed with code %d", (int)r);
+    return RADMMM_OK;
+}
+
 static int make_map(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
     EncodeFn enc = get_encode();
     RADMMM_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -904,6 +923,16 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     }
     P.n_a_maps = n_a;
     P.n_b_maps = n_b;
+    // TMA stores for the kinds whose only activation output is out0 (RADMMM_B200_TMA_STORE=0: per-lane 16-byte stores)
+    static const bool tma_store = []() { const char* e = getenv("RADMMM_B200_TMA_STORE"); return !(e && e[0] == '0'); }();
+    const int kind = args.epi.kind;
+    if (tma_store && !args.wgrad && (kind == EPI_START || kind == EPI_IN || kind == EPI_RS || kind == EPI_DH0) &&
+        args.epi.out0.ptr != nullptr && (reinterpret_cast<uintptr_t>(args.epi.out0.ptr) & 15) == 0 && (args.epi.out0.ld * 2) % 16 == 0) {
+        const ActMat& o = args.epi.out0;
+        RADMMM_TRY(make_store_map(&P.out_map[0], o.ptr, o.ld, args.R, o.ld));
+        if (x3) RADMMM_TRY(make_store_map(&P.out_map[1], (const __nv_bfloat16*)o.ptr + o.plane_stride, o.ld, args.R, o.ld));
+        P.out_tma = 1;
+    }
 
     const bool wg = args.wgrad != 0;
     if (use_cl) {
