@@ -201,6 +201,10 @@ __device__ __forceinline__ void staged_fetch32(const Stager& st, const ActMat& m
 
 template <int MODE>
 __device__ __forceinline__ void staged_unpack32(const Stager& st, const RawTile<MODE>& raw, float* v) {
+    if (st.tmap != nullptr) {      // the staging tile may still be the source of the previous chunk's TMA store
+        if (st.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
 #pragma unroll
     for (int plane = 0; plane < (MODE == MODE_BF16X3 ? 2 : 1); ++plane) {
 #pragma unroll

@@ -926,7 +926,7 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
     // TMA stores for the kinds whose only activation output is out0 (RADMMM_B200_TMA_STORE=0: per-lane 16-byte stores)
     static const bool tma_store = []() { const char* e = getenv("RADMMM_B200_TMA_STORE"); return !(e && e[0] == '0'); }();
     const int kind = args.epi.kind;
-    if (tma_store && !args.wgrad && (kind == EPI_START || kind == EPI_IN || kind == EPI_RS || kind == EPI_DH0) &&
+    if (tma_store && !args.wgrad && (kind == EPI_START || kind == EPI_IN || kind == EPI_RS || kind == EPI_DH0 || kind == EPI_DH) &&
         args.epi.out0.ptr != nullptr && (reinterpret_cast<uintptr_t>(args.epi.out0.ptr) & 15) == 0 && (args.epi.out0.ld * 2) % 16 == 0) {
         const ActMat& o = args.epi.out0;
         RADMMM_TRY(make_store_map(&P.out_map[0], o.ptr, o.ld, args.R, o.ld));
