@@ -37,7 +37,7 @@ TRAIN_MFLOP_PER_FRAME = 656.4    # 3 x forward (fwd + dgrad + wgrad; recompute n
 K5_FLOP_PER_GROUPED_FRAME = 2 * 1024 * 1024 * 5      # one dilated k=5 layer (the dominant kernel), per grouped frame
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at B=8 x T=800, bf16, from the
 # committed `ncu --set full` capture named below (re-measured whenever the kernel changes)
-K5_DRAM_BYTES_NCU = {"bytes": 17335552, "source": "profiles/r2_ncu_full_k5.md"}
+K5_DRAM_BYTES_NCU = {"bytes": 17337088, "source": "profiles/r2_ncu_full_k5_final.md"}
 MODEL_ARGS = dict(n_speaker_dim=16, use_accent=True, n_accent_dim=8, n_text_dim=520, n_group_size=2, n_mel_channels=80,
                   n_flows=8)
 
