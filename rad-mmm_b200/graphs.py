@@ -110,9 +110,47 @@ class GraphedTrainStep:
             self.after_backward()
         return loss.detach()
 
-    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """Copy ``batch`` (host or device tensors of the captured shapes) into the static buffers and replay.  Returns the
-        static loss tensor (device; valid until the next call)."""
+    def prefetch(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Start moving the NEXT batch (pinned host tensors of the captured shapes) to the device on a copy stream, into staging
+        buffers; the following ``step()`` (no argument) consumes it.  Called right after a replay has been enqueued, the
+        transfer overlaps that replay -- what a data loader with ``pin_memory`` + ``non_blocking`` copies does for the eager
+        loop.  The H2D copy of a batch costs 0.36 ms at B=8 x T=800 (15 MB over PCIe); without this it sits in front of
+        every replay."""
+        dev = self.static["mel"].device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._staged_ready = torch.cuda.Event()
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream(dev))
+            self._has_staged = False
+        cs = self._copy_stream
+        cs.wait_event(self._staging_free)              # the previous step's copy out of the staging buffers is done
+        with torch.cuda.stream(cs):
+            for k, dst in self._staging.items():
+                src = batch[k]
+                if src.shape != dst.shape:
+                    raise RuntimeError(f"GraphedTrainStep.prefetch: '{k}' has shape {tuple(src.shape)}, the graph was captured "
+                                       f"for {tuple(dst.shape)} (pad the batch to the captured shape)")
+                dst.copy_(src, non_blocking=True)
+            self._staged_ready.record(cs)
+        self._has_staged = True
+
+    def __call__(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        """Copy ``batch`` (host or device tensors of the captured shapes) into the static buffers and replay; with no argument,
+        consume the batch a previous ``prefetch`` staged.  Returns the static loss tensor (device; valid until the next
+        call)."""
+        if batch is None:
+            if not getattr(self, "_has_staged", False):
+                raise RuntimeError("GraphedTrainStep(): no batch given and none prefetched")
+            cur = torch.cuda.current_stream(self.static["mel"].device)
+            cur.wait_event(self._staged_ready)
+            for k, dst in self.static.items():
+                dst.copy_(self._staging[k], non_blocking=True)     # device-to-device, a few microseconds
+            self._staging_free.record(cur)
+            self._has_staged = False
+            self.graph.replay()
+            return self.loss
         for k, dst in self.static.items():
             src = batch[k]
             if src.shape != dst.shape:

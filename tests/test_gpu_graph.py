@@ -128,3 +128,29 @@ def test_reducer_collective_waits_for_every_finalising_stream():
     assert float(seen[:lin.weight.numel()].min()) == 3.0, "the bucket was read before the weight gradient had landed"
     assert float(seen[b["offsets"][1]:b["offsets"][1] + lin.bias.numel()].min()) == 5.0
     red.finish()
+
+
+def test_graphed_step_prefetch_pipeline():
+    """GraphedTrainStep.prefetch + step(): batches staged from PINNED HOST memory on the copy stream while the previous replay
+    runs; every replay must see exactly the batch prefetched for it (losses equal the direct path, in order), and calling
+    step() with nothing staged is an error."""
+    from radmmm_b200.graphs import GraphedTrainStep
+    batch, frames = 3, 96
+    dec = _decoder("fp32")
+    host = [{k: v.pin_memory() for k, v in syn.synthetic_batch(batch, frames, tag=f"prefetch.{i}").items()} for i in range(3)]
+    _eager(dec, {k: v.to(DEV) for k, v in host[0].items()}, frames)
+    step = GraphedTrainStep(dec, host[0])
+    direct = []
+    for h in host:
+        direct.append(float(step(h).cpu()))
+    assert len({round(x, 6) for x in direct}) == 3
+    with pytest.raises(RuntimeError):
+        step()
+    step.prefetch(host[0])
+    piped = []
+    for i in range(6):                                 # replay i consumes batch i % 3 while batch (i + 1) % 3 is in flight
+        loss = step()
+        step.prefetch(host[(i + 1) % 3])
+        piped.append(float(loss.cpu()))
+    for i, v in enumerate(piped):
+        assert abs(v - direct[i % 3]) <= 1e-6 * max(1.0, abs(direct[i % 3])), (piped, direct)
