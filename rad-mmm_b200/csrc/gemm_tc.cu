@@ -737,8 +737,8 @@ int launch_gemm_tc(const GemmArgs& args, int mode, cudaStream_t stream) {
         // attractive for their tile count, but a 256 x 128 pair tile streams 24 KB of MN-major operands per 64-row K block
         // for 256 tensor cycles -- 96 B/clk per SM, ~14 KB/clk over the chip, more than twice what L2 delivers: measured
         // 0.46 us per K block instead of 0.13 (profiles/r2_gemm_timeline.md).  256-wide tiles stream 32 KB per 512 cycles,
-        // the same 64 B/clk per SM as the forward convolutions, which run at the tensor peak; their 80 pair tiles are split
-        // in two along K below (160 work items for 74 pair slots, fp32 red.add into the zeroed output).
+        // the same 64 B/clk per SM as the forward convolutions, which run at the tensor peak; their 80 pair tiles run whole
+        // (no split along K, plain stores -- see the reduction-strategy note further down).
         // RADMMM_B200_WGRAD_BN128=1 restores the old choice (A/B measurements).
         static const bool bn128 = []() { const char* e = getenv("RADMMM_B200_WGRAD_BN128"); return e && e[0] == '1'; }();
         const int taps = args.wgrad == 2 ? 1 : args.n_seg;
