@@ -8,6 +8,9 @@ gradients.
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 
 from . import _native as N
@@ -66,6 +69,21 @@ def _cast(mode: int, x: torch.Tensor):
     return buf
 
 
+_tail_streams = {}
+
+
+def _tail_stream(device):
+    """Side stream for the independent tail of the LSTM backward (RADMMM_B200_LSTM_TAIL_STREAM=0: everything on one stream)."""
+    if os.environ.get("RADMMM_B200_LSTM_TAIL_STREAM", "1") == "0":
+        return None
+    # one side stream per CALLING stream: independent LSTMs running on different streams (the attribute predictors of the joint
+    # step) must not meet on a shared one
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    if key not in _tail_streams:
+        _tail_streams[key] = torch.cuda.Stream(device=device)
+    return _tail_streams[key]
+
+
 class ContextLSTMFunction(torch.autograd.Function):
     """x (B, T, In) fp32, grouped lengths (B) int32 -> (B, T, 2H); zero beyond each length."""
 
@@ -122,24 +140,38 @@ class ContextLSTMFunction(torch.autograd.Function):
                                          inp, r, k8, inp, 1, 1, N.stream()))
             dx = torch.empty(b, t, n_in, device=dev)
             N.check(lib.radmmm_context_rows_backward(N.fptr(dx_rows), N.ptr(lens), b, t, n_in, N.fptr(dx), 0, N.stream()))
+        # The three weight-gradient contractions and the bias reduction are independent and sit on the exposed tail of the
+        # training step (nothing else is left to run): dW_hh and the bias sums go to a side stream next to dW_ih.
+        main = torch.cuda.current_stream(dev)
+        side = _tail_stream(dev)
+        hp = N.round_up(2 * hid, 128)
+        es = 4 if mode == N.MODE_F32 else 2
+        npad = N.round_up(hid, 128)
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            # dW_hh[dir] = dG_dir^T H_prev_dir: the previous state of the forward direction is row r-1, of the reverse
+            # direction row r+1 (rows beyond a sequence are zero, which is exactly h_{-1} = 0)
+            h_rows = _rows(mode, out, lens)
+            dwhh_f = torch.empty(4 * hid, npad, device=dev)
+            dwhh_r = torch.empty(4 * hid, npad, device=dev)
+            N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dg_act), k8, r * k8, N.ptr(h_rows), hp, r * hp, N.fptr(dwhh_f), npad,
+                                          4 * hid * npad, r, 4 * hid, hid, 1, 1, -1, N.stream()))
+            N.check(lib.radmmm_wgrad_rows(mode, dg_act.data_ptr() + 4 * hid * es, k8, r * k8, h_rows.data_ptr() + hid * es,
+                                          hp, r * hp, N.fptr(dwhh_r), npad, 4 * hid * npad, r, 4 * hid, hid, 1, 1, 1,
+                                          N.stream()))
+            db = dg.sum(0)
+            if side is not None:          # allocated on the side stream, consumed on the main one
+                for t_ in (dwhh_f, dwhh_r, db):
+                    t_.record_stream(main)
+                for t_ in (dg_act, dg, out, h_rows):      # and the other way round
+                    t_.record_stream(side)
         # dW_ih = dG^T X
         dwih = torch.empty(k8, inp, device=dev)
         N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dg_act), k8, r * k8, N.ptr(x_rows), inp, r * inp, N.fptr(dwih), inp,
                                       k8 * inp, r, k8, inp, 1, 1, 0, N.stream()))
-        # dW_hh[dir] = dG_dir^T H_prev_dir: the previous state of the forward direction is row r-1, of the reverse
-        # direction row r+1 (rows beyond a sequence are zero, which is exactly h_{-1} = 0)
-        h_rows = _rows(mode, out, lens)
-        hp = N.round_up(2 * hid, 128)
-        es = 4 if mode == N.MODE_F32 else 2
-        npad = N.round_up(hid, 128)
-        dwhh_f = torch.empty(4 * hid, npad, device=dev)
-        dwhh_r = torch.empty(4 * hid, npad, device=dev)
-        N.check(lib.radmmm_wgrad_rows(mode, N.ptr(dg_act), k8, r * k8, N.ptr(h_rows), hp, r * hp, N.fptr(dwhh_f), npad,
-                                      4 * hid * npad, r, 4 * hid, hid, 1, 1, -1, N.stream()))
-        N.check(lib.radmmm_wgrad_rows(mode, dg_act.data_ptr() + 4 * hid * es, k8, r * k8, h_rows.data_ptr() + hid * es,
-                                      hp, r * hp, N.fptr(dwhh_r), npad, 4 * hid * npad, r, 4 * hid, hid, 1, 1, 1,
-                                      N.stream()))
-        db = dg.sum(0)
+        if side is not None:
+            main.wait_stream(side)
         dbf, dbr = db[:4 * hid].contiguous(), db[4 * hid:].contiguous()
         return (None, None, dx, None, dwih[:4 * hid, :n_in].contiguous(), dwhh_f[:, :hid].contiguous(), dbf, dbf.clone(),
                 dwih[4 * hid:, :n_in].contiguous(), dwhh_r[:, :hid].contiguous(), dbr, dbr.clone())
